@@ -1,0 +1,62 @@
+"""ctypes binding of the C-ABI CUDA library (include/dasv_b200.h).
+
+The product has NO CPU path: ``lib()`` raises if ``libdasv_b200.so`` has not been built, and every
+op wrapper in ``ops.py`` raises on non-CUDA tensors.
+"""
+import ctypes
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, 'libdasv_b200.so')
+
+_c = ctypes
+_vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/dasv_b200.h one to one
+SIGNATURES = {
+    'dasv_abi_version': (_i, []),
+    'dasv_last_error': (_c.c_char_p, []),
+    'dasv_dmha_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'dasv_dmha_bwd_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'dasv_dmha_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'dasv_attention_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'dasv_conv11_direct': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'dasv_pack_conv_weight_f32': (_i, [_vp, _vp, _i, _i, _vp]),
+    'dasv_packed_conv_weight_bf16_elems': (_sz, [_i, _i]),
+    'dasv_pack_conv_weight_bf16': (_i, [_vp, _vp, _i, _i, _vp]),
+    'dasv_conv3x3_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'dasv_maxpool2x2': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasv_conv3x3_igemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasv_fc_tail_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'dasv_cosine_pairs': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    'dasv_cosine_matrix_workspace_bytes': (_sz, [_i, _i]),
+    'dasv_cosine_matrix': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+}
+
+_LIB = None
+
+
+class DasvError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library.  Fails loudly when it is missing: there is no fallback implementation."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise DasvError('%s is missing: build it with `python -m doubleattentionspeakerverification_b200.build` '
+                            '(this package has no CPU or PyTorch fallback)' % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)      # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = h
+    return _LIB
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dasv_last_error()
+        raise DasvError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else '?'))

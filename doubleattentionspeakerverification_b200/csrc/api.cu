@@ -1,0 +1,31 @@
+// Error plumbing and version entry points of the C ABI (include/dasv_b200.h).
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace dasv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// Launch-configuration errors only (no host sync): asynchronous faults surface at the caller's
+// next synchronisation, exactly like a stock PyTorch op on the same stream.
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace dasv
+
+extern "C" int dasv_abi_version(void) { return 1; }
+extern "C" const char* dasv_last_error(void) { return dasv::g_err; }

@@ -1,0 +1,271 @@
+// CUDA-core pieces of the VGG front-end (scripts/CNNs.py:56-91):
+//   * conv11 (Cin = 1) direct convolution + bias + ReLU -- not a tensor-core shape (K = 9);
+//   * fp32 implicit-GEMM conv3x3 + bias + ReLU: the fp32-parity path (1e-4 relative);
+//   * 2x2 ceil-mode max-pool on NHWC, optionally writing the front-end's [B,T',C*F'] layout;
+//   * weight re-packing for both conv paths.
+// Activations are NHWC [B,T,F,C]; rows t >= lengths[b] are written as zero.
+#include "common.cuh"
+
+namespace dasv {
+
+// ------------------------------------------------------------------------------ conv11 direct
+// One CTA per (b, t) row.  Thread item = (f, 8-channel group); 9 taps x 8 channels of FMAs.
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const int32_t* __restrict__ lengths,
+                                                           void* __restrict__ y, int B, int T, int F, int Cout) {
+    extern __shared__ float sm[];
+    float* w_sm = sm;                     // [9][Cout]
+    float* b_sm = w_sm + 9 * Cout;        // [Cout]
+    float* x_sm = b_sm + Cout;            // [3][F+2]
+    const int bt = blockIdx.x;
+    const int b = bt / T, t = bt - b * T;
+    const int L = lengths ? min(max(lengths[b], 0), T) : T;
+    const int CG = Cout / 8;
+    const size_t row_elems = static_cast<size_t>(F) * Cout;
+    if (t >= L) {   // masked row: zeros
+        if (OUT_BF16) {
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + bt * row_elems);
+            for (int i = threadIdx.x; i < F * CG; i += blockDim.x) o[i] = make_uint4(0, 0, 0, 0);
+        } else {
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(y) + bt * row_elems);
+            for (int i = threadIdx.x; i < F * CG * 2; i += blockDim.x) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
+        const int tap = i / Cout, c = i - tap * Cout;
+        w_sm[i] = w[c * 9 + tap];         // reference layout [Cout,1,3,3]
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) b_sm[i] = bias[i];
+    for (int i = threadIdx.x; i < 3 * (F + 2); i += blockDim.x) {
+        const int r = i / (F + 2), fc = i - r * (F + 2);
+        const int tt = t + r - 1, ff = fc - 1;
+        float v = 0.f;
+        if (tt >= 0 && tt < L && ff >= 0 && ff < F) v = x[(static_cast<size_t>(b) * T + tt) * F + ff];
+        x_sm[i] = v;                      // rows >= L of the input are treated as zero (masking rule)
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < F * CG; i += blockDim.x) {
+        const int f = i / CG, cg = i - f * CG;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = b_sm[cg * 8 + e];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float xv = x_sm[dy * (F + 2) + f + dx];
+                const float* wr = w_sm + (dy * 3 + dx) * Cout + cg * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, wr[e], acc[e]);
+            }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+        if (OUT_BF16) {
+            uint4 v;
+            v.x = pack_bf16(acc[0], acc[1]); v.y = pack_bf16(acc[2], acc[3]);
+            v.z = pack_bf16(acc[4], acc[5]); v.w = pack_bf16(acc[6], acc[7]);
+            reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + bt * row_elems)[i] = v;
+        } else {
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(y) + bt * row_elems);
+            o[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            o[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ weight packing
+__global__ void pack_w_f32_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // output index [tap][ci][co]
+    if (i >= 9 * Cin * Cout) return;
+    const int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
+    p[i] = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap];
+}
+// [Cout_pad][9][Cin] bf16, rows co >= Cout are zero (Cout_pad = Cout rounded up to 128).
+__global__ void pack_w_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int Cout, int Cin, int Cout_pad) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // [co][tap][ci]
+    if (i >= static_cast<size_t>(Cout_pad) * 9 * Cin) return;
+    const int ci = i % Cin, tap = (i / Cin) % 9, co = i / (static_cast<size_t>(Cin) * 9);
+    const float v = co < Cout ? w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] : 0.f;
+    p[i] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------ fp32 implicit GEMM
+// C[pixel, co] = sum_{tap, ci} X[pixel shifted by tap, ci] * Wp[tap][ci][co]; 64x64 tile, 16-deep
+// K slices, 256 threads x (4x4) outputs.  Plain fp32 FMAs: this is the 1e-4 parity path.
+constexpr int kF32TM = 64, kF32TN = 64, kF32TK = 16;
+
+__global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                                         const float* __restrict__ bias, const int32_t* __restrict__ lengths,
+                                                         float* __restrict__ y, int B, int T, int F, int Cin, int Cout) {
+    __shared__ float As[kF32TK][kF32TM + 4];
+    __shared__ float Bs[kF32TK][kF32TN];
+    const long long npix = static_cast<long long>(B) * T * F;
+    const long long m0 = static_cast<long long>(blockIdx.x) * kF32TM;
+    const int n0 = blockIdx.y * kF32TN;
+    const int tid = threadIdx.x;
+    const int ty = tid / 16, tx = tid % 16;
+
+    // the pixel this thread loads for the A tile
+    const int lp = tid / 4, lc = (tid % 4) * 4;
+    const long long pix = m0 + lp;
+    int pb = 0, pt = 0, pf = 0, pL = 0;
+    const bool pix_ok = pix < npix;
+    if (pix_ok) {
+        pb = static_cast<int>(pix / (static_cast<long long>(T) * F));
+        const int r = static_cast<int>(pix - static_cast<long long>(pb) * T * F);
+        pt = r / F; pf = r - pt * F;
+        pL = lengths ? min(max(lengths[pb], 0), T) : T;
+    }
+    const int bk = tid / 16, bn = (tid % 16) * 4;     // B tile element this thread loads
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int tt = pt + dy, ff = pf + dx;
+        const bool src_ok = pix_ok && tt >= 0 && tt < pL && ff >= 0 && ff < F;
+        const float* src = x + ((static_cast<size_t>(pb) * T + tt) * F + ff) * Cin;
+        for (int c0 = 0; c0 < Cin; c0 += kF32TK) {
+            float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src_ok && c0 + lc < Cin) av = *reinterpret_cast<const float4*>(src + c0 + lc);
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + bk < Cin && n0 + bn < Cout)
+                bv = *reinterpret_cast<const float4*>(wp + (static_cast<size_t>(tap) * Cin + c0 + bk) * Cout + n0 + bn);
+            __syncthreads();
+            As[lc + 0][lp] = av.x; As[lc + 1][lp] = av.y; As[lc + 2][lp] = av.z; As[lc + 3][lp] = av.w;
+            *reinterpret_cast<float4*>(&Bs[bk][bn]) = bv;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kF32TK; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+            }
+        }
+    }
+    const int n = n0 + tx * 4;
+    if (n >= Cout) return;
+    const float4 bv = *reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long p = m0 + ty * 4 + i;
+        if (p >= npix) continue;
+        const int b = static_cast<int>(p / (static_cast<long long>(T) * F));
+        const int t = static_cast<int>((p - static_cast<long long>(b) * T * F) / F);
+        const int L = lengths ? min(max(lengths[b], 0), T) : T;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < L) {
+            o.x = fmaxf(acc[i][0] + bv.x, 0.f); o.y = fmaxf(acc[i][1] + bv.y, 0.f);
+            o.z = fmaxf(acc[i][2] + bv.z, 0.f); o.w = fmaxf(acc[i][3] + bv.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(y + static_cast<size_t>(p) * Cout + n) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------ max-pool 2x2 ceil
+template <typename TI>
+DASV_DEVICE float ld_act(const TI* p);
+template <>
+DASV_DEVICE float ld_act<float>(const float* p) { return *p; }
+template <>
+DASV_DEVICE float ld_act<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+DASV_DEVICE void st_act(float* p, float v) { *p = v; }
+DASV_DEVICE void st_act(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename TI, typename TO, bool REF>
+__global__ void maxpool2x2_kernel(const TI* __restrict__ x, TO* __restrict__ y, int B, int T, int F, int C) {
+    const int T2 = (T + 1) / 2, F2 = (F + 1) / 2;
+    const size_t n = static_cast<size_t>(B) * T2 * F2 * C;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        int c, f2, t2, b;
+        size_t r = i;
+        if (REF) { f2 = r % F2; r /= F2; c = r % C; r /= C; }   // feature index = c*F2 + f2 (CNNs.py:88-89)
+        else     { c = r % C; r /= C; f2 = r % F2; r /= F2; }
+        t2 = r % T2; b = r / T2;
+        float m = -INFINITY;
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+            for (int df = 0; df < 2; ++df) {
+                const int t = 2 * t2 + dt, f = 2 * f2 + df;
+                if (t < T && f < F) m = fmaxf(m, ld_act<TI>(x + ((static_cast<size_t>(b) * T + t) * F + f) * C + c));
+            }
+        st_act(y + i, m);
+    }
+}
+
+}  // namespace dasv
+
+using namespace dasv;
+
+extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* bias, const int32_t* lengths,
+                                  void* y, int y_dtype, int B, int T, int F, int Cout, void* stream) {
+    if (!x || !w || !bias || !y) { set_error("conv11_direct: null argument"); return 1; }
+    if (Cout % 8 != 0 || Cout <= 0) { set_error("conv11_direct: Cout=%d must be a positive multiple of 8", Cout); return 1; }
+    if (y_dtype != 0 && y_dtype != 1) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
+    if (B <= 0 || T <= 0) return 0;
+    const size_t smem = (static_cast<size_t>(10) * Cout + 3 * (F + 2)) * sizeof(float);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (y_dtype == 1) conv11_direct_kernel<true><<<B * T, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
+    else conv11_direct_kernel<false><<<B * T, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
+    return check_launch("conv11_direct");
+}
+
+extern "C" int dasv_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, void* stream) {
+    if (!w || !packed) { set_error("pack_conv_weight_f32: null argument"); return 1; }
+    const int n = 9 * Cin * Cout;
+    pack_w_f32_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, packed, Cout, Cin);
+    return check_launch("pack_conv_weight_f32");
+}
+
+extern "C" size_t dasv_packed_conv_weight_bf16_elems(int Cout, int Cin) {
+    const size_t cp = (static_cast<size_t>(Cout) + 127) / 128 * 128;
+    return cp * 9 * static_cast<size_t>(Cin);
+}
+
+extern "C" int dasv_pack_conv_weight_bf16(const float* w, void* packed, int Cout, int Cin, void* stream) {
+    if (!w || !packed) { set_error("pack_conv_weight_bf16: null argument"); return 1; }
+    const int cp = (Cout + 127) / 128 * 128;
+    const size_t n = static_cast<size_t>(cp) * 9 * Cin;
+    pack_w_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, cp);
+    return check_launch("pack_conv_weight_bf16");
+}
+
+extern "C" int dasv_conv3x3_f32(const float* x, const float* wp, const float* bias, const int32_t* lengths,
+                                float* y, int B, int T, int F, int Cin, int Cout, void* stream) {
+    if (!x || !wp || !bias || !y) { set_error("conv3x3_f32: null argument"); return 1; }
+    if (Cin % 4 != 0 || Cout % 4 != 0) { set_error("conv3x3_f32: Cin=%d and Cout=%d must be multiples of 4", Cin, Cout); return 1; }
+    if (B <= 0 || T <= 0) return 0;
+    const long long npix = static_cast<long long>(B) * T * F;
+    dim3 grid(static_cast<unsigned>((npix + kF32TM - 1) / kF32TM), (Cout + kF32TN - 1) / kF32TN);
+    conv3x3_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, wp, bias, lengths, y, B, T, F, Cin, Cout);
+    return check_launch("conv3x3_f32");
+}
+
+extern "C" int dasv_maxpool2x2(const void* x, int x_dtype, void* y, int y_dtype, int ref_layout,
+                               int B, int T, int F, int C, void* stream) {
+    if (!x || !y) { set_error("maxpool2x2: null argument"); return 1; }
+    if (B <= 0 || T <= 0) return 0;
+    const size_t n = static_cast<size_t>(B) * ((T + 1) / 2) * ((F + 1) / 2) * C;
+    const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define DASV_POOL(TI, TO, REF) \
+    maxpool2x2_kernel<TI, TO, REF><<<grid, 256, 0, s>>>(static_cast<const TI*>(x), static_cast<TO*>(y), B, T, F, C)
+    if (x_dtype == 0 && y_dtype == 0) { if (ref_layout) DASV_POOL(float, float, true); else DASV_POOL(float, float, false); }
+    else if (x_dtype == 1 && y_dtype == 1) { if (ref_layout) DASV_POOL(__nv_bfloat16, __nv_bfloat16, true); else DASV_POOL(__nv_bfloat16, __nv_bfloat16, false); }
+    else if (x_dtype == 1 && y_dtype == 0) { if (ref_layout) DASV_POOL(__nv_bfloat16, float, true); else DASV_POOL(__nv_bfloat16, float, false); }
+    else { set_error("maxpool2x2: unsupported dtype pair %d -> %d", x_dtype, y_dtype); return 1; }
+#undef DASV_POOL
+    return check_launch("maxpool2x2");
+}

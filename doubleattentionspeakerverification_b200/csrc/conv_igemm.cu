@@ -1,0 +1,393 @@
+// bf16 tensor-core implicit-GEMM 3x3 convolution for the VGG front-end (scripts/CNNs.py:73-86),
+// written for sm_100a: TMA -> swizzled SMEM -> tcgen05.mma (accumulators in TMEM) -> tcgen05.ld
+// epilogue with bias + ReLU + length mask (+ 2x2 ceil-mode max-pool, + the front-end's final
+// [B,T',C*F'] re-layout) fused, so activations make one HBM round trip per layer.
+//
+// GEMM orientation (chosen for the epilogue):  D[co, pixel] = sum_k W[co, k] * X[pixel, k],
+//   k = (tap, ci).  A = packed weights [Cout_pad][9*Cin] (K-major, 128 rows per CTA tile = the 128
+//   TMEM lanes), B = an activation patch of N = BF x BT x BB pixels (f, t, utterance) loaded by ONE
+//   4-D TMA box per (tap, 64-channel slice): the box origin is shifted by the tap offset and TMA's
+//   out-of-bounds zero fill implements the conv padding (also across utterance boundaries).
+//   With output channels on TMEM lanes a thread owns one channel and sees pixels along TMEM
+//   columns, so the 2x2 pool window (columns j, j+1, j+BF, j+BF+1) is thread-local, and the final
+//   layer's feature order c*F'+f is a contiguous store.
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue.  Pipelines: SMEM ring full/empty, double-buffered TMEM accumulator
+//   full/empty, persistent static tile schedule (tile = blockIdx.x + i*gridDim.x).
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace dasv {
+
+constexpr int kConvThreads = 256;
+constexpr int kConvTileM = 128;                 // output channels per CTA tile = TMEM lanes
+constexpr int kConvKC = 64;                     // channels per K slice (64 bf16 = one 128-byte swizzle row)
+constexpr uint32_t kConvABytes = kConvTileM * kConvKC * 2;
+
+struct ConvParams {
+    const float* bias;
+    const int32_t* lengths;
+    void* y;
+    int B, T, F, Cin, Cout;
+    int BF, BT, BB;          // patch: BF frequency bins x BT frames x BB utterances
+    int N, Npad;             // pixels per patch, rounded up to 16 (UMMA N)
+    int n_ft, n_tt, n_bt, n_mt;
+    int kchunks;             // Cin / 64
+    int stages;
+    int pool, ref_layout, y_f32;
+    uint32_t b_bytes;        // bytes one B box delivers (N * 128)
+    uint32_t stage_bytes;    // A + B(padded) per ring stage
+    uint32_t tmem_cols;
+};
+
+struct ConvTile {
+    int m, f0, t0, b0;
+};
+
+DASV_DEVICE ConvTile conv_decode_tile(const ConvParams& p, int tile) {
+    ConvTile c;
+    c.m = tile % p.n_mt;
+    int pt = tile / p.n_mt;
+    c.f0 = (pt % p.n_ft) * p.BF; pt /= p.n_ft;
+    c.t0 = (pt % p.n_tt) * p.BT; pt /= p.n_tt;
+    c.b0 = pt * p.BB;
+    return c;
+}
+
+DASV_DEVICE int conv_len(const ConvParams& p, int b) {
+    if (b >= p.B) return 0;
+    return p.lengths ? min(max(p.lengths[b], 0), p.T) : p.T;
+}
+
+// A patch whose every frame lies at or beyond its utterance's valid length produces only zeros.
+DASV_DEVICE bool conv_tile_masked(const ConvParams& p, const ConvTile& c) {
+    if (p.lengths == nullptr) return false;
+    for (int bb = 0; bb < p.BB; ++bb)
+        if (conv_len(p, c.b0 + bb) > c.t0) return false;
+    return true;
+}
+
+DASV_DEVICE void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+DASV_DEVICE void tmem_ld_x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+
+template <bool F32>
+DASV_DEVICE void conv_store(void* y, size_t idx, float v) {
+    if (F32) static_cast<float*>(y)[idx] = v;
+    else static_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand.
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* ring = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* acc_full = empty + p.stages;      // [2]
+    uint64_t* acc_empty = acc_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = p.n_mt * p.n_ft * p.n_tt * p.n_bt;
+    const int ksteps = 9 * p.kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 2) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const ConvTile c = conv_decode_tile(p, tile);
+                if (conv_tile_masked(p, c)) continue;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                        const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
+                        mbar_wait(&empty[st], ph ^ 1u);
+                        unsigned char* a_sm = ring + static_cast<size_t>(st) * p.stage_bytes;
+                        mbar_arrive_expect_tx(&full[st], kConvABytes + p.b_bytes);
+                        tma_load_2d(a_sm, &tmA, &full[st], tap * p.Cin + kc * kConvKC, c.m * kConvTileM);
+                        tma_load_4d(a_sm + kConvABytes, &tmB, &full[st], kc * kConvKC, c.f0 + dx, c.t0 + dy, c.b0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kConvTileM, static_cast<uint32_t>(p.Npad));
+            uint32_t it = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const ConvTile c = conv_decode_tile(p, tile);
+                if (conv_tile_masked(p, c)) continue;
+                const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                mbar_wait(&acc_empty[as], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * static_cast<uint32_t>(p.Npad);
+                for (int ks = 0; ks < ksteps; ++ks, ++it) {
+                    const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
+                    const uint64_t a_desc = umma_desc_k128(a_addr);
+                    const uint64_t b_desc = umma_desc_k128(a_addr + kConvABytes);
+#pragma unroll
+                    for (int k = 0; k < kConvKC / 16; ++k)     // +32 B per 16-element K step inside the swizzle atom
+                        umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                                  (ks | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty[st]);                   // frees the ring slot when these MMAs retire
+                }
+                umma_commit(&acc_full[as]);                    // accumulator complete -> epilogue
+                ++acc_it;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (TMEM -> regs -> HBM)
+        const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int T = p.T, F = p.F, Cout = p.Cout, BF = p.BF, BT = p.BT;
+        const int T2 = (T + 1) / 2, F2 = F / 2;
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const ConvTile c = conv_decode_tile(p, tile);
+            const int n = c.m * kConvTileM + q * 32 + lane;
+            const bool n_ok = n < Cout;
+            const bool masked = conv_tile_masked(p, c);
+            uint32_t tcol = 0;
+            if (!masked) {
+                const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+                tcol = tmem_base + lane_addr + as * static_cast<uint32_t>(p.Npad);
+            }
+            const float bias = n_ok ? p.bias[n] : 0.f;
+            if (!p.pool) {
+                // y[b, t, f, n] = relu(acc + bias), zero for t >= L
+                for (int j0 = 0; j0 < p.N; j0 += 16) {
+                    uint32_t r[16];
+                    if (!masked) { tmem_ld_x16(tcol + j0, r); tc_wait_ld(); }
+                    int bb = j0 / (BT * BF), rem = j0 - bb * (BT * BF);
+                    int tl = rem / BF, fl = rem - tl * BF;
+                    int Lb = conv_len(p, c.b0 + bb);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j0 + j < p.N) {
+                            const int b = c.b0 + bb, t = c.t0 + tl, f = c.f0 + fl;
+                            if (n_ok && b < p.B && t < T) {
+                                const float v = (!masked && t < Lb) ? fmaxf(__uint_as_float(r[j]) + bias, 0.f) : 0.f;
+                                conv_store<false>(p.y, ((static_cast<size_t>(b) * T + t) * F + f) * Cout + n, v);
+                            }
+                            if (++fl == BF) { fl = 0; if (++tl == BT) { tl = 0; ++bb; Lb = conv_len(p, c.b0 + bb); } }
+                        }
+                    }
+                }
+            } else {
+                // pooled[b, t2, f2, n] = relu(max over the valid 2x2 window + bias)   (max and +bias/ReLU commute)
+                for (int bb = 0; bb < p.BB; ++bb) {
+                    const int b = c.b0 + bb;
+                    const int Lb = conv_len(p, b);
+                    for (int tp = 0; tp < BT / 2; ++tp) {
+                        const int t = c.t0 + 2 * tp;
+                        if (b >= p.B || t >= T) continue;       // warp-uniform
+                        const bool r0_ok = !masked && t < Lb, r1_ok = !masked && (t + 1) < Lb;
+                        const uint32_t col0 = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF);
+                        const int t2 = t >> 1;
+                        for (int fp0 = 0; fp0 < BF / 2; fp0 += 4) {
+                            uint32_t v[4][4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (!masked && fp0 + u < BF / 2) {      // warp-uniform
+                                    tmem_ld_x2(col0 + 2 * (fp0 + u), v[u][0], v[u][1]);
+                                    tmem_ld_x2(col0 + BF + 2 * (fp0 + u), v[u][2], v[u][3]);
+                                }
+                            }
+                            if (!masked) tc_wait_ld();
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (fp0 + u < BF / 2 && n_ok) {
+                                    float m = 0.f;
+                                    if (r0_ok) {
+                                        m = fmaxf(__uint_as_float(v[u][0]), __uint_as_float(v[u][1]));
+                                        if (r1_ok) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
+                                        m = fmaxf(m + bias, 0.f);
+                                    }
+                                    const int f2 = (c.f0 >> 1) + fp0 + u;
+                                    if (p.ref_layout) {
+                                        const size_t idx = (static_cast<size_t>(b) * T2 + t2) * (static_cast<size_t>(Cout) * F2) +
+                                                           static_cast<size_t>(n) * F2 + f2;      // feature = c*F' + f (CNNs.py:88-89)
+                                        if (p.y_f32) conv_store<true>(p.y, idx, m); else conv_store<false>(p.y, idx, m);
+                                    } else {
+                                        conv_store<false>(p.y, ((static_cast<size_t>(b) * T2 + t2) * F2 + f2) * Cout + n, m);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (!masked) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
+                ++acc_it;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+struct ConvPlan {
+    int BF, BT, BB, N, Npad;
+    double cost;
+};
+
+// Pick the patch shape that minimises the modelled tensor time of the whole layer: per 16-deep
+// K step a 128 x Npad MMA costs max(Npad/2 tensor cycles, (128+Npad)/4 SMEM-read cycles).
+static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool) {
+    ConvPlan best{0, 0, 0, 0, 0, 1e300};
+    const double ksteps = 9.0 * Cin / 16.0;
+    for (int BF = 2; BF <= F && BF <= 256; BF += 2) {
+        if (F % BF != 0) continue;
+        const int bt_max = 256 / BF;
+        for (int BT = pool ? 2 : 1; BT <= bt_max; BT += pool ? 2 : 1) {
+            if (BT > T + 1 && BT > 2) break;
+            const int n_tt = (T + BT - 1) / BT;
+            const int bb_max = (n_tt == 1) ? 256 / (BF * BT) : 1;
+            for (int BB = 1; BB <= bb_max && BB <= B; ++BB) {
+                const int N = BF * BT * BB, Npad = (N + 15) / 16 * 16;
+                if (Npad > 256) continue;
+                const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB);
+                const double step = Npad / 2.0 > (128 + Npad) / 4.0 ? Npad / 2.0 : (128 + Npad) / 4.0;
+                const double cost = tiles * (step * ksteps + 700.0);
+                if (cost < best.cost) best = ConvPlan{BF, BT, BB, N, Npad, cost};
+            }
+        }
+    }
+    return best;
+}
+
+}  // namespace dasv
+
+using namespace dasv;
+
+extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, const int32_t* lengths,
+                                       void* y, int y_dtype, int flags,
+                                       int B, int T, int F, int Cin, int Cout, void* stream) {
+    if (!x || !wp || !bias || !y) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
+    if (Cin % kConvKC != 0 || Cin <= 0) { set_error("conv3x3_igemm_bf16: Cin=%d must be a positive multiple of 64", Cin); return 1; }
+    if (Cout <= 0 || Cout % 8 != 0) { set_error("conv3x3_igemm_bf16: Cout=%d must be a positive multiple of 8", Cout); return 1; }
+    if (F <= 0 || F % 2 != 0 || F > 256) { set_error("conv3x3_igemm_bf16: F=%d must be even and <= 256", F); return 1; }
+    if (!(flags & 1)) { set_error("conv3x3_igemm_bf16: the epilogue always applies ReLU (flag DASV_CONV_RELU required)"); return 1; }
+    const bool pool = (flags & 2) != 0, ref = (flags & 4) != 0;
+    if (ref && !pool) { set_error("conv3x3_igemm_bf16: REF_LAYOUT requires POOL"); return 1; }
+    if (!ref && y_dtype != 1) { set_error("conv3x3_igemm_bf16: NHWC output must be bf16"); return 1; }
+    if (y_dtype != 0 && y_dtype != 1) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
+    if (B <= 0 || T <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15)) {
+        set_error("conv3x3_igemm_bf16: x and wp must be 16-byte aligned"); return 1;
+    }
+    EncodeTiledFn encode = get_encode_tiled();
+    if (!encode) { set_error("conv3x3_igemm_bf16: cuTensorMapEncodeTiled is not available from the CUDA driver"); return 1; }
+
+    const ConvPlan pl = conv_plan(B, T, F, Cin, pool);
+    if (pl.N == 0) { set_error("conv3x3_igemm_bf16: no patch shape for T=%d F=%d", T, F); return 1; }
+    const int cout_pad = (Cout + kConvTileM - 1) / kConvTileM * kConvTileM;
+
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(9) * Cin, static_cast<cuuint64_t>(cout_pad)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(9) * Cin * 2};
+        const cuuint32_t box[2] = {kConvKC, kConvTileM};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: weight tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
+    }
+    {
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(F), static_cast<cuuint64_t>(T),
+                                    static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cin) * 2, static_cast<cuuint64_t>(F) * Cin * 2,
+                                       static_cast<cuuint64_t>(T) * F * Cin * 2};
+        const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(pl.BT),
+                                   static_cast<cuuint32_t>(pl.BB)};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: activation tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
+    }
+
+    ConvParams p{};
+    p.bias = bias; p.lengths = lengths; p.y = y;
+    p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.Cout = Cout;
+    p.BF = pl.BF; p.BT = pl.BT; p.BB = pl.BB; p.N = pl.N; p.Npad = pl.Npad;
+    p.n_ft = F / pl.BF; p.n_tt = (T + pl.BT - 1) / pl.BT; p.n_bt = (B + pl.BB - 1) / pl.BB; p.n_mt = cout_pad / kConvTileM;
+    p.kchunks = Cin / kConvKC;
+    p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
+    p.b_bytes = static_cast<uint32_t>(pl.N) * 128u;
+    p.stage_bytes = kConvABytes + ((static_cast<uint32_t>(pl.Npad) * 128u + 1023u) & ~1023u);
+    int stages = static_cast<int>((220u * 1024u) / p.stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) { set_error("conv3x3_igemm_bf16: ring does not fit shared memory"); return 1; }
+    p.stages = stages;
+    uint32_t cols = 32;
+    while (cols < 2u * pl.Npad) cols <<= 1;
+    p.tmem_cols = cols;
+    const long long n_tiles = static_cast<long long>(p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
+    if (n_tiles > 0x7fffffffLL) { set_error("conv3x3_igemm_bf16: too many tiles"); return 1; }
+
+    const size_t smem = static_cast<size_t>(stages) * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = static_cast<int>(n_tiles < sms ? n_tiles : sms);
+    conv3x3_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+    return check_launch("conv3x3_igemm_bf16");
+}

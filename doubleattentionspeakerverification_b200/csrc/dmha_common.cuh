@@ -1,0 +1,58 @@
+// Shared pieces of the fused DoubleMHA pooling kernels (forward and backward).
+//
+// Work decomposition (both directions):
+//   * one CTA owns one utterance at a time (all H heads must meet for the head softmax) and
+//     loops persistently over utterances b = blockIdx.x, blockIdx.x + gridDim.x, ...
+//   * a producer warp streams the utterance's valid frames HBM -> SMEM with 1-D bulk async
+//     copies (cp.async.bulk, the TMA engine's linear mode) into a ring of `stages` buffers of
+//     `fps` frames each, signalling per-stage "full" mbarriers; 8 consumer warps release
+//     stages through "empty" mbarriers.  x[b] is contiguous, so every copy is one linear burst.
+//   * consumer threads are split in groups of G lanes (G = 8/16/32, a sub-warp); a group owns
+//     head(s) and reads a head's row of one frame as NV 16-byte vectors per lane; row
+//     reductions are xor-shuffles inside the group.
+#pragma once
+#include "common.cuh"
+
+namespace dasv {
+
+constexpr int kDmhaConsumerWarps = 8;
+constexpr int kDmhaConsumerThreads = kDmhaConsumerWarps * 32;
+constexpr int kDmhaThreads = kDmhaConsumerThreads + 32;   // + producer warp
+constexpr int kDmhaFB = 4;                                 // frames processed together (ILP)
+
+struct DmhaPlan {
+    int bf16, G, NV, HPG, S, fps, stages;
+    size_t smem_bytes;
+    int err;    // 0 ok
+};
+
+template <int VE, bool BF16>
+DASV_DEVICE void load_row_vec(const unsigned char* p, float (&f)[VE]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    if constexpr (BF16) {
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+    } else {
+        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+        f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    }
+}
+
+template <int G>
+DASV_DEVICE float group_sum(float v) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+DASV_DEVICE float warp_sum(float v) { return group_sum<32>(v); }
+DASV_DEVICE float warp_max(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// Host-side plan shared by forward and backward so both walk the ring identically.
+DmhaPlan dmha_make_plan(int x_dtype, int T, int D, int H, bool backward);
+
+}  // namespace dasv

@@ -1,0 +1,237 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw device pointers and the
+current CUDA stream, check the status code.  No arithmetic happens here and nothing falls back to
+PyTorch or the CPU: a tensor that is not on a CUDA device is an error.
+"""
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+CONV_RELU, CONV_POOL, CONV_REF_LAYOUT = 1, 2, 4
+
+
+def _dev(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DasvError('%s must be a CUDA tensor (this package has no CPU path)' % name)
+    return t
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_code(t, name):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise _lib.DasvError('%s: dtype %s not supported (float32 or bfloat16)' % (name, t.dtype))
+
+
+def _f32(t, name):
+    _dev(t, name)
+    if t.dtype != torch.float32:
+        raise _lib.DasvError('%s must be float32, got %s' % (name, t.dtype))
+    return t.contiguous()
+
+
+def _lengths(lengths, B, device):
+    if lengths is None:
+        return None
+    lengths = torch.as_tensor(lengths, device=device).to(torch.int32).contiguous()
+    if lengths.numel() != B:
+        raise _lib.DasvError('lengths has %d entries for a batch of %d' % (lengths.numel(), B))
+    return lengths
+
+
+# ------------------------------------------------------------------------------------ pooling
+def dmha_fwd(x, query, att=None, lengths=None, keep=None, need_align=True, need_out=True):
+    """Fused DoubleMHA forward (att given) or MultiHeadAttention forward (att None).
+
+    Returns dict(out [B,dh]|None, ctx [B,H,dh], lse [B,H], headw [B,H]|None, align [B,T,H]|None)."""
+    _dev(x, 'x')
+    x = x.contiguous()
+    B, T, D = x.shape
+    query = _f32(query, 'query')
+    dh, H = query.shape
+    if dh * H != D:
+        raise _lib.DasvError('query [%d,%d] does not match feature size %d' % (dh, H, D))
+    with torch.cuda.device(x.device):
+        dev = x.device
+        att_c = None if att is None else _f32(att, 'att').reshape(-1)
+        lengths = _lengths(lengths, B, dev)
+        keep_c = None if keep is None else _dev(keep, 'keep').to(torch.uint8).contiguous()
+        f = dict(device=dev, dtype=torch.float32)
+        out = torch.empty((B, dh), **f) if (att is not None and need_out) else None
+        ctx = torch.empty((B, H, dh), **f)
+        lse = torch.empty((B, H), **f)
+        headw = torch.empty((B, H), **f) if att is not None else None
+        align = torch.empty((B, T, H), **f) if need_align else None
+        rc = _lib.lib().dasv_dmha_fwd(_p(x), _dtype_code(x, 'x'), _p(lengths), _p(query), _p(att_c), _p(keep_c),
+                                      _p(out), _p(ctx), _p(lse), _p(headw), _p(align), B, T, D, H, _stream())
+        _lib.check(rc, 'dasv_dmha_fwd')
+    return dict(out=out, ctx=ctx, lse=lse, headw=headw, align=align)
+
+
+def dmha_bwd(x, query, att, g_out, g_ctx, ctx, lse, headw, lengths=None):
+    """Closed-form backward of dmha_fwd.  Returns (dx, dquery [dh,H], datt [dh]|None)."""
+    _dev(x, 'x')
+    x = x.contiguous()
+    B, T, D = x.shape
+    query = _f32(query, 'query')
+    dh, H = query.shape
+    with torch.cuda.device(x.device):
+        dev = x.device
+        att_c = None if att is None else _f32(att, 'att').reshape(-1)
+        g_out = None if g_out is None else _f32(g_out, 'g_out')
+        g_ctx = None if g_ctx is None else _f32(g_ctx, 'g_ctx')
+        lengths = _lengths(lengths, B, dev)
+        dx = torch.empty_like(x)
+        dquery = torch.empty((dh, H), device=dev, dtype=torch.float32)
+        datt = torch.empty((dh,), device=dev, dtype=torch.float32) if att is not None else None
+        L = _lib.lib()
+        ws = torch.empty((max(int(L.dasv_dmha_bwd_workspace_bytes(B, T, D, H)), 4),), device=dev, dtype=torch.uint8)
+        rc = L.dasv_dmha_bwd(_p(x), _dtype_code(x, 'x'), _p(lengths), _p(query), _p(att_c), _p(g_out), _p(g_ctx),
+                             _p(ctx), _p(lse), _p(headw), _p(dx), _p(dquery), _p(datt), _p(ws), B, T, D, H, _stream())
+        _lib.check(rc, 'dasv_dmha_bwd')
+    return dx, dquery, datt
+
+
+def attention_fwd(x, att, lengths=None, keep=None):
+    """Single-query attention over dim 1 (Attention / stand-alone HeadAttention).  Returns (out [B,D], align [B,T])."""
+    _dev(x, 'x')
+    x = x.contiguous()
+    B, T, D = x.shape
+    with torch.cuda.device(x.device):
+        att_c = _f32(att, 'att').reshape(-1)
+        lengths = _lengths(lengths, B, x.device)
+        keep_c = None if keep is None else _dev(keep, 'keep').to(torch.uint8).contiguous()
+        out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+        align = torch.empty((B, T), device=x.device, dtype=torch.float32)
+        rc = _lib.lib().dasv_attention_fwd(_p(x), _dtype_code(x, 'x'), _p(lengths), _p(keep_c), _p(att_c), _p(out), _p(align),
+                                           B, T, D, _stream())
+        _lib.check(rc, 'dasv_attention_fwd')
+    return out, align
+
+
+# ------------------------------------------------------------------------------------ front-end
+def pack_conv_weight_f32(w):
+    w = _f32(w, 'w')
+    Cout, Cin = w.shape[0], w.shape[1]
+    with torch.cuda.device(w.device):
+        p = torch.empty((9, Cin, Cout), device=w.device, dtype=torch.float32)
+        _lib.check(_lib.lib().dasv_pack_conv_weight_f32(_p(w), _p(p), Cout, Cin, _stream()), 'dasv_pack_conv_weight_f32')
+    return p
+
+
+def pack_conv_weight_bf16(w):
+    w = _f32(w, 'w')
+    Cout, Cin = w.shape[0], w.shape[1]
+    with torch.cuda.device(w.device):
+        n = int(_lib.lib().dasv_packed_conv_weight_bf16_elems(Cout, Cin))
+        p = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
+        _lib.check(_lib.lib().dasv_pack_conv_weight_bf16(_p(w), _p(p), Cout, Cin, _stream()), 'dasv_pack_conv_weight_bf16')
+    return p
+
+
+def conv11_direct(x, w, bias, lengths=None, out_dtype=torch.float32):
+    """x [B,T,F] f32 -> relu(conv3x3(x) + bias) as NHWC [B,T,F,Cout]."""
+    x = _f32(x, 'x')
+    B, T, Fq = x.shape
+    w, bias = _f32(w, 'w'), _f32(bias, 'bias')
+    Cout = w.shape[0]
+    with torch.cuda.device(x.device):
+        lengths = _lengths(lengths, B, x.device)
+        y = torch.empty((B, T, Fq, Cout), device=x.device, dtype=out_dtype)
+        rc = _lib.lib().dasv_conv11_direct(_p(x), _p(w), _p(bias), _p(lengths), _p(y), _dtype_code(y, 'y'), B, T, Fq, Cout, _stream())
+        _lib.check(rc, 'dasv_conv11_direct')
+    return y
+
+
+def conv3x3_f32(x, wp, bias, lengths=None):
+    """fp32 CUDA-core conv3x3 + bias + ReLU on NHWC; wp from pack_conv_weight_f32."""
+    x = _f32(x, 'x')
+    B, T, Fq, Cin = x.shape
+    Cout = wp.shape[2]
+    with torch.cuda.device(x.device):
+        lengths = _lengths(lengths, B, x.device)
+        y = torch.empty((B, T, Fq, Cout), device=x.device, dtype=torch.float32)
+        rc = _lib.lib().dasv_conv3x3_f32(_p(x), _p(wp), _p(_f32(bias, 'bias')), _p(lengths), _p(y), B, T, Fq, Cin, Cout, _stream())
+        _lib.check(rc, 'dasv_conv3x3_f32')
+    return y
+
+
+def maxpool2x2(x, ref_layout=False, out_dtype=None):
+    """2x2 stride-2 ceil-mode max-pool on NHWC; ref_layout=True writes [B,T2,C*F2] (feature = c*F2+f)."""
+    _dev(x, 'x')
+    x = x.contiguous()
+    B, T, Fq, C = x.shape
+    out_dtype = out_dtype or x.dtype
+    T2, F2 = (T + 1) // 2, (Fq + 1) // 2
+    with torch.cuda.device(x.device):
+        shape = (B, T2, C * F2) if ref_layout else (B, T2, F2, C)
+        y = torch.empty(shape, device=x.device, dtype=out_dtype)
+        rc = _lib.lib().dasv_maxpool2x2(_p(x), _dtype_code(x, 'x'), _p(y), _dtype_code(y, 'y'), int(ref_layout), B, T, Fq, C, _stream())
+        _lib.check(rc, 'dasv_maxpool2x2')
+    return y
+
+
+def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16):
+    """bf16 tcgen05 implicit-GEMM conv3x3 + bias + ReLU (+ fused 2x2 ceil max-pool) on NHWC bf16."""
+    _dev(x, 'x')
+    if x.dtype != torch.bfloat16:
+        raise _lib.DasvError('conv3x3_igemm_bf16: x must be bfloat16')
+    x = x.contiguous()
+    B, T, Fq, Cin = x.shape
+    flags = CONV_RELU | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0)
+    with torch.cuda.device(x.device):
+        lengths = _lengths(lengths, B, x.device)
+        if pool:
+            T2, F2 = (T + 1) // 2, Fq // 2
+            shape = (B, T2, Cout * F2) if ref_layout else (B, T2, F2, Cout)
+        else:
+            shape = (B, T, Fq, Cout)
+        y = torch.empty(shape, device=x.device, dtype=out_dtype if ref_layout else torch.bfloat16)
+        rc = _lib.lib().dasv_conv3x3_igemm_bf16(_p(x), _p(wp), _p(_f32(bias, 'bias')), _p(lengths), _p(y), _dtype_code(y, 'y'),
+                                                flags, B, T, Fq, Cin, Cout, _stream())
+        _lib.check(rc, 'dasv_conv3x3_igemm_bf16')
+    return y
+
+
+# ------------------------------------------------------------------------------------ tail / scoring
+def fc_tail(pooled, w1t, b1, w2t, b2, bn_scale, bn_shift):
+    pooled = _f32(pooled, 'pooled')
+    B, Din = pooled.shape
+    E = w1t.shape[1]
+    with torch.cuda.device(pooled.device):
+        emb = torch.empty((B, E), device=pooled.device, dtype=torch.float32)
+        rc = _lib.lib().dasv_fc_tail_f32(_p(pooled), _p(w1t), _p(b1), _p(w2t), _p(b2), _p(bn_scale), _p(bn_shift), _p(emb),
+                                         B, Din, E, _stream())
+        _lib.check(rc, 'dasv_fc_tail_f32')
+    return emb
+
+
+def cosine_pairs(emb, ia, ib):
+    emb = _f32(emb, 'emb')
+    ia = _dev(ia, 'ia').to(torch.int32).contiguous()
+    ib = _dev(ib, 'ib').to(torch.int32).contiguous()
+    n = ia.numel()
+    with torch.cuda.device(emb.device):
+        scores = torch.empty((n,), device=emb.device, dtype=torch.float32)
+        _lib.check(_lib.lib().dasv_cosine_pairs(_p(emb), _p(ia), _p(ib), _p(scores), n, emb.shape[1], _stream()), 'dasv_cosine_pairs')
+    return scores
+
+
+def cosine_matrix(enrol, test):
+    enrol, test = _f32(enrol, 'enrol'), _f32(test, 'test')
+    Ne, E = enrol.shape
+    Nt = test.shape[0]
+    with torch.cuda.device(enrol.device):
+        scores = torch.empty((Ne, Nt), device=enrol.device, dtype=torch.float32)
+        ws = torch.empty((Ne + Nt,), device=enrol.device, dtype=torch.float32)
+        _lib.check(_lib.lib().dasv_cosine_matrix(_p(enrol), _p(test), _p(scores), _p(ws), Ne, Nt, E, _stream()), 'dasv_cosine_matrix')
+    return scores

@@ -144,3 +144,11 @@ def make_pooling_case(batch, frames, dim, heads, seed=0, with_lengths=False):
         lengths = rs.randint(max(1, frames // 2), frames + 1, size=(batch,)).astype(np.int32)
         lengths[0] = frames
     return dict(x=x, query=query, att=att, g=g, keep=keep, lengths=lengths)
+
+
+def load_state_dict(module, sd, prefix=''):
+    """Load a ``make_state_dict`` dictionary (numpy) into a torch module of the reference's layout."""
+    import torch
+    own = module.state_dict()
+    module.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(sd[prefix + k])) for k in own})
+    return module

@@ -1,0 +1,145 @@
+/* dasv_b200 — C ABI of the B200-native DoubleMHA speaker-embedding extraction path.
+ *
+ * The reference (fedecosta/DoubleAttentionSpeakerVerification) has no FFI of its own: its
+ * boundary is the Python nn.Module API of scripts/CNNs.py, scripts/poolings.py and
+ * scripts/model.py.  The Python classes of the same names in
+ * doubleattentionspeakerverification_b200/ keep that API and call ONLY the entry points below
+ * (through ctypes).  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory,
+ *     including outputs and workspaces (sizes are given per function);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host, allocates,
+ *     or creates streams; all functions are re-entrant per device;
+ *   - return 0 on success; non-zero = error, message via dasv_last_error() (thread-local);
+ *   - dtype codes: DASV_F32 = 0, DASV_BF16 = 1;
+ *   - "nullable" arguments may be NULL to skip that input/output.
+ */
+#ifndef DASV_B200_H
+#define DASV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DASV_F32 0
+#define DASV_BF16 1
+
+/* conv flags */
+#define DASV_CONV_RELU 1        /* apply ReLU after bias (always set by the VGG blocks)            */
+#define DASV_CONV_POOL 2        /* fuse max_pool2d(2, stride 2, ceil_mode) into the epilogue         */
+#define DASV_CONV_REF_LAYOUT 4  /* with POOL: write [B,T',C*F'] with feature = c*F'+f (CNNs.py:88-89) */
+
+int dasv_abi_version(void);
+const char* dasv_last_error(void);
+
+/* ---------------------------------------------------------------- DoubleMHA pooling
+ * Replaces DoubleMHA.forward = MultiHeadAttention.forward -> HeadAttention.forward
+ * (scripts/poolings.py:126-129 -> :100-109 -> innerKeyValueAttention :73-80 -> :45-51,:61-71)
+ * with ONE pass over x:
+ *   s[b,t,h] = <x[b,t,h,:], query[:,h]> / sqrt(H);  p = softmax_t(s) over t < lengths[b];
+ *   ctx[b,h,:] = sum_t p x;  u[b,h] = <ctx[b,h,:], att>;  u = -inf where keep==0;
+ *   headw = softmax_h(u);  out[b,:] = sum_h headw ctx[b,h,:].
+ * x [B,T,D] (x_dtype), D = H*dh;  lengths [B] int32 nullable (NULL = all T);
+ * query [dh,H] f32 (reference layout);  att [dh] f32 nullable (NULL = MultiHeadAttention only:
+ * no head stage, `out`/`headw` must then be NULL);  keep [B,H] uint8 nullable (training-mode
+ * head drop-out mask, poolings.py:39-43, drawn by the caller);
+ * out [B,dh], ctx [B,H,dh], lse [B,H], headw [B,H], align [B,T,H] : f32, each nullable.
+ */
+int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
+                  const float* query, const float* att, const uint8_t* keep,
+                  float* out, float* ctx, float* lse, float* headw, float* align,
+                  int B, int T, int D, int H, void* stream);
+
+/* Backward of the above w.r.t. x, query, att (closed form): one pass that reads
+ * x and writes dx.  g_out [B,dh] f32 nullable (gradient of `out`);  g_ctx [B,H,dh] f32 nullable
+ * (gradient arriving directly on ctx, i.e. MultiHeadAttention used alone);  ctx/lse/headw are
+ * the forward's saved outputs (headw nullable iff att is NULL);  dx [B,T,D] in x_dtype;
+ * dquery [dh,H] f32, datt [dh] f32 (nullable iff att NULL) are OVERWRITTEN, deterministically
+ * (per-CTA partials in `workspace`, then a fixed-order reduction).
+ */
+size_t dasv_dmha_bwd_workspace_bytes(int B, int T, int D, int H);
+int dasv_dmha_bwd(const void* x, int x_dtype, const int32_t* lengths,
+                  const float* query, const float* att,
+                  const float* g_out, const float* g_ctx,
+                  const float* ctx, const float* lse, const float* headw,
+                  void* dx, float* dquery, float* datt, void* workspace,
+                  int B, int T, int D, int H, void* stream);
+
+/* Attention.forward (scripts/poolings.py:22-27): single query over time, no scale; also the
+ * stand-alone HeadAttention.forward (poolings.py:45-51,61-71; T = heads, D = head size) with its
+ * training-mode drop mask.  x [B,T,D] (x_dtype), keep [B,T] uint8 nullable, att [D] f32,
+ * out [B,D] f32, align [B,T] f32 (required: it is both the module's second return value and
+ * the kernel's score workspace). */
+int dasv_attention_fwd(const void* x, int x_dtype, const int32_t* lengths, const uint8_t* keep,
+                       const float* att, float* out, float* align, int B, int T, int D, void* stream);
+
+/* ---------------------------------------------------------------- VGG front-end
+ * Activations are NHWC [B,T,F,C]; the reference's NCHW [B,1,T,80] input (CNNs.py:70) is NHWC
+ * with C=1.  `lengths` (nullable) = valid frames per utterance AT THIS LAYER'S INPUT resolution;
+ * rows t >= lengths[b] of the conv output are written as zero (SURVEY.md §5.7 masking rule).
+ */
+
+/* conv11: Conv2d(1, Cout, 3, padding 1) + bias + ReLU (CNNs.py:72).
+ * x [B,T,F] f32, w [Cout,1,3,3] f32 (reference layout), bias [Cout] f32, y [B,T,F,Cout] (y_dtype). */
+int dasv_conv11_direct(const float* x, const float* w, const float* bias, const int32_t* lengths,
+                       void* y, int y_dtype, int B, int T, int F, int Cout, void* stream);
+
+/* Weight re-packing (done once per module, cached by the caller):
+ *   f32 path : w [Cout,Cin,3,3] f32 -> [9][Cin][Cout] f32
+ *   bf16 path: w [Cout,Cin,3,3] f32 -> [Cout_pad][9][Cin] bf16 (K-major A operand for tcgen05;
+ *              Cout_pad = Cout rounded up to 128, extra rows zero; element count from
+ *              dasv_packed_conv_weight_bf16_elems) */
+int dasv_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, void* stream);
+size_t dasv_packed_conv_weight_bf16_elems(int Cout, int Cin);
+int dasv_pack_conv_weight_bf16(const float* w, void* packed, int Cout, int Cin, void* stream);
+
+/* fp32 CUDA-core implicit-GEMM conv3x3 + bias + ReLU (+ row mask): the fp32-parity path
+ * (1e-4 relative) for conv12..conv42 (CNNs.py:73-85).  x [B,T,F,Cin] f32, wp packed f32,
+ * y [B,T,F,Cout] f32.  Cin % 4 == 0, Cout % 4 == 0. */
+int dasv_conv3x3_f32(const float* x, const float* wp, const float* bias, const int32_t* lengths,
+                     float* y, int B, int T, int F, int Cin, int Cout, void* stream);
+
+/* max_pool2d(2, stride 2, ceil_mode=True) on NHWC (CNNs.py:74,78,82,86); x [B,T,F,C] (dtype),
+ * y [B,ceil(T/2),ceil(F/2),C] same dtype, or with ref_layout != 0 the front-end's final
+ * [B,T',C*F'] tensor with feature index c*F'+f (CNNs.py:88-89) in y_dtype. */
+int dasv_maxpool2x2(const void* x, int x_dtype, void* y, int y_dtype, int ref_layout,
+                    int B, int T, int F, int C, void* stream);
+
+/* bf16 tensor-core implicit-GEMM conv3x3 (tcgen05.mma, TMEM accumulators, TMA-fed) with bias,
+ * ReLU, row mask and optionally the 2x2 ceil-mode max-pool fused into the epilogue
+ * (CNNs.py:73-86, one call per conv).  x [B,T,F,Cin] bf16, wp [Cout][9][Cin] bf16, bias f32.
+ * Output: without POOL y [B,T,F,Cout] bf16; with POOL y [B,T2,F2,Cout] bf16, or with
+ * REF_LAYOUT y [B,T2,Cout*F2] in y_dtype (T2 = ceil(T/2), F2 = F/2).
+ * Requirements: Cin % 64 == 0, Cout % 8 == 0, F even and <= 256 (the reference's 80-bin input
+ * gives F = 80, 40, 20, 10).  Needs the CUDA driver (tensor maps are encoded per call). */
+int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, const int32_t* lengths,
+                            void* y, int y_dtype, int flags,
+                            int B, int T, int F, int Cin, int Cout, void* stream);
+
+/* ---------------------------------------------------------------- embedding tail
+ * getEmbedding's FC block, eval mode: b2(relu(fc2(relu(fc1(pooled))))) (scripts/model.py:56-57).
+ * Packing: w1t [Din,E] = fc1.weight^T, w2t [E,E] = fc2.weight^T (f32),
+ * bn_scale = b2.weight / sqrt(b2.running_var + eps), bn_shift = b2.bias - b2.running_mean*bn_scale.
+ * pooled [B,Din] f32 -> emb [B,E] f32. */
+int dasv_fc_tail_f32(const float* pooled, const float* w1t, const float* b1, const float* w2t,
+                     const float* b2, const float* bn_scale, const float* bn_shift, float* emb,
+                     int B, int Din, int E, void* stream);
+
+/* ---------------------------------------------------------------- trial scoring
+ * scoreCosineDistance = F.cosine_similarity(dim=-1, eps=1e-8) (scripts/utils.py:18-21), batched:
+ *   pairs : score[i] = cos(emb[ia[i]], emb[ib[i]])            (the trial-list form, train.py:117-133)
+ *   matrix: score[i,j] = cos(enrol[i], test[j])               (cross-product form)            */
+int dasv_cosine_pairs(const float* emb, const int32_t* ia, const int32_t* ib, float* scores,
+                      int n_pairs, int E, void* stream);
+size_t dasv_cosine_matrix_workspace_bytes(int Ne, int Nt);
+int dasv_cosine_matrix(const float* enrol, const float* test, float* scores, void* workspace,
+                       int Ne, int Nt, int E, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DASV_B200_H */

@@ -1,0 +1,107 @@
+"""GPU parity of the VGG front-end kernels: fp32 CUDA-core path (1e-4) and the bf16 tcgen05
+implicit-GEMM path (bf16 tolerances), against the numpy oracle and the live-reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, max_rel, min_cosine
+from doubleattentionspeakerverification_b200 import CNNs, ops, synth
+from oracle import path_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+
+
+@pytest.mark.parametrize('idx', range(4))
+def test_frontend_fp32_golden(idx):
+    g = golden('frontend_%d.npz' % idx)
+    front = str(g['front'])
+    K, B, T, seed = [int(v) for v in g['spec']]
+    cfg = synth.example_config(front_end=front, kernel_size=K, embedding_size=32, heads_number=8, num_spkrs=4)
+    sd = synth.make_state_dict(cfg, seed)
+    net = (CNNs.VGG3L if front == 'VGG3L' else CNNs.VGG4L)(K, precision='fp32')
+    synth.load_state_dict(net, sd, 'front_end.')
+    net = net.cuda().eval()
+    with torch.no_grad():
+        y = net(dev(synth.make_logmel(B, T, seed)))
+    assert y.shape == g['out'].shape
+    assert max_rel(y.cpu().numpy(), g['out']) < 1e-4
+
+
+def test_frontend_bf16_golden_k512():
+    g = golden('frontend_3.npz')
+    K, B, T, seed = [int(v) for v in g['spec']]
+    cfg = synth.example_config(kernel_size=K, embedding_size=32, heads_number=8, num_spkrs=4)
+    net = synth.load_state_dict(CNNs.VGG4L(K, precision='bf16'), synth.make_state_dict(cfg, seed), 'front_end.').cuda().eval()
+    assert net.resolved_precision() == 'bf16'
+    with torch.no_grad():
+        y = net(dev(synth.make_logmel(B, T, seed)))
+    assert y.dtype == torch.float32 and y.shape == g['out'].shape
+    assert min_cosine(y.cpu().numpy().reshape(B, -1), g['out'].reshape(B, -1)) > 0.9999
+    assert max_rel(y.cpu().numpy(), g['out']) < 3e-2
+
+
+CASES = [  # B, T, F, Cin, Cout, pool, ref, with_lengths
+    (1, 16, 80, 64, 64, True, False, False),
+    (2, 20, 80, 64, 128, False, False, False),
+    (2, 21, 40, 128, 128, True, False, True),
+    (3, 13, 20, 128, 256, False, False, True),
+    (3, 12, 20, 256, 256, True, False, False),
+    (5, 7, 10, 64, 192, False, False, True),
+    (5, 7, 10, 128, 264, True, True, True),
+    (4, 50, 10, 64, 128, True, True, False),
+    (1, 3, 80, 64, 8, True, False, False),
+]
+
+
+@pytest.mark.parametrize('B,T,F,Cin,Cout,pool,ref,with_len', CASES)
+def test_igemm_vs_oracle(B, T, F, Cin, Cout, pool, ref, with_len):
+    rs = np.random.RandomState(B * 100 + T + Cin)
+    x = bf16_round(np.maximum(rs.standard_normal((B, T, F, Cin)), 0).astype(np.float32))
+    w = bf16_round((rs.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32))
+    bias = (rs.standard_normal((Cout,)) * 0.1).astype(np.float32)
+    lengths = None
+    if with_len:
+        lengths = rs.randint(1, T + 1, size=(B,)).astype(np.int32)
+        lengths[0] = T
+        x = po._zero_rows(x, lengths)          # the layer's input already obeys the masking rule
+    ref_y = po._zero_rows(po.relu(po.conv3x3_same(x, w, bias)), lengths)
+    if pool:
+        ref_y = po.maxpool2x2_ceil(ref_y)
+        if ref:
+            Bq, T2, F2, C = ref_y.shape
+            ref_y = ref_y.transpose(0, 1, 3, 2).reshape(Bq, T2, C * F2)
+    y = ops.conv3x3_igemm_bf16(dev(x, torch.bfloat16), ops.pack_conv_weight_bf16(dev(w)), dev(bias), Cout,
+                               lengths=None if lengths is None else dev(lengths), pool=pool, ref_layout=ref,
+                               out_dtype=torch.float32)
+    assert tuple(y.shape) == ref_y.shape
+    # inputs are bf16-exact and accumulation is fp32: only the summation order and, for the NHWC
+    # bf16 outputs, the final rounding to bf16 (2^-9 relative) differ from the oracle
+    tol = 1e-4 if y.dtype == torch.float32 else 6e-3
+    assert max_rel(y.float().cpu().numpy(), ref_y) < tol
+
+
+def test_conv11_and_pool_kernels():
+    rs = np.random.RandomState(5)
+    x = rs.standard_normal((2, 9, 80)).astype(np.float32)
+    w = rs.standard_normal((16, 1, 3, 3)).astype(np.float32)
+    b = rs.standard_normal((16,)).astype(np.float32)
+    L = np.array([9, 4], np.int32)
+    ref = po._zero_rows(po.relu(po.conv3x3_same(po._zero_rows(x[..., None], L), w, b)), L)
+    y = ops.conv11_direct(dev(x), dev(w), dev(b), dev(L))
+    assert max_rel(y.cpu().numpy(), ref) < 1e-5
+    yb = ops.conv11_direct(dev(x), dev(w), dev(b), dev(L), out_dtype=torch.bfloat16)
+    assert max_rel(yb.float().cpu().numpy(), ref) < 6e-3
+    p = ops.maxpool2x2(y)
+    assert max_rel(p.cpu().numpy(), po.maxpool2x2_ceil(ref)) == 0.0
+    pr = ops.maxpool2x2(y, ref_layout=True)
+    pp = po.maxpool2x2_ceil(ref)
+    assert max_rel(pr.cpu().numpy(), pp.transpose(0, 1, 3, 2).reshape(2, 5, -1)) == 0.0
