@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Headline benchmark: speaker-embedding extraction throughput (embeddings/sec, 4 s utterances) of the
+exampleModel config (VGG4L K=1024 + DoubleMHA H=32 + FC/BN, E=400) on synthetic log-mel, plus the
+DoubleMHA pooling microbench (BASELINE.json configs[1]) as achieved HBM GB/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path (getEmbedding) over one batch of 256 utterances x 400 frames x 80
+bins per GPU (weak scaling: utterances are independent, sharded over ranks, no data-path collective).
+``value`` is timed with inputs resident in HBM; ``e2e`` through the public module API with pinned HOST
+input, H2D + D2H inside the timed region (and, for N > 1, the NCCL all-gather of the embeddings).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+BATCH, FRAMES, BINS = 256, 400, 80
+METRIC, UNIT = 'embeddings/sec (4 s utts)', 'embeddings/s'
+
+
+def peaks():
+    p = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            m = json.load(f)
+        p.update(hbm_gbs=float(m['hbm_gbs']), bf16_tflops=float(m['bf16_tflops']),
+                 bf16_tflops_sustained=float(m.get('bf16_tflops_sustained', m['bf16_tflops'])), source='measured')
+    except Exception:
+        pass
+    return p
+
+
+def conv_flops(batch, frames, kernel_size=1024):
+    """Algorithmic FLOPs of the VGG4L conv stack (2*MACs), per layer name."""
+    from doubleattentionspeakerverification_b200 import synth
+    out, T, F = {}, frames, BINS
+    for i, ((cin, cout), name) in enumerate(zip(synth.vgg_channels('VGG4L', kernel_size), synth.conv_names('VGG4L'))):
+        out[name] = 2.0 * batch * T * F * cout * 9 * cin
+        if i % 2 == 1:
+            T, F = (T + 1) // 2, (F + 1) // 2
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_reference_rate(target_s, threads=None):
+    """The reference's CPU path (oracle/torch_port.py: the same torch calls as scripts/model.py:52-59 on the
+    reference's layouts), exampleModel config, 4 s utterances, all host threads.  Bounded sample."""
+    from doubleattentionspeakerverification_b200 import synth
+    from oracle import torch_port as tp
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = synth.example_config()
+    sd = tp.as_torch(synth.make_state_dict(cfg, 1234))
+    nb = 4
+    x = torch.from_numpy(synth.make_logmel(nb, FRAMES, 7))
+    tp.get_embedding(x[:1], sd, cfg)                      # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        tp.get_embedding(x, sd, cfg)
+        n += nb
+        el = time.perf_counter() - t0
+        if el >= target_s or n >= BATCH:
+            break
+    return n / el, n, el, threads
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    per_step = []
+    total_budget = 60.0
+    step_s = max(1.0, total_budget / max(1, args.steps + args.warmup))
+    for i in range(args.warmup + args.steps):
+        rate, n, el, threads = cpu_reference_rate(step_s)
+        if i >= args.warmup:
+            per_step.append((n, el))
+    n_tot = sum(n for n, _ in per_step)
+    t_tot = sum(t for _, t in per_step)
+    value = n_tot / t_tot
+    sample = '%d utterances of the 256 x 400-frame batch per step (bounded CPU sample), fp32, %d torch threads' % (
+        per_step[0][0], threads)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / len(per_step), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'full embedding extraction VGG4L(K=1024)+DoubleMHA(H=32)+FC(E=400), 4 s (400x80) log-mel '
+                                   'utterances, random-init (BASELINE configs[2])', 'batch_per_gpu': BATCH},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-dmha', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl b200 needs a CUDA device (there is no CPU fallback)')
+    from doubleattentionspeakerverification_b200 import _lib, model, ops, synth
+    _lib.lib()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    pk = peaks()
+
+    cfg = synth.example_config()
+    cfg.precision = args.precision
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, dev), synth.make_state_dict(cfg, 1234)).to(dev).eval()
+    Bn = args.batch
+    xs = [torch.from_numpy(synth.make_logmel(Bn, FRAMES, seed=100 + rank * 7 + i)).to(dev) for i in range(2)]
+    x_host = torch.from_numpy(synth.make_logmel(Bn, FRAMES, seed=300 + rank)).pin_memory()
+    x_stage = torch.empty_like(xs[0])
+    emb_host = torch.empty((Bn, cfg.embedding_size), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * Bn, cfg.embedding_size), device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_resident(i):
+        with torch.no_grad():
+            return net.getEmbedding(xs[i & 1])
+
+    def step_e2e(i):
+        with torch.no_grad():
+            x_stage.copy_(x_host, non_blocking=True)
+            emb = net.getEmbedding(x_stage)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, emb)
+            emb_host.copy_(emb, non_blocking=True)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(ms)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    _lib.LAUNCHES.clear()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps)
+    launches = sum(_lib.LAUNCHES.values())
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    value = world * Bn * args.steps / (ms * 1e-3)
+    e2e_value = world * Bn * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (conv3x3_igemm: tensor-bound), timed per launch inside real steps
+    roof = None
+    if args.precision == 'bf16':
+        fl = conv_flops(Bn, FRAMES)
+        names = [n for n in synth.conv_names('VGG4L')][1:]
+        rec = []
+        orig = ops.conv3x3_igemm_bf16
+
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = orig(*a, **k)
+            e1.record()
+            rec.append((e0, e1))
+            return y
+
+        ops.conv3x3_igemm_bf16 = wrapped
+        nsteps = max(3, min(args.steps, 10))
+        for i in range(nsteps):
+            step_resident(i)
+        torch.cuda.synchronize()
+        ops.conv3x3_igemm_bf16 = orig
+        per_layer = {n: 0.0 for n in names}
+        for j, (e0, e1) in enumerate(rec):
+            per_layer[names[j % len(names)]] += e0.elapsed_time(e1) / nsteps
+        conv_ms = sum(per_layer.values())
+        conv_fl = sum(fl[n] for n in names)
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'conv3x3_igemm_kernel (7 launches per step, conv12..conv42)',
+                'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['bf16_tflops_sustained'], 'peak_source': pk['source'] + ' sustained cuBLAS bf16',
+                'traffic': None, 'avg_launch_ms': conv_ms / len(names), 'share_of_step': conv_ms / (ms / args.steps),
+                'per_layer_tflops': {n: fl[n] / (per_layer[n] * 1e-3) / 1e12 for n in names}}
+
+    # ---- DoubleMHA pooling microbench (BASELINE configs[1]): B=512, T=200, D=1024, H=16, length-masked
+    dmha = None
+    if not args.no_dmha and rank == 0:
+        dmha = {}
+        Bp, Tp, Dp, Hp = 512, 200, 1024, 16
+        gen = torch.Generator(device=dev).manual_seed(0)
+        q = torch.randn(Dp // Hp, Hp, device=dev, generator=gen) * 0.3
+        a = torch.randn(Dp // Hp, device=dev, generator=gen) * 0.3
+        lens = torch.from_numpy(synth.make_lengths(Bp, 100, 200, seed=0)).to(dev)
+        for dt_name, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16)):
+            bufs = [torch.randn(Bp, Tp, Dp, device=dev, generator=gen).to(dt) for _ in range(2)]   # 2 x 419 MB fp32 >> L2
+            es = dt.itemsize if hasattr(dt, 'itemsize') else (4 if dt == torch.float32 else 2)
+            for case, L in (('full', None), ('masked', lens)):
+                nbytes = (Bp * Tp if L is None else int(L.sum().item())) * Dp * es + Bp * (Dp // Hp) * 4
+                for i in range(3):
+                    ops.dmha_fwd(bufs[i & 1], q, a, lengths=L, need_align=False)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                reps = 20
+                e0.record()
+                for i in range(reps):
+                    ops.dmha_fwd(bufs[i & 1], q, a, lengths=L, need_align=False)
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / reps
+                gbs = nbytes / (us * 1e-6) / 1e9
+                dmha['%s_%s' % (dt_name, case)] = {'us': us, 'gbs': gbs, 'frac': gbs / pk['hbm_gbs'], 'bytes': nbytes}
+            del bufs
+        dmha['peak_gbs'] = pk['hbm_gbs']
+        dmha['shape'] = 'B=512 T=200 D=1024 H=16; 2 rotating inputs (each > L2); no alignment output'
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, n, el, threads = cpu_reference_rate(15.0)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': '%d utterances (400x80) in %.1f s through oracle/torch_port.get_embedding, fp32' % (n, el)}
+
+    if rank == 0:
+        h2d = x_host.numel() * 4
+        d2h = emb_host.numel() * 4
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+                'config': {'workload': 'full embedding extraction VGG4L(K=1024)+DoubleMHA(H=32)+FC(E=400), 4 s (400x80) log-mel '
+                                       'utterances, random-init (BASELINE configs[2])', 'batch_per_gpu': Bn,
+                           'parallelism': 'dp%d' % world, 'l2': 'two rotating input batches; per-step intermediates (>3 GB) exceed the 126 MB L2'},
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'ms_per_step': ms_e2e / args.steps},
+                'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'dmha_microbench': dmha, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

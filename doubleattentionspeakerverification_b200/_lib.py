@@ -35,6 +35,10 @@ SIGNATURES = {
 
 _LIB = None
 
+# kernels launched per successful C call, and the running count bench.py reports as gpu_launches
+KERNELS_PER_CALL = {'dasv_dmha_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
+LAUNCHES = {}
+
 
 class DasvError(RuntimeError):
     pass
@@ -60,3 +64,4 @@ def check(rc, what):
     if rc != 0:
         msg = lib().dasv_last_error()
         raise DasvError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else '?'))
+    LAUNCHES[what] = LAUNCHES.get(what, 0) + KERNELS_PER_CALL.get(what, 1)

@@ -9,68 +9,73 @@
 namespace dasv {
 
 // ------------------------------------------------------------------------------ conv11 direct
-// One CTA per (b, t) row.  Thread item = (f, 8-channel group); 9 taps x 8 channels of FMAs.
+// One CTA per (b, chunk of kC11Rows frames).  A thread owns 8 output channels: their 9x8 weights and bias
+// live in registers for the whole chunk, so the inner loop is 9 broadcast LDS + 72 FMA per pixel and the
+// kernel is bound by its NHWC output write (the layer's only real traffic).  Threads are laid out
+// (channel group fastest), so the 16-byte stores of neighbouring threads form one contiguous run.
+constexpr int kC11Rows = 8;
+
 template <bool OUT_BF16>
 __global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const int32_t* __restrict__ lengths,
                                                            void* __restrict__ y, int B, int T, int F, int Cout) {
-    extern __shared__ float sm[];
-    float* w_sm = sm;                     // [9][Cout]
-    float* b_sm = w_sm + 9 * Cout;        // [Cout]
-    float* x_sm = b_sm + Cout;            // [3][F+2]
-    const int bt = blockIdx.x;
-    const int b = bt / T, t = bt - b * T;
+    extern __shared__ float x_sm[];       // [kC11Rows + 2][F + 2], zero halo
+    const int chunks = (T + kC11Rows - 1) / kC11Rows;
+    const int b = blockIdx.x / chunks, t0 = (blockIdx.x - b * chunks) * kC11Rows;
     const int L = lengths ? min(max(lengths[b], 0), T) : T;
+    const int rows = min(kC11Rows, T - t0);
     const int CG = Cout / 8;
-    const size_t row_elems = static_cast<size_t>(F) * Cout;
-    if (t >= L) {   // masked row: zeros
-        if (OUT_BF16) {
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + bt * row_elems);
-            for (int i = threadIdx.x; i < F * CG; i += blockDim.x) o[i] = make_uint4(0, 0, 0, 0);
-        } else {
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(y) + bt * row_elems);
-            for (int i = threadIdx.x; i < F * CG * 2; i += blockDim.x) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        return;
-    }
-    for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
-        const int tap = i / Cout, c = i - tap * Cout;
-        w_sm[i] = w[c * 9 + tap];         // reference layout [Cout,1,3,3]
-    }
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) b_sm[i] = bias[i];
-    for (int i = threadIdx.x; i < 3 * (F + 2); i += blockDim.x) {
-        const int r = i / (F + 2), fc = i - r * (F + 2);
-        const int tt = t + r - 1, ff = fc - 1;
+    const int PL = 256 / CG;                                  // pixel lanes (CG <= 256 checked by the host)
+    const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+    const bool active = pl < PL;
+    const int W2 = F + 2;
+
+    for (int i = threadIdx.x; i < (kC11Rows + 2) * W2; i += blockDim.x) {
+        const int r = i / W2, fc = i - r * W2;
+        const int tt = t0 + r - 1, ff = fc - 1;
         float v = 0.f;
         if (tt >= 0 && tt < L && ff >= 0 && ff < F) v = x[(static_cast<size_t>(b) * T + tt) * F + ff];
-        x_sm[i] = v;                      // rows >= L of the input are treated as zero (masking rule)
+        x_sm[i] = v;                      // input rows >= L count as zero (masking rule)
+    }
+    float wr[9][8], br[8];
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            br[e] = bias[cg * 8 + e];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) wr[tap][e] = w[(cg * 8 + e) * 9 + tap];   // reference layout [Cout,1,3,3]
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < F * CG; i += blockDim.x) {
-        const int f = i / CG, cg = i - f * CG;
+    if (!active) return;
+    const size_t row_elems = static_cast<size_t>(F) * Cout;
+    for (int p = pl; p < rows * F; p += PL) {
+        const int tl = p / F, f = p - tl * F;
+        const int t = t0 + tl;
         float acc[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = b_sm[cg * 8 + e];
+        for (int e = 0; e < 8; ++e) acc[e] = br[e];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const float xv = x_sm[dy * (F + 2) + f + dx];
-                const float* wr = w_sm + (dy * 3 + dx) * Cout + cg * 8;
+                const float xv = x_sm[(tl + dy) * W2 + f + dx];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, wr[e], acc[e]);
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, wr[dy * 3 + dx][e], acc[e]);
             }
+        const bool valid = t < L;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+        for (int e = 0; e < 8; ++e) acc[e] = valid ? fmaxf(acc[e], 0.f) : 0.f;
+        const size_t o = (static_cast<size_t>(b) * T + t) * row_elems + static_cast<size_t>(f) * Cout + cg * 8;
         if (OUT_BF16) {
             uint4 v;
             v.x = pack_bf16(acc[0], acc[1]); v.y = pack_bf16(acc[2], acc[3]);
             v.z = pack_bf16(acc[4], acc[5]); v.w = pack_bf16(acc[6], acc[7]);
-            reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + bt * row_elems)[i] = v;
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + o) = v;
         } else {
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(y) + bt * row_elems);
-            o[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            o[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(y) + o);
+            op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
     }
 }
@@ -213,11 +218,15 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
     if (!x || !w || !bias || !y) { set_error("conv11_direct: null argument"); return 1; }
     if (Cout % 8 != 0 || Cout <= 0) { set_error("conv11_direct: Cout=%d must be a positive multiple of 8", Cout); return 1; }
     if (y_dtype != 0 && y_dtype != 1) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
+    if (Cout > 2048) { set_error("conv11_direct: Cout=%d > 2048", Cout); return 1; }
     if (B <= 0 || T <= 0) return 0;
-    const size_t smem = (static_cast<size_t>(10) * Cout + 3 * (F + 2)) * sizeof(float);
+    const size_t smem = static_cast<size_t>(kC11Rows + 2) * (F + 2) * sizeof(float);
+    if (smem > 48 * 1024) { set_error("conv11_direct: F=%d too wide", F); return 1; }
+    const int chunks = (T + kC11Rows - 1) / kC11Rows;
+    const unsigned grid = static_cast<unsigned>(B) * chunks;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (y_dtype == 1) conv11_direct_kernel<true><<<B * T, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
-    else conv11_direct_kernel<false><<<B * T, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
+    if (y_dtype == 1) conv11_direct_kernel<true><<<grid, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
+    else conv11_direct_kernel<false><<<grid, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
     return check_launch("conv11_direct");
 }
 

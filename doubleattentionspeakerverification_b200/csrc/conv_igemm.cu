@@ -24,6 +24,8 @@ constexpr int kConvThreads = 256;
 constexpr int kConvTileM = 128;                 // output channels per CTA tile = TMEM lanes
 constexpr int kConvKC = 64;                     // channels per K slice (64 bf16 = one 128-byte swizzle row)
 constexpr uint32_t kConvABytes = kConvTileM * kConvKC * 2;
+constexpr int kConvEpiChunk = 64;               // output pixels staged per epilogue chunk
+constexpr uint32_t kConvEpiBytes = kConvEpiChunk * kConvTileM * 2;   // [64][128] bf16, double-buffered
 
 struct ConvParams {
     const float* bias;
@@ -94,7 +96,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     unsigned char* ring = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes);
+    unsigned char* stage = smem + static_cast<size_t>(p.stages) * p.stage_bytes;     // epilogue staging, 2 x kConvEpiBytes
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + 2 * kConvEpiBytes);
     uint64_t* empty = full + p.stages;
     uint64_t* acc_full = empty + p.stages;      // [2]
     uint64_t* acc_empty = acc_full + 2;         // [2]
@@ -166,17 +169,26 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------ epilogue (TMEM -> regs -> HBM)
+        // ------------------------------------------------------------ epilogue (TMEM -> regs -> SMEM -> HBM)
+        // A thread owns one output channel (its TMEM lane).  NHWC outputs go through a [64 pixels][128 ch]
+        // bf16 staging tile so that the global stores are 16-byte, fully coalesced runs of 256 B per pixel;
+        // the final layer's [B,T',C*F'] fp32 output is already contiguous per thread and is stored directly.
         const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+        const int et = threadIdx.x - 128;                       // 0..127
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int T = p.T, F = p.F, Cout = p.Cout, BF = p.BF, BT = p.BT;
         const int T2 = (T + 1) / 2, F2 = F / 2;
-        uint32_t acc_it = 0;
+        const int OBF = p.pool ? BF / 2 : BF, OBT = p.pool ? BT / 2 : BT;   // output patch
+        const int OT = p.pool ? T2 : T, OF = p.pool ? F2 : F;
+        const int NO = p.BB * OBT * OBF;                        // output pixels per tile
+        const int ch = q * 32 + lane;                           // channel within the 128-wide tile
+        uint32_t acc_it = 0, chunk_it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const ConvTile c = conv_decode_tile(p, tile);
-            const int n = c.m * kConvTileM + q * 32 + lane;
+            const int n = c.m * kConvTileM + ch;
             const bool n_ok = n < Cout;
             const bool masked = conv_tile_masked(p, c);
+            const int ot0 = p.pool ? (c.t0 >> 1) : c.t0, of0 = p.pool ? (c.f0 >> 1) : c.f0;
             uint32_t tcol = 0;
             if (!masked) {
                 const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
@@ -185,28 +197,9 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tcol = tmem_base + lane_addr + as * static_cast<uint32_t>(p.Npad);
             }
             const float bias = n_ok ? p.bias[n] : 0.f;
-            if (!p.pool) {
-                // y[b, t, f, n] = relu(acc + bias), zero for t >= L
-                for (int j0 = 0; j0 < p.N; j0 += 16) {
-                    uint32_t r[16];
-                    if (!masked) { tmem_ld_x16(tcol + j0, r); tc_wait_ld(); }
-                    int bb = j0 / (BT * BF), rem = j0 - bb * (BT * BF);
-                    int tl = rem / BF, fl = rem - tl * BF;
-                    int Lb = conv_len(p, c.b0 + bb);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j0 + j < p.N) {
-                            const int b = c.b0 + bb, t = c.t0 + tl, f = c.f0 + fl;
-                            if (n_ok && b < p.B && t < T) {
-                                const float v = (!masked && t < Lb) ? fmaxf(__uint_as_float(r[j]) + bias, 0.f) : 0.f;
-                                conv_store<false>(p.y, ((static_cast<size_t>(b) * T + t) * F + f) * Cout + n, v);
-                            }
-                            if (++fl == BF) { fl = 0; if (++tl == BT) { tl = 0; ++bb; Lb = conv_len(p, c.b0 + bb); } }
-                        }
-                    }
-                }
-            } else {
-                // pooled[b, t2, f2, n] = relu(max over the valid 2x2 window + bias)   (max and +bias/ReLU commute)
+
+            if (p.ref_layout) {
+                // pooled[b, t2, n*F2 + f2] = relu(max over the valid 2x2 window + bias)   (feature = c*F' + f, CNNs.py:88-89)
                 for (int bb = 0; bb < p.BB; ++bb) {
                     const int b = c.b0 + bb;
                     const int Lb = conv_len(p, b);
@@ -215,7 +208,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         if (b >= p.B || t >= T) continue;       // warp-uniform
                         const bool r0_ok = !masked && t < Lb, r1_ok = !masked && (t + 1) < Lb;
                         const uint32_t col0 = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF);
-                        const int t2 = t >> 1;
+                        const size_t row = (static_cast<size_t>(b) * T2 + (t >> 1)) * (static_cast<size_t>(Cout) * F2) +
+                                           static_cast<size_t>(n) * F2 + (c.f0 >> 1);
                         for (int fp0 = 0; fp0 < BF / 2; fp0 += 4) {
                             uint32_t v[4][4];
 #pragma unroll
@@ -235,25 +229,95 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                         if (r1_ok) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
                                         m = fmaxf(m + bias, 0.f);
                                     }
-                                    const int f2 = (c.f0 >> 1) + fp0 + u;
-                                    if (p.ref_layout) {
-                                        const size_t idx = (static_cast<size_t>(b) * T2 + t2) * (static_cast<size_t>(Cout) * F2) +
-                                                           static_cast<size_t>(n) * F2 + f2;      // feature = c*F' + f (CNNs.py:88-89)
-                                        if (p.y_f32) conv_store<true>(p.y, idx, m); else conv_store<false>(p.y, idx, m);
-                                    } else {
-                                        conv_store<false>(p.y, ((static_cast<size_t>(b) * T2 + t2) * F2 + f2) * Cout + n, m);
-                                    }
+                                    if (p.y_f32) conv_store<true>(p.y, row + fp0 + u, m); else conv_store<false>(p.y, row + fp0 + u, m);
                                 }
                             }
                         }
                     }
                 }
+                if (!masked) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
+                    ++acc_it;
+                }
+                continue;
             }
-            if (!masked) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
-                ++acc_it;
+
+            // ---------------- NHWC bf16 output, in chunks of kConvEpiChunk output pixels
+            for (int o0 = 0; o0 < NO; o0 += kConvEpiChunk) {
+                const int cnt = min(kConvEpiChunk, NO - o0);
+                unsigned char* buf = stage + (chunk_it & 1u) * kConvEpiBytes;
+                if (!masked) {
+                    // phase 1: this thread's channel of `cnt` output pixels -> staging[pixel][ch]
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + ch;
+                    if (!p.pool) {
+                        for (int j0 = 0; j0 < cnt; j0 += 16) {
+                            uint32_t r[16];
+                            tmem_ld_x16(tcol + o0 + j0, r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j0 + j < cnt)
+                                    dst[(j0 + j) * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias, 0.f));
+                        }
+                    } else {
+                        // output o -> (bb, tp, fp); window columns (bb*BT + 2tp)*BF + 2fp (+1, +BF, +BF+1)
+                        int bb = o0 / (OBT * OBF), rem = o0 - bb * (OBT * OBF);
+                        int tp = rem / OBF, fp = rem - tp * OBF;
+                        for (int j0 = 0; j0 < cnt; j0 += 4) {
+                            uint32_t v[4][4];
+                            bool r1[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (j0 + u < cnt) {             // warp-uniform
+                                    const uint32_t col = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF + 2 * fp);
+                                    r1[u] = (c.t0 + 2 * tp + 1) < conv_len(p, c.b0 + bb);   // ceil-mode / masked second row
+                                    tmem_ld_x2(col, v[u][0], v[u][1]);
+                                    tmem_ld_x2(col + BF, v[u][2], v[u][3]);
+                                    if (++fp == OBF) { fp = 0; if (++tp == OBT) { tp = 0; ++bb; } }
+                                }
+                            }
+                            tc_wait_ld();
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (j0 + u < cnt) {
+                                    float m = fmaxf(__uint_as_float(v[u][0]), __uint_as_float(v[u][1]));
+                                    if (r1[u]) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
+                                    dst[(j0 + u) * kConvTileM] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));   // max and +bias/ReLU commute
+                                }
+                            }
+                        }
+                    }
+                    if (o0 + kConvEpiChunk >= NO) {             // all TMEM reads of this tile are done: release the accumulator
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
+                        ++acc_it;
+                    }
+                    named_bar_sync(1, 128);
+                }
+                // phase 2: 16 threads per pixel copy 256 B runs to y (zeros for masked frames)
+                {
+                    const int seg = et & 15;
+                    const bool seg_ok = c.m * kConvTileM + seg * 8 < Cout;
+                    for (int po = et >> 4; po < cnt; po += 8) {
+                        const int o = o0 + po;
+                        const int bb = o / (OBT * OBF), rem = o - bb * (OBT * OBF);
+                        const int tl = rem / OBF, fl = rem - tl * OBF;
+                        const int b = c.b0 + bb, to = ot0 + tl, fo = of0 + fl;
+                        if (b < p.B && to < OT && seg_ok) {
+                            const int t_in = p.pool ? 2 * to : to;
+                            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                            if (!masked && t_in < conv_len(p, b))
+                                val = *reinterpret_cast<const uint4*>(buf + po * (kConvTileM * 2) + seg * 16);
+                            __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) +
+                                                ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c.m * kConvTileM + seg * 8;
+                            *reinterpret_cast<uint4*>(yp) = val;
+                        }
+                    }
+                }
+                if (!masked) ++chunk_it;
             }
         }
     }
@@ -371,7 +435,8 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
     p.b_bytes = static_cast<uint32_t>(pl.N) * 128u;
     p.stage_bytes = kConvABytes + ((static_cast<uint32_t>(pl.Npad) * 128u + 1023u) & ~1023u);
-    int stages = static_cast<int>((220u * 1024u) / p.stage_bytes);
+    const uint32_t kFixed = 2 * kConvEpiBytes + 1024 + 512;     // staging + alignment slack + barriers
+    int stages = static_cast<int>((227u * 1024u - kFixed) / p.stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv3x3_igemm_bf16: ring does not fit shared memory"); return 1; }
     p.stages = stages;
@@ -381,7 +446,7 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     const long long n_tiles = static_cast<long long>(p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
     if (n_tiles > 0x7fffffffLL) { set_error("conv3x3_igemm_bf16: too many tiles"); return 1; }
 
-    const size_t smem = static_cast<size_t>(stages) * p.stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    const size_t smem = static_cast<size_t>(stages) * p.stage_bytes + kFixed;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
     int dev = 0, sms = 0;

@@ -374,26 +374,27 @@ extern "C" int dasv_dmha_bwd(const void* x, int x_dtype, const int32_t* lengths,
                              const float* ctx, const float* lse, const float* headw,
                              void* dx, float* dquery, float* datt, void* workspace,
                              int B, int T, int D, int H, void* stream) {
+    if (B <= 0) return 0;
     if (!x || !query || !ctx || !lse || !dx || !dquery || !workspace) { set_error("dmha_bwd: null argument"); return 1; }
     if (x_dtype != 0 && x_dtype != 1) { set_error("dmha_bwd: bad dtype %d", x_dtype); return 1; }
     if (att != nullptr && (!g_out || !headw || !datt)) { set_error("dmha_bwd: att given but g_out/headw/datt missing"); return 1; }
     if (att == nullptr && !g_ctx) { set_error("dmha_bwd: MultiHeadAttention-only mode needs g_ctx"); return 1; }
-    if (B <= 0) return 0;
-    const DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, true);
+    DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, true);
     if (pl.err) { set_error("dmha_bwd: unsupported shape D=%d H=%d dtype=%d (plan error %d)", D, H, x_dtype, pl.err); return 1; }
     DmhaBwdParams p{};
     p.x = static_cast<const unsigned char*>(x);
     p.lengths = lengths; p.query = query; p.att = att; p.g_out = g_out; p.g_ctx = g_ctx;
     p.ctx = ctx; p.lse = lse; p.headw = headw; p.dx = static_cast<unsigned char*>(dx);
     p.B = B; p.T = T; p.D = D; p.H = H; p.dh = D / H;
-    p.fps = pl.fps; p.stages = pl.stages; p.S = pl.S;
     p.inv_sqrt_h = 1.0f / sqrtf(static_cast<float>(H));
     p.scale_log2 = kLog2e * p.inv_sqrt_h;
     const size_t parts = static_cast<size_t>(B < kDmhaBwdMaxGrid ? B : kDmhaBwdMaxGrid);
     p.ws_dq = static_cast<float*>(workspace);
     p.ws_da = p.ws_dq + parts * D;
     const uint32_t stage_bytes = static_cast<uint32_t>(pl.fps) * D * (pl.bf16 ? 2 : 4);
-    const size_t smem = dmha_bwd_smem(D, H, p.dh, pl.stages, stage_bytes).total;
+    size_t smem = dmha_bwd_smem(D, H, p.dh, pl.stages, stage_bytes).total;
+    while (smem > 227 * 1024 && pl.stages > 2) smem = dmha_bwd_smem(D, H, p.dh, --pl.stages, stage_bytes).total;   // very wide features: shallower ring
+    p.fps = pl.fps; p.stages = pl.stages; p.S = pl.S;
     if (smem > 227 * 1024) { set_error("dmha_bwd: D=%d needs %zu B of shared memory (> 227 KB)", D, smem); return 1; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return pl.bf16 ? dispatch_bwd<true>(pl, p, smem, dquery, datt, s) : dispatch_bwd<false>(pl, p, smem, dquery, datt, s);

@@ -386,15 +386,15 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
                              const float* query, const float* att, const uint8_t* keep,
                              float* out, float* ctx, float* lse, float* headw, float* align,
                              int B, int T, int D, int H, void* stream) {
+    if (B < 0 || T < 0) { set_error("dmha_fwd: negative shape"); return 1; }
+    if (B == 0) return 0;
     if (x == nullptr || query == nullptr) { set_error("dmha_fwd: null x/query"); return 1; }
     if (x_dtype != 0 && x_dtype != 1) { set_error("dmha_fwd: bad dtype %d", x_dtype); return 1; }
-    if (B < 0 || T < 0) { set_error("dmha_fwd: negative shape"); return 1; }
     if (att == nullptr && (out != nullptr || headw != nullptr)) {
         set_error("dmha_fwd: out/headw need att (att==NULL selects the MultiHeadAttention-only mode)");
         return 1;
     }
-    if (B == 0) return 0;
-    const DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, false);
+    DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, false);
     if (pl.err) {
         set_error("dmha_fwd: unsupported shape D=%d H=%d dtype=%d (plan error %d: need D%%H==0, "
                   "head size multiple of %d and <= 512 elements per 32 lanes, H <= 4*groups)",
@@ -406,10 +406,11 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
     p.lengths = lengths; p.query = query; p.att = att; p.keep = keep;
     p.out = out; p.ctx = ctx; p.lse = lse; p.headw = headw; p.align = align;
     p.B = B; p.T = T; p.D = D; p.H = H; p.dh = D / H;
-    p.fps = pl.fps; p.stages = pl.stages; p.S = pl.S;
     p.scale_log2 = kLog2e / sqrtf(static_cast<float>(H));     // d_k = query.size(-1) = H (poolings.py:75)
     const uint32_t stage_bytes = static_cast<uint32_t>(pl.fps) * D * (pl.bf16 ? 2 : 4);
-    const size_t smem = dmha_fwd_smem(D, H, p.dh, pl.S, pl.stages, stage_bytes).total;
+    size_t smem = dmha_fwd_smem(D, H, p.dh, pl.S, pl.stages, stage_bytes).total;
+    while (smem > 227 * 1024 && pl.stages > 2) smem = dmha_fwd_smem(D, H, p.dh, pl.S, --pl.stages, stage_bytes).total;   // very wide features: shallower ring
+    p.fps = pl.fps; p.stages = pl.stages; p.S = pl.S;
     if (smem > 227 * 1024) { set_error("dmha_fwd: D=%d needs %zu B of shared memory (> 227 KB)", D, smem); return 1; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return pl.bf16 ? dispatch_fwd<true>(pl, p, smem, s) : dispatch_fwd<false>(pl, p, smem, s);

@@ -10,9 +10,9 @@
 
 namespace dasv {
 
-constexpr int kTailUPB = 8;
+constexpr int kTailUPB = 4;
 
-__global__ void __launch_bounds__(256) fc_tail_kernel(const float* __restrict__ pooled, const float* __restrict__ w1t,
+__global__ void __launch_bounds__(512) fc_tail_kernel(const float* __restrict__ pooled, const float* __restrict__ w1t,
                                                      const float* __restrict__ b1, const float* __restrict__ w2t,
                                                      const float* __restrict__ b2, const float* __restrict__ bn_scale,
                                                      const float* __restrict__ bn_shift, float* __restrict__ emb,
@@ -31,7 +31,17 @@ __global__ void __launch_bounds__(256) fc_tail_kernel(const float* __restrict__ 
         float acc[kTailUPB];
 #pragma unroll
         for (int u = 0; u < kTailUPB; ++u) acc[u] = 0.f;
-        for (int d = 0; d < Din; ++d) {
+        int d = 0;
+        for (; d + 8 <= Din; d += 8) {          // 8 independent weight loads in flight per thread
+            float w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = w1t[static_cast<size_t>(d + k) * E + e];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(in_sm[u * Din + d + k], w[k], acc[u]);
+        }
+        for (; d < Din; ++d) {
             const float w = w1t[static_cast<size_t>(d) * E + e];
 #pragma unroll
             for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(in_sm[u * Din + d], w, acc[u]);
@@ -45,7 +55,17 @@ __global__ void __launch_bounds__(256) fc_tail_kernel(const float* __restrict__ 
         float acc[kTailUPB];
 #pragma unroll
         for (int u = 0; u < kTailUPB; ++u) acc[u] = 0.f;
-        for (int d = 0; d < E; ++d) {
+        int d = 0;
+        for (; d + 8 <= E; d += 8) {
+            float w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = w2t[static_cast<size_t>(d + k) * E + e];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(h_sm[u * E + d + k], w[k], acc[u]);
+        }
+        for (; d < E; ++d) {
             const float w = w2t[static_cast<size_t>(d) * E + e];
 #pragma unroll
             for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(h_sm[u * E + d], w, acc[u]);
@@ -216,7 +236,7 @@ extern "C" int dasv_fc_tail_f32(const float* pooled, const float* w1t, const flo
     if (smem > 200 * 1024) { set_error("fc_tail: Din=%d E=%d need %zu B of shared memory", Din, E, smem); return 1; }
     cudaError_t e = cudaFuncSetAttribute(fc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("fc_tail: smem attribute: %s", cudaGetErrorString(e)); return 1; }
-    fc_tail_kernel<<<(B + kTailUPB - 1) / kTailUPB, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    fc_tail_kernel<<<(B + kTailUPB - 1) / kTailUPB, 512, smem, static_cast<cudaStream_t>(stream)>>>(
         pooled, w1t, b1, w2t, b2, bn_scale, bn_shift, emb, B, Din, E);
     return check_launch("fc_tail");
 }

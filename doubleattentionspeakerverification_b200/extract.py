@@ -1,0 +1,119 @@
+"""Batched, variable-length, data-parallel embedding extraction and trial scoring.
+
+Replaces the reference's validation loop (scripts/train.py:117-133: two batch-1 forwards and one
+``.item()`` sync per trial line) with: every unique utterance embedded once, in padded + length-masked
+batches (SURVEY.md §5.7 masking rule => identical to per-utterance batch-1 results), utterances sharded
+over the ranks of one ``torchrun`` job (one process per GPU), ONE all-gather of the ``[N/R, E]`` embedding
+shards, then batched cosine scoring.  Utterances are independent, so there is no other collective.
+
+The host logic here (sharding plan, batching, order restoration) is device-agnostic and covered by
+world_size-2 ``gloo`` tests on CPU with a stub embedder; the product embedder is
+``SpeakerClassifier.getEmbedding`` on CUDA.
+"""
+import numpy as np
+import torch
+
+from . import utils
+
+
+def shard_plan(lengths, world):
+    """Length-sorted snake deal: sort utterances by decreasing length and deal them to ranks 0..R-1, R-1..0,
+    ..., so every rank gets the same number (±1) and nearly the same total frames.  Returns ``[index arrays]``
+    per rank (each sorted by decreasing length).  Deterministic: every rank computes the same plan."""
+    lengths = np.asarray(lengths)
+    order = np.argsort(-lengths, kind='stable')
+    pos = np.arange(len(order))
+    rnd, col = pos // world, pos % world
+    owner = np.where(rnd % 2 == 0, col, world - 1 - col)
+    return [order[owner == r] for r in range(world)]
+
+
+def batch_plan(lengths, max_frames, max_batch=None, multiple=1):
+    """Greedy batches over a length-sorted index list: a batch's padded size (its longest utterance rounded
+    up to ``multiple`` x its count) stays <= max_frames.  Returns a list of index arrays."""
+    idx = np.argsort(-np.asarray(lengths), kind='stable')
+    batches, cur = [], []
+    for i in idx:
+        Tpad = -(-int(lengths[cur[0]] if cur else lengths[i]) // multiple) * multiple
+        if cur and ((len(cur) + 1) * Tpad > max_frames or (max_batch and len(cur) >= max_batch)):
+            batches.append(np.array(cur))
+            cur = []
+        cur.append(int(i))
+    if cur:
+        batches.append(np.array(cur))
+    return batches
+
+
+def pad_batch(feats, idx, multiple=1):
+    """Stack ``feats[i]`` (``[T_i, F]`` arrays) into a zero-padded ``[len(idx), Tmax, F]`` float32 array + lengths."""
+    L = np.array([feats[i].shape[0] for i in idx], np.int32)
+    Tmax = -(-int(L.max()) // multiple) * multiple
+    x = np.zeros((len(idx), Tmax, feats[idx[0]].shape[1]), np.float32)
+    for j, i in enumerate(idx):
+        x[j, :L[j]] = feats[i]
+    return x, L
+
+
+def extract_local(embed_fn, feats, indices, device, max_frames=256 * 400, max_batch=None):
+    """Embed ``feats[i] for i in indices`` in padded, length-masked batches.  ``embed_fn(x [B,T,F], lengths [B])
+    -> [B,E]`` (e.g. ``net.getEmbedding``).  Returns ``[len(indices), E]`` in the order of ``indices``."""
+    indices = np.asarray(indices)
+    if len(indices) == 0:
+        return None
+    lengths = np.array([feats[i].shape[0] for i in indices])
+    out = None
+    for b in batch_plan(lengths, max_frames, max_batch):
+        x, L = pad_batch(feats, indices[b])
+        xt = torch.from_numpy(x)
+        if torch.device(device).type == 'cuda':
+            xt = xt.pin_memory().to(device, non_blocking=True)
+        emb = embed_fn(xt, torch.from_numpy(L).to(device))
+        if out is None:
+            out = torch.empty((len(indices), emb.shape[1]), device=emb.device, dtype=emb.dtype)
+        out[torch.from_numpy(b).to(emb.device)] = emb
+    return out
+
+
+def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, max_batch=None, embedding_size=None):
+    """Every rank embeds its shard, then one all-gather; returns ``[N, E]`` embeddings of ALL utterances, in
+    the original order, on every rank.  Without an initialised process group it is the single-GPU path."""
+    import torch.distributed as dist
+    N = len(feats)
+    lengths = np.array([f.shape[0] for f in feats])
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    plan = shard_plan(lengths, world)
+    local = extract_local(embed_fn, feats, plan[rank], device, max_frames, max_batch)
+    if world == 1:
+        out = torch.empty_like(local)
+        out[torch.from_numpy(plan[0]).to(local.device)] = local
+        return out
+    per = max(len(p) for p in plan)                       # shards differ by at most one utterance: pad to equal
+    E = local.shape[1] if local is not None else embedding_size
+    if E is None:
+        raise ValueError('a rank with an empty shard needs embedding_size')
+    send = torch.zeros((per, E), device=device, dtype=torch.float32)
+    if local is not None:
+        send[:local.shape[0]] = local
+    recv = torch.empty((world * per, E), device=device, dtype=torch.float32)
+    dist.all_gather_into_tensor(recv, send, group=group)   # the path's only collective (NCCL over NVLink on GPUs)
+    out = torch.empty((N, E), device=device, dtype=torch.float32)
+    for r in range(world):
+        n = len(plan[r])
+        if n:
+            out[torch.from_numpy(plan[r]).to(device)] = recv[r * per:r * per + n]
+    return out
+
+
+def score_trial_list(emb, trials, device=None):
+    """``trials``: ``[M,2]`` integer array of (utterance A, utterance B) indices -> ``[M]`` cosine scores."""
+    t = torch.as_tensor(np.asarray(trials), device=emb.device if device is None else device)
+    return utils.score_pairs(emb, t[:, 0], t[:, 1])
+
+
+def score_cross(emb, enrol_idx, test_idx):
+    """Cross-product scoring: ``[len(enrol_idx), len(test_idx)]`` cosine matrix."""
+    e = emb[torch.as_tensor(np.asarray(enrol_idx), device=emb.device)].contiguous()
+    t = emb[torch.as_tensor(np.asarray(test_idx), device=emb.device)].contiguous()
+    return utils.score_matrix(e, t)

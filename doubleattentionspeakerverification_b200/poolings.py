@@ -30,12 +30,9 @@ class _DoubleMHAFn(torch.autograd.Function):
         ctx.save_for_backward(x, query, att if att is not None else query.new_empty(0),
                               r['ctx'], r['lse'], r['headw'] if att is not None else query.new_empty(0))
         first = r['out'] if att is not None else r['ctx']
-        ctx.mark_non_differentiable(r['align'])
-        if att is not None:
-            ctx.mark_non_differentiable(r['headw'])
-            return first, r['align'], r['headw']
-        ctx.mark_non_differentiable(r['lse'])
-        return first, r['align'], r['lse']
+        third = r['headw'] if att is not None else r['lse']
+        ctx.mark_non_differentiable(r['align'], third)
+        return first, r['align'], third
 
     @staticmethod
     def backward(ctx, g_first, _g_align, _g_third):

@@ -1,0 +1,82 @@
+"""Host-side logic of the data-parallel extractor (no GPU): sharding plan, batching/padding, and the
+world_size-2 all-gather order restoration over gloo with a stub embedder."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from doubleattentionspeakerverification_b200 import extract
+
+
+def stub_embed(x, lengths):
+    """Deterministic per-utterance 'embedding' that depends only on the valid frames (so padding or batch
+    composition errors change it): [sum, sum of squares, length, first-frame mean]."""
+    out = []
+    for b in range(x.shape[0]):
+        v = x[b, :int(lengths[b])].double()
+        out.append(torch.stack([v.sum(), (v * v).sum(), torch.tensor(float(lengths[b]), dtype=torch.float64), v[0].mean()]))
+    return torch.stack(out).float()
+
+
+def make_feats(n, seed=0):
+    rs = np.random.RandomState(seed)
+    return [rs.standard_normal((int(rs.randint(20, 200)), 8)).astype(np.float32) for _ in range(n)]
+
+
+def test_shard_plan_is_balanced_partition():
+    lengths = np.random.RandomState(1).randint(200, 2000, size=101)
+    for world in (1, 2, 4, 8):
+        plan = extract.shard_plan(lengths, world)
+        allidx = np.sort(np.concatenate(plan))
+        assert np.array_equal(allidx, np.arange(101))
+        sizes = [len(p) for p in plan]
+        assert max(sizes) - min(sizes) <= 1
+        frames = [lengths[p].sum() for p in plan]
+        assert max(frames) / min(frames) < 1.1
+
+
+def test_batch_plan_respects_budget_and_covers_all():
+    lengths = np.random.RandomState(2).randint(200, 2000, size=57)
+    batches = extract.batch_plan(lengths, max_frames=8000, max_batch=6)
+    assert np.array_equal(np.sort(np.concatenate(batches)), np.arange(57))
+    for b in batches:
+        assert len(b) <= 6 and (len(b) == 1 or len(b) * lengths[b].max() <= 8000)
+    x, L = extract.pad_batch(make_feats(5), [4, 0, 2])
+    assert x.shape[0] == 3 and x.shape[1] == L.max() and np.all(x[1, L[1]:] == 0)
+
+
+def test_single_process_matches_per_utterance():
+    feats = make_feats(23, seed=3)
+    emb = extract.extract_sharded(stub_embed, feats, 'cpu', max_frames=600)
+    want = torch.cat([stub_embed(torch.from_numpy(f)[None], torch.tensor([f.shape[0]])) for f in feats])
+    assert torch.allclose(emb, want, rtol=1e-5, atol=1e-5)
+
+
+def _worker(rank, world, port, n):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        feats = make_feats(n, seed=4)
+        emb = extract.extract_sharded(stub_embed, feats, 'cpu', max_frames=500, embedding_size=4)
+        want = torch.cat([stub_embed(torch.from_numpy(f)[None], torch.tensor([f.shape[0]])) for f in feats])
+        assert emb.shape == want.shape
+        assert torch.allclose(emb, want, rtol=1e-5, atol=1e-5), 'rank %d: gathered embeddings out of order' % rank
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_world2_gloo_allgather_restores_order():
+    for n in (11, 1):      # odd count (uneven shards) and fewer utterances than ranks (an empty shard)
+        mp.spawn(_worker, args=(2, _free_port(), n), nprocs=2, join=True)

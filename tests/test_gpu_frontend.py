@@ -101,7 +101,7 @@ def test_conv11_and_pool_kernels():
     yb = ops.conv11_direct(dev(x), dev(w), dev(b), dev(L), out_dtype=torch.bfloat16)
     assert max_rel(yb.float().cpu().numpy(), ref) < 6e-3
     p = ops.maxpool2x2(y)
-    assert max_rel(p.cpu().numpy(), po.maxpool2x2_ceil(ref)) == 0.0
+    pp = po.maxpool2x2_ceil(y.cpu().numpy())          # pooling itself is exact
+    assert max_rel(p.cpu().numpy(), pp) == 0.0
     pr = ops.maxpool2x2(y, ref_layout=True)
-    pp = po.maxpool2x2_ceil(ref)
     assert max_rel(pr.cpu().numpy(), pp.transpose(0, 1, 3, 2).reshape(2, 5, -1)) == 0.0
