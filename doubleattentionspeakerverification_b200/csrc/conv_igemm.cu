@@ -11,8 +11,8 @@
 //   With output channels on TMEM lanes a thread owns one channel and sees pixels along TMEM
 //   columns, so the 2x2 pool window (columns j, j+1, j+BF, j+BF+1) is thread-local, and the final
 //   layer's feature order c*F'+f is a contiguous store.
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-//   warps 4-7 = epilogue.  Pipelines: SMEM ring full/empty, double-buffered TMEM accumulator
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//   warps 4-11 = epilogue (two warps per TMEM lane quarter).  Pipelines: SMEM ring full/empty, double-buffered TMEM accumulator
 //   full/empty, persistent static tile schedule (tile = blockIdx.x + i*gridDim.x).
 #include "common.cuh"
 #include <cuda.h>
@@ -20,12 +20,12 @@
 
 namespace dasv {
 
-constexpr int kConvThreads = 256;
+constexpr int kConvThreads = 384;              // 4 role warps + 8 epilogue warps
 constexpr int kConvTileM = 128;                 // output channels per CTA tile = TMEM lanes
 constexpr int kConvKC = 64;                     // channels per K slice (64 bf16 = one 128-byte swizzle row)
 constexpr uint32_t kConvABytes = kConvTileM * kConvKC * 2;
-constexpr int kConvEpiChunk = 64;               // output pixels staged per epilogue chunk
-constexpr uint32_t kConvEpiBytes = kConvEpiChunk * kConvTileM * 2;   // [64][128] bf16, double-buffered
+constexpr int kConvEpiChunk = 32;               // output pixels staged per epilogue chunk
+constexpr uint32_t kConvEpiBytes = kConvEpiChunk * kConvTileM * 2;   // [32][128] bf16; double-buffered per epilogue half
 
 struct ConvParams {
     const float* bias;
@@ -96,8 +96,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     unsigned char* ring = smem;
-    unsigned char* stage = smem + static_cast<size_t>(p.stages) * p.stage_bytes;     // epilogue staging, 2 x kConvEpiBytes
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage + 2 * kConvEpiBytes);
+    unsigned char* stage = smem + static_cast<size_t>(p.stages) * p.stage_bytes;     // epilogue staging, 2 halves x 2 x kConvEpiBytes
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + 4 * kConvEpiBytes);
     uint64_t* empty = full + p.stages;
     uint64_t* acc_full = empty + p.stages;      // [2]
     uint64_t* acc_empty = acc_full + 2;         // [2]
@@ -109,7 +109,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
@@ -170,18 +170,23 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (TMEM -> regs -> SMEM -> HBM)
-        // A thread owns one output channel (its TMEM lane).  NHWC outputs go through a [64 pixels][128 ch]
-        // bf16 staging tile so that the global stores are 16-byte, fully coalesced runs of 256 B per pixel;
-        // the final layer's [B,T',C*F'] fp32 output is already contiguous per thread and is stored directly.
+        // 8 warps = 2 halves x 4 TMEM lane quarters.  A thread owns one output channel (its TMEM lane); the two
+        // halves take alternate chunks of kConvEpiChunk output pixels.  NHWC outputs go through a per-half,
+        // double-buffered [32 pixels][128 ch] bf16 staging tile so the global stores are 16-byte, fully coalesced
+        // runs of 256 B per pixel; the final layer's [B,T',C*F'] output is contiguous per thread and stored directly.
         const int q = warp & 3;                                 // TMEM lane quarter this warp may read
-        const int et = threadIdx.x - 128;                       // 0..127
+        const int half = (warp - 4) >> 2;                       // 0 or 1
+        const int et = (threadIdx.x - 128) & 127;               // thread index within the half
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int T = p.T, F = p.F, Cout = p.Cout, BF = p.BF, BT = p.BT;
         const int T2 = (T + 1) / 2, F2 = F / 2;
         const int OBF = p.pool ? BF / 2 : BF, OBT = p.pool ? BT / 2 : BT;   // output patch
         const int OT = p.pool ? T2 : T, OF = p.pool ? F2 : F;
-        const int NO = p.BB * OBT * OBF;                        // output pixels per tile
+        const int OPP = OBT * OBF;                              // output pixels per utterance of the patch
+        const int NO = p.BB * OPP;                              // output pixels per tile
+        const float inv_obf = 1.0f / static_cast<float>(OBF), inv_opp = 1.0f / static_cast<float>(OPP);
         const int ch = q * 32 + lane;                           // channel within the 128-wide tile
+        unsigned char* my_stage = stage + half * (2 * kConvEpiBytes);
         uint32_t acc_it = 0, chunk_it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const ConvTile c = conv_decode_tile(p, tile);
@@ -200,37 +205,36 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
             if (p.ref_layout) {
                 // pooled[b, t2, n*F2 + f2] = relu(max over the valid 2x2 window + bias)   (feature = c*F' + f, CNNs.py:88-89)
-                for (int bb = 0; bb < p.BB; ++bb) {
+                for (int rp = half; rp < p.BB * (BT / 2); rp += 2) {
+                    const int bb = rp / (BT / 2), tp = rp - bb * (BT / 2);
                     const int b = c.b0 + bb;
                     const int Lb = conv_len(p, b);
-                    for (int tp = 0; tp < BT / 2; ++tp) {
-                        const int t = c.t0 + 2 * tp;
-                        if (b >= p.B || t >= T) continue;       // warp-uniform
-                        const bool r0_ok = !masked && t < Lb, r1_ok = !masked && (t + 1) < Lb;
-                        const uint32_t col0 = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF);
-                        const size_t row = (static_cast<size_t>(b) * T2 + (t >> 1)) * (static_cast<size_t>(Cout) * F2) +
-                                           static_cast<size_t>(n) * F2 + (c.f0 >> 1);
-                        for (int fp0 = 0; fp0 < BF / 2; fp0 += 4) {
-                            uint32_t v[4][4];
+                    const int t = c.t0 + 2 * tp;
+                    if (b >= p.B || t >= T) continue;           // warp-uniform
+                    const bool r0_ok = !masked && t < Lb, r1_ok = !masked && (t + 1) < Lb;
+                    const uint32_t col0 = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF);
+                    const size_t row = (static_cast<size_t>(b) * T2 + (t >> 1)) * (static_cast<size_t>(Cout) * F2) +
+                                       static_cast<size_t>(n) * F2 + (c.f0 >> 1);
+                    for (int fp0 = 0; fp0 < BF / 2; fp0 += 4) {
+                        uint32_t v[4][4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (!masked && fp0 + u < BF / 2) {      // warp-uniform
-                                    tmem_ld_x2(col0 + 2 * (fp0 + u), v[u][0], v[u][1]);
-                                    tmem_ld_x2(col0 + BF + 2 * (fp0 + u), v[u][2], v[u][3]);
-                                }
+                        for (int u = 0; u < 4; ++u) {
+                            if (!masked && fp0 + u < BF / 2) {  // warp-uniform
+                                tmem_ld_x2(col0 + 2 * (fp0 + u), v[u][0], v[u][1]);
+                                tmem_ld_x2(col0 + BF + 2 * (fp0 + u), v[u][2], v[u][3]);
                             }
-                            if (!masked) tc_wait_ld();
+                        }
+                        if (!masked) tc_wait_ld();
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (fp0 + u < BF / 2 && n_ok) {
-                                    float m = 0.f;
-                                    if (r0_ok) {
-                                        m = fmaxf(__uint_as_float(v[u][0]), __uint_as_float(v[u][1]));
-                                        if (r1_ok) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
-                                        m = fmaxf(m + bias, 0.f);
-                                    }
-                                    if (p.y_f32) conv_store<true>(p.y, row + fp0 + u, m); else conv_store<false>(p.y, row + fp0 + u, m);
+                        for (int u = 0; u < 4; ++u) {
+                            if (fp0 + u < BF / 2 && n_ok) {
+                                float m = 0.f;
+                                if (r0_ok) {
+                                    m = fmaxf(__uint_as_float(v[u][0]), __uint_as_float(v[u][1]));
+                                    if (r1_ok) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
+                                    m = fmaxf(m + bias, 0.f);
                                 }
+                                if (p.y_f32) conv_store<true>(p.y, row + fp0 + u, m); else conv_store<false>(p.y, row + fp0 + u, m);
                             }
                         }
                     }
@@ -244,27 +248,34 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 continue;
             }
 
-            // ---------------- NHWC bf16 output, in chunks of kConvEpiChunk output pixels
-            for (int o0 = 0; o0 < NO; o0 += kConvEpiChunk) {
+            // ---------------- NHWC bf16 output: this half's chunks of kConvEpiChunk output pixels
+            const int n_chunks = (NO + kConvEpiChunk - 1) / kConvEpiChunk;
+            for (int ck = half; ck < n_chunks; ck += 2) {
+                const int o0 = ck * kConvEpiChunk;
                 const int cnt = min(kConvEpiChunk, NO - o0);
-                unsigned char* buf = stage + (chunk_it & 1u) * kConvEpiBytes;
+                unsigned char* buf = my_stage + (chunk_it & 1u) * kConvEpiBytes;
                 if (!masked) {
                     // phase 1: this thread's channel of `cnt` output pixels -> staging[pixel][ch]
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + ch;
                     if (!p.pool) {
-                        for (int j0 = 0; j0 < cnt; j0 += 16) {
-                            uint32_t r[16];
-                            tmem_ld_x16(tcol + o0 + j0, r);
-                            tc_wait_ld();
+                        uint32_t r0[16], r1[16];
+                        tmem_ld_x16(tcol + o0, r0);
+                        if (cnt > 16) tmem_ld_x16(tcol + o0 + 16, r1);          // warp-uniform
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < cnt) dst[j * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r0[j]) + bias, 0.f));
+                        if (cnt > 16) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (j0 + j < cnt)
-                                    dst[(j0 + j) * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias, 0.f));
+                                if (16 + j < cnt) dst[(16 + j) * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r1[j]) + bias, 0.f));
                         }
                     } else {
                         // output o -> (bb, tp, fp); window columns (bb*BT + 2tp)*BF + 2fp (+1, +BF, +BF+1)
-                        int bb = o0 / (OBT * OBF), rem = o0 - bb * (OBT * OBF);
-                        int tp = rem / OBF, fp = rem - tp * OBF;
+                        int bb = __float2int_rz((static_cast<float>(o0) + 0.5f) * inv_opp);
+                        int rem = o0 - bb * OPP;
+                        int tp = __float2int_rz((static_cast<float>(rem) + 0.5f) * inv_obf), fp = rem - tp * OBF;
+                        int Lcur = conv_len(p, c.b0 + bb);
                         for (int j0 = 0; j0 < cnt; j0 += 4) {
                             uint32_t v[4][4];
                             bool r1[4];
@@ -272,10 +283,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             for (int u = 0; u < 4; ++u) {
                                 if (j0 + u < cnt) {             // warp-uniform
                                     const uint32_t col = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF + 2 * fp);
-                                    r1[u] = (c.t0 + 2 * tp + 1) < conv_len(p, c.b0 + bb);   // ceil-mode / masked second row
+                                    r1[u] = (c.t0 + 2 * tp + 1) < Lcur;     // ceil-mode / masked second row
                                     tmem_ld_x2(col, v[u][0], v[u][1]);
                                     tmem_ld_x2(col + BF, v[u][2], v[u][3]);
-                                    if (++fp == OBF) { fp = 0; if (++tp == OBT) { tp = 0; ++bb; } }
+                                    if (++fp == OBF) { fp = 0; if (++tp == OBT) { tp = 0; ++bb; Lcur = conv_len(p, c.b0 + bb); } }
                                 }
                             }
                             tc_wait_ld();
@@ -289,35 +300,40 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             }
                         }
                     }
-                    if (o0 + kConvEpiChunk >= NO) {             // all TMEM reads of this tile are done: release the accumulator
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
-                        ++acc_it;
-                    }
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1 + half, 128);
                 }
                 // phase 2: 16 threads per pixel copy 256 B runs to y (zeros for masked frames)
                 {
                     const int seg = et & 15;
                     const bool seg_ok = c.m * kConvTileM + seg * 8 < Cout;
-                    for (int po = et >> 4; po < cnt; po += 8) {
-                        const int o = o0 + po;
-                        const int bb = o / (OBT * OBF), rem = o - bb * (OBT * OBF);
-                        const int tl = rem / OBF, fl = rem - tl * OBF;
-                        const int b = c.b0 + bb, to = ot0 + tl, fo = of0 + fl;
-                        if (b < p.B && to < OT && seg_ok) {
-                            const int t_in = p.pool ? 2 * to : to;
-                            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                            if (!masked && t_in < conv_len(p, b))
-                                val = *reinterpret_cast<const uint4*>(buf + po * (kConvTileM * 2) + seg * 16);
-                            __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) +
-                                                ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c.m * kConvTileM + seg * 8;
-                            *reinterpret_cast<uint4*>(yp) = val;
+#pragma unroll
+                    for (int i = 0; i < kConvEpiChunk / 8; ++i) {
+                        const int po = (et >> 4) + 8 * i;
+                        if (po < cnt) {
+                            const int o = o0 + po;
+                            const int bb = __float2int_rz((static_cast<float>(o) + 0.5f) * inv_opp);
+                            const int rem = o - bb * OPP;
+                            const int tl = __float2int_rz((static_cast<float>(rem) + 0.5f) * inv_obf), fl = rem - tl * OBF;
+                            const int b = c.b0 + bb, to = ot0 + tl, fo = of0 + fl;
+                            if (b < p.B && to < OT && seg_ok) {
+                                const int t_in = p.pool ? 2 * to : to;
+                                uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                                if (!masked && t_in < conv_len(p, b))
+                                    val = *reinterpret_cast<const uint4*>(buf + po * (kConvTileM * 2) + seg * 16);
+                                __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) +
+                                                    ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c.m * kConvTileM + seg * 8;
+                                *reinterpret_cast<uint4*>(yp) = val;
+                            }
                         }
                     }
                 }
                 if (!masked) ++chunk_it;
+            }
+            if (!masked) {                                      // all of this warp's TMEM reads of the tile are done
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
+                ++acc_it;
             }
         }
     }
@@ -435,7 +451,7 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
     p.b_bytes = static_cast<uint32_t>(pl.N) * 128u;
     p.stage_bytes = kConvABytes + ((static_cast<uint32_t>(pl.Npad) * 128u + 1023u) & ~1023u);
-    const uint32_t kFixed = 2 * kConvEpiBytes + 1024 + 512;     // staging + alignment slack + barriers
+    const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512;     // staging + alignment slack + barriers
     int stages = static_cast<int>((227u * 1024u - kFixed) / p.stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv3x3_igemm_bf16: ring does not fit shared memory"); return 1; }

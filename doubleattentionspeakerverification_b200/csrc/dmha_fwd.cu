@@ -45,6 +45,82 @@ __host__ __device__ inline DmhaFwdSmem dmha_fwd_smem(int D, int H, int dh, int S
     return s;
 }
 
+// Per-utterance tail shared by both consumer mappings: merge the S partial (max, sum, weighted sum) states of
+// every head, finish ctx / lse, then the attention over heads (poolings.py:45-51,61-71) and the alignment fix-up.
+DASV_DEVICE void dmha_fwd_finish(const DmhaFwdParams& p, int b, int Lb, int warp, int lane, int tid,
+                                 float* pacc, float* pm, float* pl, float* u_sm, float* w_sm, const float* a_sm) {
+    const int H = p.H, dh = p.dh, S = p.S, T = p.T;
+        for (int h = warp; h < H; h += kDmhaConsumerWarps) {
+            float M = -INFINITY;
+            for (int s = 0; s < S; ++s) M = fmaxf(M, pm[h * S + s]);
+            const float Mref = (M == -INFINITY) ? 0.f : M;
+            float Lsum = 0.f;
+            for (int s = 0; s < S; ++s) Lsum += pl[h * S + s] * fast_exp2(pm[h * S + s] - Mref);
+            const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;
+            float dot = 0.f;
+            for (int d = lane; d < dh; d += 32) {
+                float c = 0.f;
+                for (int s = 0; s < S; ++s) c = fmaf(pacc[(h * S + s) * dh + d], fast_exp2(pm[h * S + s] - Mref), c);
+                c *= inv;
+                pacc[(h * S) * dh + d] = c;                    // ctx[b,h,d], kept in smem for the head stage
+                if (p.ctx != nullptr) p.ctx[(static_cast<size_t>(b) * H + h) * dh + d] = c;
+                if (p.att != nullptr) dot = fmaf(c, a_sm[d], dot);
+            }
+            dot = warp_sum(dot);
+            __syncwarp();
+            if (lane == 0) {
+                u_sm[h] = dot;                                  // poolings.py:47 (no scale)
+                const float lse2 = M + log2f(Lsum);             // log2 units; -inf for an empty utterance
+                pm[h * S] = lse2;
+                if (p.lse != nullptr) p.lse[static_cast<size_t>(b) * H + h] = lse2 * kLn2;
+            }
+        }
+        named_bar_sync(1, kDmhaConsumerThreads);
+
+        if (p.att != nullptr) {
+            if (warp == 0) {
+                // softmax over heads (poolings.py:50), with the training-mode keep mask (poolings.py:42)
+                float mx = -INFINITY;
+                for (int h = lane; h < H; h += 32) {
+                    const bool kept = p.keep == nullptr || p.keep[static_cast<size_t>(b) * H + h] != 0;
+                    const float u = kept ? u_sm[h] : -INFINITY;
+                    u_sm[h] = u;
+                    mx = fmaxf(mx, u);
+                }
+                mx = warp_max(mx);
+                float sum = 0.f;
+                for (int h = lane; h < H; h += 32) {
+                    const float e = expf(u_sm[h] - mx);        // all heads dropped -> NaN, as in the reference
+                    w_sm[h] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                for (int h = lane; h < H; h += 32) {
+                    const float w = w_sm[h] / sum;
+                    w_sm[h] = w;
+                    if (p.headw != nullptr) p.headw[static_cast<size_t>(b) * H + h] = w;
+                }
+            }
+            named_bar_sync(1, kDmhaConsumerThreads);
+            if (p.out != nullptr) {
+                for (int d = tid; d < dh; d += kDmhaConsumerThreads) {
+                    float o = 0.f;
+                    for (int h = 0; h < H; ++h) o = fmaf(w_sm[h], pacc[(h * S) * dh + d], o);   // poolings.py:68-69
+                    p.out[static_cast<size_t>(b) * dh + d] = o;
+                }
+            }
+        }
+        if (p.align != nullptr) {
+            // alignment = softmax over time (poolings.py:77): exp2(raw - lse); frames >= L are 0
+            float* ab = p.align + static_cast<size_t>(b) * T * H;
+            for (int i = tid; i < T * H; i += kDmhaConsumerThreads) {
+                const int t = i / H, h = i - t * H;
+                ab[i] = (t < Lb) ? fast_exp2(ab[i] - pm[h * S]) : 0.f;
+            }
+        }
+        named_bar_sync(1, kDmhaConsumerThreads);   // pacc/pm/u/w are reused by the next utterance
+}
+
 // Resident CTAs per SM the register allocator must allow: the light configurations want >= 4
 // co-resident utterances per SM so that a batch of a few hundred utterances is one wave.
 template <bool BF16, int NV, int HPG>
@@ -244,75 +320,177 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd_min_ctas<BF16, NV, HPG>
         }
         named_bar_sync(1, kDmhaConsumerThreads);
 
-        for (int h = warp; h < H; h += kDmhaConsumerWarps) {
-            float M = -INFINITY;
-            for (int s = 0; s < S; ++s) M = fmaxf(M, pm[h * S + s]);
-            const float Mref = (M == -INFINITY) ? 0.f : M;
-            float Lsum = 0.f;
-            for (int s = 0; s < S; ++s) Lsum += pl[h * S + s] * fast_exp2(pm[h * S + s] - Mref);
-            const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;
-            float dot = 0.f;
-            for (int d = lane; d < dh; d += 32) {
-                float c = 0.f;
-                for (int s = 0; s < S; ++s) c = fmaf(pacc[(h * S + s) * dh + d], fast_exp2(pm[h * S + s] - Mref), c);
-                c *= inv;
-                pacc[(h * S) * dh + d] = c;                    // ctx[b,h,d], kept in smem for the head stage
-                if (p.ctx != nullptr) p.ctx[(static_cast<size_t>(b) * H + h) * dh + d] = c;
-                if (p.att != nullptr) dot = fmaf(c, a_sm[d], dot);
+        dmha_fwd_finish(p, b, Lb, warp, lane, tid, pacc, pm, pl, u_sm, w_sm, a_sm);
+    }
+}
+
+// ---------------------------------------------------------------------------------- v2 consumer mapping
+// The kernel above keeps one 16-byte vector per lane (a head row is spread over up to 32 lanes), which makes
+// the per-row shuffle reduction and the redundant softmax bookkeeping dominate: ncu showed it issue-bound
+// (71 % issue-active, 0.74 warp instructions per input float) at 47 % of DRAM throughput.  v2 gives a lane
+// NV vectors (16-24 elements) of a (frame, head) row, G = 2..32 lanes per row, so a row costs log2(G) shuffles,
+// and rescales the running sums lazily (only when the running max grows by > 2^kLazy), ~0.1 warp
+// instructions per float.  Row groups of one LDS.128 phase start at different vectors (rot) so that rows whose
+// byte size is a multiple of 128 do not collide on the same banks.
+constexpr float kDmhaLazy = 8.0f;
+
+template <bool BF16, int NV>
+constexpr int dmha_fwd2_min_ctas() { return (NV * (BF16 ? 8 : 4) <= 12) ? 3 : 2; }
+
+template <bool BF16, int G, int NV>
+__global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) dmha_fwd2_kernel(const DmhaFwdParams p) {
+    constexpr int VE = BF16 ? 8 : 4;
+    constexpr uint32_t ES = BF16 ? 2u : 4u;
+    constexpr int RPW = 32 / G;                                 // (frame, head) rows per warp
+    constexpr int GPP = (G >= 8) ? 1 : 8 / G;                   // row groups per 8-lane LDS.128 phase
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int D = p.D, H = p.H, dh = p.dh, S = p.S, T = p.T;
+    const uint32_t frame_bytes = static_cast<uint32_t>(D) * ES;
+    const uint32_t stage_bytes = p.fps * frame_bytes;
+    const DmhaFwdSmem L = dmha_fwd_smem(D, H, dh, S, p.stages, stage_bytes);
+    unsigned char* ring = smem + L.ring;
+    float* q_sm = reinterpret_cast<float*>(smem + L.q);
+    float* a_sm = reinterpret_cast<float*>(smem + L.a);
+    float* pacc = reinterpret_cast<float*>(smem + L.pacc);
+    float* pm = reinterpret_cast<float*>(smem + L.pm);
+    float* pl = reinterpret_cast<float*>(smem + L.pl);
+    float* u_sm = reinterpret_cast<float*>(smem + L.u);
+    float* w_sm = reinterpret_cast<float*>(smem + L.w);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* empty = full + p.stages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kDmhaConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < D; i += kDmhaThreads) {
+        const int h = i / dh, d = i - h * dh;
+        q_sm[i] = p.query[d * H + h];               // reference layout [dh, H] (poolings.py:90)
+    }
+    if (p.att != nullptr)
+        for (int i = tid; i < dh; i += kDmhaThreads) a_sm[i] = p.att[i];
+    __syncthreads();
+
+    if (warp == kDmhaConsumerWarps) {
+        if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
+            uint32_t it = 0;
+            for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+                int Lb = p.lengths ? p.lengths[b] : T;
+                Lb = max(0, min(Lb, T));
+                const unsigned char* xb = p.x + static_cast<size_t>(b) * T * frame_bytes;
+                for (int f0 = 0; f0 < Lb; f0 += p.fps, ++it) {
+                    const int st = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(&empty[st], ph ^ 1u);
+                    const uint32_t bytes = static_cast<uint32_t>(min(p.fps, Lb - f0)) * frame_bytes;
+                    mbar_arrive_expect_tx(&full[st], bytes);
+                    bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
+                }
             }
-            dot = warp_sum(dot);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers
+    const int grp = warp * RPW + lane / G, lig = lane % G;
+    const int head = grp % H, slot = grp / H;       // this group's head and frame slot (frames f = slot mod S)
+    const bool active = slot < S;
+    const int rot = (lane / G) % GPP;
+    uint32_t voff[NV];
+    bool vok[NV];
+    float qreg[NV][VE];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int idx = ((v + rot) % NV) * G + lig;             // 16-byte vector of the row held in slot v
+        vok[v] = active && idx * VE < dh;
+        voff[v] = static_cast<uint32_t>(head) * dh * ES + static_cast<uint32_t>(idx) * 16u;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) qreg[v][e] = vok[v] ? q_sm[head * dh + idx * VE + e] : 0.f;
+    }
+
+    uint32_t it = 0;
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        int Lb = p.lengths ? p.lengths[b] : T;
+        Lb = max(0, min(Lb, T));
+        float m = -INFINITY, l = 0.f, acc[NV][VE];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int e = 0; e < VE; ++e) acc[v][e] = 0.f;
+
+        for (int f0 = 0; f0 < Lb; f0 += p.fps, ++it) {
+            const int st = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1u;
+            mbar_wait(&full[st], ph);
+            const int nf = min(p.fps, Lb - f0);
+            const unsigned char* sbase = ring + st * stage_bytes;
+            const int trips = (nf + S - 1) / S;                  // warp-uniform (fps is a multiple of S)
+            for (int i = 0; i < trips; ++i) {
+                const int f = slot + i * S;
+                const bool valid = active && f < nf;
+                const unsigned char* row = sbase + static_cast<uint32_t>(f) * frame_bytes;
+                float xs[NV][VE];
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    if (valid && vok[v]) {
+                        load_row_vec<VE, BF16>(row + voff[v], xs[v]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) xs[v][e] = 0.f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < VE; e += 2) {
+                        s0 = fmaf(xs[v][e], qreg[v][e], s0);
+                        s1 = fmaf(xs[v][e + 1], qreg[v][e + 1], s1);
+                    }
+                }
+                const float sc = group_sum<G>(s0 + s1) * p.scale_log2;   // log2-unit score of this (frame, head)
+                if (valid) {
+                    if (p.align != nullptr && lig == 0)
+                        p.align[(static_cast<size_t>(b) * T + f0 + f) * H + head] = sc;   // raw score, normalised below
+                    if (sc > m + kDmhaLazy) {                    // lazy rescale; first frame: m = -inf -> corr = 0
+                        const float corr = fast_exp2(m - sc);
+                        l *= corr;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v)
+#pragma unroll
+                            for (int e = 0; e < VE; ++e) acc[v][e] *= corr;
+                        m = sc;
+                    }
+                    const float pr = fast_exp2(sc - m);
+                    l += pr;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) acc[v][e] = fmaf(pr, xs[v][e], acc[v][e]);
+                }
+            }
             __syncwarp();
-            if (lane == 0) {
-                u_sm[h] = dot;                                  // poolings.py:47 (no scale)
-                const float lse2 = M + log2f(Lsum);             // log2 units; -inf for an empty utterance
-                pm[h * S] = lse2;
-                if (p.lse != nullptr) p.lse[static_cast<size_t>(b) * H + h] = lse2 * kLn2;
-            }
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+
+        // ------------------------------------------------------------ merge the S frame slots, head stage
+        if (active) {
+            const int sl = head * S + slot;
+            if (lig == 0) { pm[sl] = m; pl[sl] = l; }
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (vok[v]) {
+                    const int idx = ((v + rot) % NV) * G + lig;
+#pragma unroll
+                    for (int e = 0; e < VE; ++e) pacc[sl * dh + idx * VE + e] = acc[v][e];
+                }
         }
         named_bar_sync(1, kDmhaConsumerThreads);
-
-        if (p.att != nullptr) {
-            if (warp == 0) {
-                // softmax over heads (poolings.py:50), with the training-mode keep mask (poolings.py:42)
-                float mx = -INFINITY;
-                for (int h = lane; h < H; h += 32) {
-                    const bool kept = p.keep == nullptr || p.keep[static_cast<size_t>(b) * H + h] != 0;
-                    const float u = kept ? u_sm[h] : -INFINITY;
-                    u_sm[h] = u;
-                    mx = fmaxf(mx, u);
-                }
-                mx = warp_max(mx);
-                float sum = 0.f;
-                for (int h = lane; h < H; h += 32) {
-                    const float e = expf(u_sm[h] - mx);        // all heads dropped -> NaN, as in the reference
-                    w_sm[h] = e;
-                    sum += e;
-                }
-                sum = warp_sum(sum);
-                for (int h = lane; h < H; h += 32) {
-                    const float w = w_sm[h] / sum;
-                    w_sm[h] = w;
-                    if (p.headw != nullptr) p.headw[static_cast<size_t>(b) * H + h] = w;
-                }
-            }
-            named_bar_sync(1, kDmhaConsumerThreads);
-            if (p.out != nullptr) {
-                for (int d = tid; d < dh; d += kDmhaConsumerThreads) {
-                    float o = 0.f;
-                    for (int h = 0; h < H; ++h) o = fmaf(w_sm[h], pacc[(h * S) * dh + d], o);   // poolings.py:68-69
-                    p.out[static_cast<size_t>(b) * dh + d] = o;
-                }
-            }
-        }
-        if (p.align != nullptr) {
-            // alignment = softmax over time (poolings.py:77): exp2(raw - lse); frames >= L are 0
-            float* ab = p.align + static_cast<size_t>(b) * T * H;
-            for (int i = tid; i < T * H; i += kDmhaConsumerThreads) {
-                const int t = i / H, h = i - t * H;
-                ab[i] = (t < Lb) ? fast_exp2(ab[i] - pm[h * S]) : 0.f;
-            }
-        }
-        named_bar_sync(1, kDmhaConsumerThreads);   // pacc/pm/u/w are reused by the next utterance
+        dmha_fwd_finish(p, b, Lb, warp, lane, tid, pacc, pm, pl, u_sm, w_sm, a_sm);
     }
 }
 
@@ -348,9 +526,8 @@ DmhaPlan dmha_make_plan(int x_dtype, int T, int D, int H, bool backward) {
     return pl;
 }
 
-template <bool BF16, int G, int NV, int HPG>
-static int launch_fwd(const DmhaFwdParams& p, size_t smem, cudaStream_t stream) {
-    auto kern = dmha_fwd_kernel<BF16, G, NV, HPG>;
+template <typename Kern>
+static int launch_fwd_kernel(Kern kern, const DmhaFwdParams& p, size_t smem, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("dmha_fwd: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
     int dev = 0, sms = 0, occ = 0;
@@ -367,7 +544,7 @@ static int launch_fwd(const DmhaFwdParams& p, size_t smem, cudaStream_t stream) 
 template <bool BF16>
 static int dispatch_fwd(const DmhaPlan& pl, const DmhaFwdParams& p, size_t smem, cudaStream_t s) {
 #define DASV_CASE(g, nv, hpg) \
-    if (pl.G == g && pl.NV == nv && pl.HPG == hpg) return launch_fwd<BF16, g, nv, hpg>(p, smem, s);
+    if (pl.G == g && pl.NV == nv && pl.HPG == hpg) return launch_fwd_kernel(dmha_fwd_kernel<BF16, g, nv, hpg>, p, smem, s);
     DASV_CASE(8, 1, 1) DASV_CASE(8, 1, 4)
     DASV_CASE(16, 1, 1) DASV_CASE(16, 1, 4)
     DASV_CASE(32, 1, 1) DASV_CASE(32, 1, 4)
@@ -375,6 +552,46 @@ static int dispatch_fwd(const DmhaPlan& pl, const DmhaFwdParams& p, size_t smem,
     DASV_CASE(32, 4, 1) DASV_CASE(32, 4, 4)
 #undef DASV_CASE
     set_error("dmha_fwd: no kernel for G=%d NV=%d HPG=%d", pl.G, pl.NV, pl.HPG);
+    return 1;
+}
+
+// v2 mapping: NV vectors per lane (<= 5 fp32 / 3 bf16), G = 2..32 lanes per row, needs H <= 256/G row groups.
+struct DmhaPlan2 { int ok, G, NV, S, fps, stages; };
+
+static DmhaPlan2 dmha_make_plan2(int x_dtype, int T, int D, int H) {
+    DmhaPlan2 pl{};
+    const bool bf16 = x_dtype == 1;
+    const int VE = bf16 ? 8 : 4, nvmax = bf16 ? 3 : 5;
+    if (H <= 0 || D <= 0 || D % H != 0) return pl;
+    const int dh = D / H;
+    if (dh % VE != 0) return pl;
+    const int nvec = dh / VE;
+    int G = 2;
+    while (G <= 32 && (nvec + G - 1) / G > nvmax) G <<= 1;
+    if (G > 32) return pl;
+    const int ngrp = kDmhaConsumerThreads / G;
+    if (H > ngrp) return pl;
+    int S = ngrp / H;
+    if (S > 8) S = 8;
+    const size_t frame_bytes = static_cast<size_t>(D) * (bf16 ? 2 : 4);
+    int fps = static_cast<int>((16 * 1024) / frame_bytes) / S * S;
+    if (fps < S) fps = S;
+    const int tcap = (T + S - 1) / S * S;
+    if (fps > tcap) fps = tcap > 0 ? tcap : S;
+    pl.ok = 1; pl.G = G; pl.NV = (nvec + G - 1) / G; pl.S = S; pl.fps = fps; pl.stages = 3;
+    return pl;
+}
+
+template <bool BF16>
+static int dispatch_fwd2(const DmhaPlan2& pl, const DmhaFwdParams& p, size_t smem, cudaStream_t s) {
+#define DASV_CASE2(g, nv) \
+    if (pl.G == g && pl.NV == nv) return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv>, p, smem, s);
+#define DASV_ROW2(g) DASV_CASE2(g, 1) DASV_CASE2(g, 2) DASV_CASE2(g, 3) \
+    if constexpr (!BF16) { DASV_CASE2(g, 4) DASV_CASE2(g, 5) }
+    DASV_ROW2(2) DASV_ROW2(4) DASV_ROW2(8) DASV_ROW2(16) DASV_ROW2(32)
+#undef DASV_ROW2
+#undef DASV_CASE2
+    set_error("dmha_fwd: no v2 kernel for G=%d NV=%d", pl.G, pl.NV);
     return 1;
 }
 
@@ -394,6 +611,26 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
         set_error("dmha_fwd: out/headw need att (att==NULL selects the MultiHeadAttention-only mode)");
         return 1;
     }
+    DmhaFwdParams p{};
+    p.x = static_cast<const unsigned char*>(x);
+    p.lengths = lengths; p.query = query; p.att = att; p.keep = keep;
+    p.out = out; p.ctx = ctx; p.lse = lse; p.headw = headw; p.align = align;
+    p.B = B; p.T = T; p.D = D; p.H = H; p.dh = H > 0 ? D / H : 0;
+    p.scale_log2 = kLog2e / sqrtf(static_cast<float>(H));     // d_k = query.size(-1) = H (poolings.py:75)
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool bf16 = x_dtype == 1;
+
+    DmhaPlan2 p2 = dmha_make_plan2(x_dtype, T, D, H);
+    if (p2.ok) {
+        const uint32_t stage_bytes = static_cast<uint32_t>(p2.fps) * D * (bf16 ? 2 : 4);
+        size_t smem = dmha_fwd_smem(D, H, p.dh, p2.S, p2.stages, stage_bytes).total;
+        while (smem > 227 * 1024 && p2.stages > 2) smem = dmha_fwd_smem(D, H, p.dh, p2.S, --p2.stages, stage_bytes).total;
+        if (smem <= 227 * 1024) {
+            p.fps = p2.fps; p.stages = p2.stages; p.S = p2.S;
+            return bf16 ? dispatch_fwd2<true>(p2, p, smem, s) : dispatch_fwd2<false>(p2, p, smem, s);
+        }
+    }
+    // shapes outside the v2 mapping (more heads than row groups, very wide rows): v1 mapping
     DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, false);
     if (pl.err) {
         set_error("dmha_fwd: unsupported shape D=%d H=%d dtype=%d (plan error %d: need D%%H==0, "
@@ -401,17 +638,10 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
                   D, H, x_dtype, pl.err, x_dtype ? 8 : 4);
         return 1;
     }
-    DmhaFwdParams p{};
-    p.x = static_cast<const unsigned char*>(x);
-    p.lengths = lengths; p.query = query; p.att = att; p.keep = keep;
-    p.out = out; p.ctx = ctx; p.lse = lse; p.headw = headw; p.align = align;
-    p.B = B; p.T = T; p.D = D; p.H = H; p.dh = D / H;
-    p.scale_log2 = kLog2e / sqrtf(static_cast<float>(H));     // d_k = query.size(-1) = H (poolings.py:75)
     const uint32_t stage_bytes = static_cast<uint32_t>(pl.fps) * D * (pl.bf16 ? 2 : 4);
     size_t smem = dmha_fwd_smem(D, H, p.dh, pl.S, pl.stages, stage_bytes).total;
     while (smem > 227 * 1024 && pl.stages > 2) smem = dmha_fwd_smem(D, H, p.dh, pl.S, --pl.stages, stage_bytes).total;   // very wide features: shallower ring
     p.fps = pl.fps; p.stages = pl.stages; p.S = pl.S;
     if (smem > 227 * 1024) { set_error("dmha_fwd: D=%d needs %zu B of shared memory (> 227 KB)", D, smem); return 1; }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     return pl.bf16 ? dispatch_fwd<true>(pl, p, smem, s) : dispatch_fwd<false>(pl, p, smem, s);
 }
