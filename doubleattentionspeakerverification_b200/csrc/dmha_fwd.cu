@@ -5,6 +5,7 @@
 // Roofline: HBM.  Algorithmic bytes per utterance = L_b * D * sizeof(x) read (+ D/H*4 out).
 #include "dmha_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace dasv {
 
@@ -337,7 +338,7 @@ constexpr float kDmhaLazy = 8.0f;
 template <bool BF16, int NV>
 constexpr int dmha_fwd2_min_ctas() { return (NV * (BF16 ? 8 : 4) <= 12) ? 3 : 2; }
 
-template <bool BF16, int G, int NV>
+template <bool BF16, int G, int NV, int FB, bool RAGGED>
 __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) dmha_fwd2_kernel(const DmhaFwdParams p) {
     constexpr int VE = BF16 ? 8 : 4;
     constexpr uint32_t ES = BF16 ? 2u : 4u;
@@ -380,18 +381,18 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
 
     if (warp == kDmhaConsumerWarps) {
         if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
-            uint32_t it = 0;
+            int st = 0;
+            uint32_t ph = 0;
             for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
                 int Lb = p.lengths ? p.lengths[b] : T;
                 Lb = max(0, min(Lb, T));
                 const unsigned char* xb = p.x + static_cast<size_t>(b) * T * frame_bytes;
-                for (int f0 = 0; f0 < Lb; f0 += p.fps, ++it) {
-                    const int st = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1u;
+                for (int f0 = 0; f0 < Lb; f0 += p.fps) {
                     mbar_wait(&empty[st], ph ^ 1u);
                     const uint32_t bytes = static_cast<uint32_t>(min(p.fps, Lb - f0)) * frame_bytes;
                     mbar_arrive_expect_tx(&full[st], bytes);
                     bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
+                    if (++st == p.stages) { st = 0; ph ^= 1u; }
                 }
             }
         }
@@ -415,7 +416,8 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
         for (int e = 0; e < VE; ++e) qreg[v][e] = vok[v] ? q_sm[head * dh + idx * VE + e] : 0.f;
     }
 
-    uint32_t it = 0;
+    int st = 0;
+    uint32_t ph = 0;
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         int Lb = p.lengths ? p.lengths[b] : T;
         Lb = max(0, min(Lb, T));
@@ -425,56 +427,71 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
 #pragma unroll
             for (int e = 0; e < VE; ++e) acc[v][e] = 0.f;
 
-        for (int f0 = 0; f0 < Lb; f0 += p.fps, ++it) {
-            const int st = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1u;
+        for (int f0 = 0; f0 < Lb; f0 += p.fps) {
             mbar_wait(&full[st], ph);
             const int nf = min(p.fps, Lb - f0);
             const unsigned char* sbase = ring + st * stage_bytes;
-            const int trips = (nf + S - 1) / S;                  // warp-uniform (fps is a multiple of S)
-            for (int i = 0; i < trips; ++i) {
-                const int f = slot + i * S;
-                const bool valid = active && f < nf;
-                const unsigned char* row = sbase + static_cast<uint32_t>(f) * frame_bytes;
-                float xs[NV][VE];
-                float s0 = 0.f, s1 = 0.f;
+            // FB (frame, head) rows per trip: rows fb+slot and fb+S+slot are independent until the softmax
+            // update, which gives the LDS -> FMA -> shuffle -> exp2 chain a second row to overlap with.
+            for (int fb = 0; fb < nf; fb += FB * S) {            // warp-uniform trip count (fps is a multiple of S)
+                float xs[FB][NV][VE];
+                float sc[FB];
+                bool valid[FB];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    if (valid && vok[v]) {
-                        load_row_vec<VE, BF16>(row + voff[v], xs[v]);
-                    } else {
+                for (int r = 0; r < FB; ++r) {
+                    const int f = fb + r * S + slot;
+                    valid[r] = active && f < nf;
+                    const unsigned char* row = sbase + static_cast<uint32_t>(valid[r] ? f : 0) * frame_bytes;   // safe address when idle
+                    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                        for (int e = 0; e < VE; ++e) xs[v][e] = 0.f;
+                    for (int v = 0; v < NV; ++v) {
+                        if (RAGGED && !vok[v]) {
+#pragma unroll
+                            for (int e = 0; e < VE; ++e) xs[r][v][e] = 0.f;
+                        } else {
+                            load_row_vec<VE, BF16>(row + voff[v], xs[r][v]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < VE; e += 2) {
+                            s0 = fmaf(xs[r][v][e], qreg[v][e], s0);
+                            s1 = fmaf(xs[r][v][e + 1], qreg[v][e + 1], s1);
+                        }
                     }
-#pragma unroll
-                    for (int e = 0; e < VE; e += 2) {
-                        s0 = fmaf(xs[v][e], qreg[v][e], s0);
-                        s1 = fmaf(xs[v][e + 1], qreg[v][e + 1], s1);
-                    }
+                    sc[r] = s0 + s1;
                 }
-                const float sc = group_sum<G>(s0 + s1) * p.scale_log2;   // log2-unit score of this (frame, head)
-                if (valid) {
-                    if (p.align != nullptr && lig == 0)
-                        p.align[(static_cast<size_t>(b) * T + f0 + f) * H + head] = sc;   // raw score, normalised below
-                    if (sc > m + kDmhaLazy) {                    // lazy rescale; first frame: m = -inf -> corr = 0
-                        const float corr = fast_exp2(m - sc);
-                        l *= corr;
 #pragma unroll
-                        for (int v = 0; v < NV; ++v)
+                for (int r = 0; r < FB; ++r) sc[r] = group_sum<G>(sc[r]);
+                float mx = -INFINITY;
 #pragma unroll
-                            for (int e = 0; e < VE; ++e) acc[v][e] *= corr;
-                        m = sc;
-                    }
-                    const float pr = fast_exp2(sc - m);
+                for (int r = 0; r < FB; ++r) {
+                    sc[r] = valid[r] ? sc[r] * p.scale_log2 : -INFINITY;     // log2-unit score of this (frame, head)
+                    mx = fmaxf(mx, sc[r]);
+                    if (p.align != nullptr && valid[r] && lig == 0)
+                        p.align[(static_cast<size_t>(b) * T + f0 + fb + r * S + slot) * H + head] = sc[r];   // raw score, normalised below
+                }
+                if (mx > m + kDmhaLazy) {                        // lazy rescale; first frame: m = -inf -> corr = 0
+                    const float corr = fast_exp2(m - mx);
+                    l *= corr;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+#pragma unroll
+                        for (int e = 0; e < VE; ++e) acc[v][e] *= corr;
+                    m = mx;
+                }
+                const float mref = (m == -INFINITY) ? 0.f : m;  // idle group: exp2(-inf - 0) = 0
+#pragma unroll
+                for (int r = 0; r < FB; ++r) {
+                    const float pr = fast_exp2(sc[r] - mref);
                     l += pr;
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
 #pragma unroll
-                        for (int e = 0; e < VE; ++e) acc[v][e] = fmaf(pr, xs[v][e], acc[v][e]);
+                        for (int e = 0; e < VE; ++e) acc[v][e] = fmaf(pr, xs[r][v][e], acc[v][e]);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
+            if (++st == p.stages) { st = 0; ph ^= 1u; }
         }
 
         // ------------------------------------------------------------ merge the S frame slots, head stage
@@ -556,12 +573,12 @@ static int dispatch_fwd(const DmhaPlan& pl, const DmhaFwdParams& p, size_t smem,
 }
 
 // v2 mapping: NV vectors per lane (<= 5 fp32 / 3 bf16), G = 2..32 lanes per row, needs H <= 256/G row groups.
-struct DmhaPlan2 { int ok, G, NV, S, fps, stages; };
+struct DmhaPlan2 { int ok, G, NV, S, fps, stages, FB, ragged; };
 
 static DmhaPlan2 dmha_make_plan2(int x_dtype, int T, int D, int H) {
     DmhaPlan2 pl{};
     const bool bf16 = x_dtype == 1;
-    const int VE = bf16 ? 8 : 4, nvmax = bf16 ? 3 : 5;
+    const int VE = bf16 ? 8 : 4, nvmax = bf16 ? 3 : 5;        // <= 20-24 elements of a row per lane (96 registers, 2 CTAs/SM)
     if (H <= 0 || D <= 0 || D % H != 0) return pl;
     const int dh = D / H;
     if (dh % VE != 0) return pl;
@@ -578,14 +595,24 @@ static DmhaPlan2 dmha_make_plan2(int x_dtype, int T, int D, int H) {
     if (fps < S) fps = S;
     const int tcap = (T + S - 1) / S * S;
     if (fps > tcap) fps = tcap > 0 ? tcap : S;
-    pl.ok = 1; pl.G = G; pl.NV = (nvec + G - 1) / G; pl.S = S; pl.fps = fps; pl.stages = 3;
+    pl.ok = 1; pl.G = G; pl.NV = (nvec + G - 1) / G; pl.S = S; pl.fps = fps; pl.stages = 4;
+    // tuning overrides for sweeps (scripts/sweep_dmha.py); unset in production
+    if (const char* e = getenv("DASV_DMHA_FPS")) { const int v = atoi(e); if (v > 0) pl.fps = (v + S - 1) / S * S; }
+    if (const char* e = getenv("DASV_DMHA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 16) pl.stages = v; }
+    fps = pl.fps;
+    pl.ragged = (pl.G * pl.NV != nvec);                  // some lanes' vector slots fall outside the row
+    pl.FB = (!pl.ragged && fps % (2 * S) == 0) ? 2 : 1;
     return pl;
 }
 
 template <bool BF16>
 static int dispatch_fwd2(const DmhaPlan2& pl, const DmhaFwdParams& p, size_t smem, cudaStream_t s) {
 #define DASV_CASE2(g, nv) \
-    if (pl.G == g && pl.NV == nv) return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv>, p, smem, s);
+    if (pl.G == g && pl.NV == nv) { \
+        if (pl.ragged) return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv, 1, true>, p, smem, s); \
+        if (pl.FB == 2) return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv, 2, false>, p, smem, s); \
+        return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv, 1, false>, p, smem, s); \
+    }
 #define DASV_ROW2(g) DASV_CASE2(g, 1) DASV_CASE2(g, 2) DASV_CASE2(g, 3) \
     if constexpr (!BF16) { DASV_CASE2(g, 4) DASV_CASE2(g, 5) }
     DASV_ROW2(2) DASV_ROW2(4) DASV_ROW2(8) DASV_ROW2(16) DASV_ROW2(32)
@@ -624,6 +651,9 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
     if (p2.ok) {
         const uint32_t stage_bytes = static_cast<uint32_t>(p2.fps) * D * (bf16 ? 2 : 4);
         size_t smem = dmha_fwd_smem(D, H, p.dh, p2.S, p2.stages, stage_bytes).total;
+        // keep two CTAs per SM when a shallower ring allows it
+        if (!getenv("DASV_DMHA_STAGES"))
+            while (smem > 113 * 1024 && p2.stages > 3) smem = dmha_fwd_smem(D, H, p.dh, p2.S, --p2.stages, stage_bytes).total;
         while (smem > 227 * 1024 && p2.stages > 2) smem = dmha_fwd_smem(D, H, p.dh, p2.S, --p2.stages, stage_bytes).total;
         if (smem <= 227 * 1024) {
             p.fps = p2.fps; p.stages = p2.stages; p.S = p2.S;
