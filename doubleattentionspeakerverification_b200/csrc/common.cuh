@@ -125,6 +125,9 @@ DASV_DEVICE uint64_t umma_desc_k128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;                             // [61,64) SWIZZLE_128B
     return d;
 }
+// NB (measured on B200): an operand view may start at ANY 128-byte row of a swizzled tile with this same
+// descriptor -- the hardware applies the 128-byte swizzle to absolute SMEM address bits; encoding the row phase in
+// the base-offset field [49,52) instead gives wrong results.
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4)            // [4,6)   D format: f32

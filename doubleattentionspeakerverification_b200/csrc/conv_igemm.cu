@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
+#include <stdio.h>
 
 namespace dasv {
 
@@ -38,9 +40,12 @@ struct ConvParams {
     int kchunks;             // Cin / 64
     int stages;
     int pool, ref_layout, y_f32;
-    uint32_t b_bytes;        // bytes one B box delivers (N * 128)
-    uint32_t stage_bytes;    // A + B(padded) per ring stage
+    uint32_t b_bytes;        // bytes one B box delivers
+    uint32_t stage_bytes;    // per ring-1 stage: A + B(padded) (per-tap mode) or one B patch (tap-row reuse mode)
     uint32_t tmem_cols;
+    int reuse;               // 1: B patches carry a +-1 frame halo and serve the three taps of a column (dy = -1,0,1)
+    int tgap;                // halo rows per utterance in accumulator-column space (2 in reuse mode, else 0)
+    int sa;                  // reuse mode: stages of the separate A (weight tile) ring
 };
 
 struct ConvTile {
@@ -79,6 +84,9 @@ DASV_DEVICE void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+DASV_DEVICE void tmem_ld_x1(uint32_t taddr, uint32_t& r0) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
+}
 DASV_DEVICE void tmem_ld_x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
 }
@@ -95,11 +103,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand.
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    unsigned char* ring = smem;
-    unsigned char* stage = smem + static_cast<size_t>(p.stages) * p.stage_bytes;     // epilogue staging, 2 halves x 2 x kConvEpiBytes
+    unsigned char* ring = smem;                                                       // ring 1
+    unsigned char* ring_a = smem + static_cast<size_t>(p.stages) * p.stage_bytes;     // ring 2: weight tiles (reuse mode)
+    unsigned char* stage = ring_a + static_cast<size_t>(p.sa) * kConvABytes;          // epilogue staging, 2 halves x 2 x kConvEpiBytes
     uint64_t* full = reinterpret_cast<uint64_t*>(stage + 4 * kConvEpiBytes);
     uint64_t* empty = full + p.stages;
-    uint64_t* acc_full = empty + p.stages;      // [2]
+    uint64_t* afull = empty + p.stages;
+    uint64_t* aempty = afull + p.sa;
+    uint64_t* acc_full = aempty + p.sa;         // [2]
     uint64_t* acc_empty = acc_full + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -109,6 +120,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < p.sa; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_mbar_init();
     }
@@ -121,20 +133,43 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            uint32_t it = 0;
+        if (lane == 0 && p.reuse) {
+            // tap-row reuse: per (64-channel slice, dx) ONE activation patch with a +-1 frame halo, then the three
+            // weight tiles of that tap column (dy = -1, 0, +1); 3x less activation traffic than one box per tap.
+            uint32_t sb = 0, bph = 0, sa = 0, aph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const ConvTile c = conv_decode_tile(p, tile);
+                if (conv_tile_masked(p, c)) continue;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        mbar_wait(&empty[sb], bph ^ 1u);
+                        mbar_arrive_expect_tx(&full[sb], p.b_bytes);
+                        tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kc * kConvKC, c.f0 + dxi - 1, c.t0 - 1, c.b0);
+                        if (++sb == static_cast<uint32_t>(p.stages)) { sb = 0; bph ^= 1u; }
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            mbar_wait(&aempty[sa], aph ^ 1u);
+                            mbar_arrive_expect_tx(&afull[sa], kConvABytes);
+                            tma_load_2d(ring_a + static_cast<size_t>(sa) * kConvABytes, &tmA, &afull[sa],
+                                        (dyi * 3 + dxi) * p.Cin + kc * kConvKC, c.m * kConvTileM);
+                            if (++sa == static_cast<uint32_t>(p.sa)) { sa = 0; aph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            uint32_t st = 0, ph = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const ConvTile c = conv_decode_tile(p, tile);
                 if (conv_tile_masked(p, c)) continue;
                 for (int tap = 0; tap < 9; ++tap) {
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-                        const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty[st], ph ^ 1u);
                         unsigned char* a_sm = ring + static_cast<size_t>(st) * p.stage_bytes;
                         mbar_arrive_expect_tx(&full[st], kConvABytes + p.b_bytes);
                         tma_load_2d(a_sm, &tmA, &full[st], tap * p.Cin + kc * kConvKC, c.m * kConvTileM);
                         tma_load_4d(a_sm + kConvABytes, &tmB, &full[st], kc * kConvKC, c.f0 + dx, c.t0 + dy, c.b0);
+                        if (++st == static_cast<uint32_t>(p.stages)) { st = 0; ph ^= 1u; }
                     }
                 }
             }
@@ -143,26 +178,52 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kConvTileM, static_cast<uint32_t>(p.Npad));
-            uint32_t it = 0, acc_it = 0;
+            uint32_t st = 0, ph = 0, sa = 0, aph = 0, acc_it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const ConvTile c = conv_decode_tile(p, tile);
                 if (conv_tile_masked(p, c)) continue;
-                const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-                mbar_wait(&acc_empty[as], aph ^ 1u);
+                const uint32_t as = acc_it & 1u, accph = (acc_it >> 1) & 1u;
+                mbar_wait(&acc_empty[as], accph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * static_cast<uint32_t>(p.Npad);
-                for (int ks = 0; ks < ksteps; ++ks, ++it) {
-                    const uint32_t st = it % p.stages, ph = (it / p.stages) & 1u;
-                    mbar_wait(&full[st], ph);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
-                    const uint64_t a_desc = umma_desc_k128(a_addr);
-                    const uint64_t b_desc = umma_desc_k128(a_addr + kConvABytes);
+                if (p.reuse) {
+                    uint32_t first = 1u;
+                    for (int g = 0; g < 3 * p.kchunks; ++g) {           // (slice, dx) groups
+                        mbar_wait(&full[st], ph);
+                        const uint32_t b_addr = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            mbar_wait(&afull[sa], aph);
+                            tc_fence_after();
+                            const uint64_t a_desc = umma_desc_k128(smem_u32(ring_a + static_cast<size_t>(sa) * kConvABytes));
+                            // view of the patch shifted by dyi frames: BF rows of 128 B per frame
+                            // (the 128-byte swizzle is a function of absolute SMEM address bits, so a view may start at any row:
+                            //  measured on B200 -- the descriptor's base-offset field must stay 0 for this)
+                            const uint64_t b_desc = umma_desc_k128(b_addr + static_cast<uint32_t>(dyi * p.BF) * 128u);
 #pragma unroll
-                    for (int k = 0; k < kConvKC / 16; ++k)     // +32 B per 16-element K step inside the swizzle atom
-                        umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
-                                  (ks | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty[st]);                   // frees the ring slot when these MMAs retire
+                            for (int k = 0; k < kConvKC / 16; ++k)
+                                umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                                          (first && k == 0) ? 0u : 1u);
+                            first = 0u;
+                            umma_commit(&aempty[sa]);
+                            if (++sa == static_cast<uint32_t>(p.sa)) { sa = 0; aph ^= 1u; }
+                        }
+                        umma_commit(&empty[st]);               // patch free once its three tap rows have retired
+                        if (++st == static_cast<uint32_t>(p.stages)) { st = 0; ph ^= 1u; }
+                    }
+                } else {
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        mbar_wait(&full[st], ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
+                        const uint64_t a_desc = umma_desc_k128(a_addr);
+                        const uint64_t b_desc = umma_desc_k128(a_addr + kConvABytes);
+#pragma unroll
+                        for (int k = 0; k < kConvKC / 16; ++k)     // +32 B per 16-element K step inside the swizzle atom
+                            umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                                      (ks | k) != 0 ? 1u : 0u);
+                        umma_commit(&empty[st]);                   // frees the ring slot when these MMAs retire
+                        if (++st == static_cast<uint32_t>(p.stages)) { st = 0; ph ^= 1u; }
+                    }
                 }
                 umma_commit(&acc_full[as]);                    // accumulator complete -> epilogue
                 ++acc_it;
@@ -183,6 +244,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int OBF = p.pool ? BF / 2 : BF, OBT = p.pool ? BT / 2 : BT;   // output patch
         const int OT = p.pool ? T2 : T, OF = p.pool ? F2 : F;
         const int OPP = OBT * OBF;                              // output pixels per utterance of the patch
+        const int PR = BT + p.tgap;                             // accumulator-column rows per utterance (halo rows leave gaps)
         const int NO = p.BB * OPP;                              // output pixels per tile
         const float inv_obf = 1.0f / static_cast<float>(OBF), inv_opp = 1.0f / static_cast<float>(OPP);
         const int ch = q * 32 + lane;                           // channel within the 128-wide tile
@@ -212,7 +274,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const int t = c.t0 + 2 * tp;
                     if (b >= p.B || t >= T) continue;           // warp-uniform
                     const bool r0_ok = !masked && t < Lb, r1_ok = !masked && (t + 1) < Lb;
-                    const uint32_t col0 = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF);
+                    const uint32_t col0 = tcol + static_cast<uint32_t>((bb * PR + 2 * tp) * BF);
                     const size_t row = (static_cast<size_t>(b) * T2 + (t >> 1)) * (static_cast<size_t>(Cout) * F2) +
                                        static_cast<size_t>(n) * F2 + (c.f0 >> 1);
                     for (int fp0 = 0; fp0 < BF / 2; fp0 += 4) {
@@ -258,17 +320,30 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     // phase 1: this thread's channel of `cnt` output pixels -> staging[pixel][ch]
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + ch;
                     if (!p.pool) {
-                        uint32_t r0[16], r1[16];
-                        tmem_ld_x16(tcol + o0, r0);
-                        if (cnt > 16) tmem_ld_x16(tcol + o0 + 16, r1);          // warp-uniform
-                        tc_wait_ld();
+                        // output o of utterance bb sits in accumulator column o + bb * tgap * BF
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < cnt) dst[j * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r0[j]) + bias, 0.f));
-                        if (cnt > 16) {
+                        for (int g16 = 0; g16 < kConvEpiChunk / 16; ++g16) {
+                            const int oa = o0 + g16 * 16;
+                            if (g16 * 16 < cnt) {                                   // warp-uniform
+                                uint32_t r[16];
+                                const int bba = __float2int_rz((static_cast<float>(oa) + 0.5f) * inv_opp);
+                                const int bbz = __float2int_rz((static_cast<float>(min(oa + 15, NO - 1)) + 0.5f) * inv_opp);
+                                const int cola = oa + bba * p.tgap * BF;
+                                if (bba == bbz && cola + 16 <= p.Npad) {
+                                    tmem_ld_x16(tcol + cola, r);
+                                } else {                        // group straddles an utterance boundary (or the accumulator's end)
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (16 + j < cnt) dst[(16 + j) * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r1[j]) + bias, 0.f));
+                                    for (int j = 0; j < 16; ++j) {
+                                        const int bbj = __float2int_rz((static_cast<float>(min(oa + j, NO - 1)) + 0.5f) * inv_opp);
+                                        tmem_ld_x1(tcol + min(oa + j + bbj * p.tgap * BF, p.Npad - 1), r[j]);
+                                    }
+                                }
+                                tc_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (g16 * 16 + j < cnt)
+                                        dst[(g16 * 16 + j) * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias, 0.f));
+                            }
                         }
                     } else {
                         // output o -> (bb, tp, fp); window columns (bb*BT + 2tp)*BF + 2fp (+1, +BF, +BF+1)
@@ -282,7 +357,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (j0 + u < cnt) {             // warp-uniform
-                                    const uint32_t col = tcol + static_cast<uint32_t>((bb * BT + 2 * tp) * BF + 2 * fp);
+                                    const uint32_t col = tcol + static_cast<uint32_t>((bb * PR + 2 * tp) * BF + 2 * fp);
                                     r1[u] = (c.t0 + 2 * tp + 1) < Lcur;     // ceil-mode / masked second row
                                     tmem_ld_x2(col, v[u][0], v[u][1]);
                                     tmem_ld_x2(col + BF, v[u][2], v[u][3]);
@@ -365,9 +440,11 @@ struct ConvPlan {
     double cost;
 };
 
-// Pick the patch shape that minimises the modelled tensor time of the whole layer: per 16-deep
-// K step a 128 x Npad MMA costs max(Npad/2 tensor cycles, (128+Npad)/4 SMEM-read cycles).
-static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool) {
+// Pick the patch shape that minimises the modelled time of the whole layer.  Per 16-deep K step a 128 x Npad
+// MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
+// ~15 TB/s chip-wide), so a step also costs its operand bytes / 64.  `halo` = 2 in tap-row reuse mode (patches carry
+// +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
+static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo) {
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
     for (int BF = 2; BF <= F && BF <= 256; BF += 2) {
@@ -378,10 +455,13 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool) {
             const int n_tt = (T + BT - 1) / BT;
             const int bb_max = (n_tt == 1) ? 256 / (BF * BT) : 1;
             for (int BB = 1; BB <= bb_max && BB <= B; ++BB) {
-                const int N = BF * BT * BB, Npad = (N + 15) / 16 * 16;
+                const int N = (BB - 1) * (BT + halo) * BF + BT * BF;      // accumulator columns incl. halo gaps
+                const int Npad = (N + 15) / 16 * 16;
                 if (Npad > 256) continue;
                 const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB);
-                const double step = Npad / 2.0 > (128 + Npad) / 4.0 ? Npad / 2.0 : (128 + Npad) / 4.0;
+                const double b_rows = halo ? BB * (BT + 2.0) * BF / 3.0 : BB * BT * BF;   // activation rows fetched per tap
+                const double ingest = (128.0 + b_rows) * 32.0 / 64.0;                   // bytes per 16-deep step / 64 B/clk
+                const double step = Npad / 2.0 > ingest ? Npad / 2.0 : ingest;
                 const double cost = tiles * (step * ksteps + 700.0);
                 if (cost < best.cost) best = ConvPlan{BF, BT, BB, N, Npad, cost};
             }
@@ -413,9 +493,13 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     EncodeTiledFn encode = get_encode_tiled();
     if (!encode) { set_error("conv3x3_igemm_bf16: cuTensorMapEncodeTiled is not available from the CUDA driver"); return 1; }
 
-    const ConvPlan pl = conv_plan(B, T, F, Cin, pool);
+    // tap-row reuse is the default; DASV_CONV_REUSE=0 selects one TMA box per tap (A/B comparisons, debugging)
+    int reuse = 1;
+    if (const char* e = getenv("DASV_CONV_REUSE")) reuse = atoi(e) != 0;
+    const ConvPlan pl = conv_plan(B, T, F, Cin, pool, reuse ? 2 : 0);
     if (pl.N == 0) { set_error("conv3x3_igemm_bf16: no patch shape for T=%d F=%d", T, F); return 1; }
     const int cout_pad = (Cout + kConvTileM - 1) / kConvTileM * kConvTileM;
+    const int box_t = pl.BT + (reuse ? 2 : 0);
 
     CUtensorMap tmA, tmB;
     {
@@ -433,7 +517,7 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
                                     static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cin) * 2, static_cast<cuuint64_t>(F) * Cin * 2,
                                        static_cast<cuuint64_t>(T) * F * Cin * 2};
-        const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(pl.BT),
+        const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(box_t),
                                    static_cast<cuuint32_t>(pl.BB)};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
@@ -449,20 +533,38 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     p.n_ft = F / pl.BF; p.n_tt = (T + pl.BT - 1) / pl.BT; p.n_bt = (B + pl.BB - 1) / pl.BB; p.n_mt = cout_pad / kConvTileM;
     p.kchunks = Cin / kConvKC;
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
-    p.b_bytes = static_cast<uint32_t>(pl.N) * 128u;
-    p.stage_bytes = kConvABytes + ((static_cast<uint32_t>(pl.Npad) * 128u + 1023u) & ~1023u);
+    p.reuse = reuse; p.tgap = reuse ? 2 : 0;
+    p.b_bytes = static_cast<uint32_t>(pl.BB) * box_t * pl.BF * 128u;
     const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512;     // staging + alignment slack + barriers
-    int stages = static_cast<int>((227u * 1024u - kFixed) / p.stage_bytes);
-    if (stages > 8) stages = 8;
-    if (stages < 2) { set_error("conv3x3_igemm_bf16: ring does not fit shared memory"); return 1; }
-    p.stages = stages;
+    const uint32_t kAvail = 227u * 1024u - kFixed;
+    if (reuse) {
+        // ring 1 = activation patches (+ the rows a 16-padded, 2-frame-shifted MMA view may touch), ring 2 = weight tiles
+        p.stage_bytes = ((static_cast<uint32_t>(pl.Npad) + 2u * pl.BF) * 128u + 1023u) & ~1023u;
+        if (p.stage_bytes < p.b_bytes) p.stage_bytes = (p.b_bytes + 1023u) & ~1023u;
+        int sb = 3;
+        int sa = (static_cast<int>(kAvail) - sb * static_cast<int>(p.stage_bytes)) / static_cast<int>(kConvABytes);
+        if (sa < 5) { sb = 2; sa = (static_cast<int>(kAvail) - sb * static_cast<int>(p.stage_bytes)) / static_cast<int>(kConvABytes); }
+        if (sa > 12) sa = 12;
+        if (sa < 3) { set_error("conv3x3_igemm_bf16: rings do not fit shared memory"); return 1; }
+        if (const char* e = getenv("DASV_CONV_SB")) { const int v = atoi(e); if (v >= 2 && v <= 4) { sb = v; sa = (static_cast<int>(kAvail) - sb * static_cast<int>(p.stage_bytes)) / static_cast<int>(kConvABytes); if (sa > 12) sa = 12; } }
+        p.stages = sb; p.sa = sa;
+    } else {
+        p.stage_bytes = kConvABytes + ((static_cast<uint32_t>(pl.Npad) * 128u + 1023u) & ~1023u);
+        int stages = static_cast<int>(kAvail / p.stage_bytes);
+        if (stages > 8) stages = 8;
+        if (stages < 2) { set_error("conv3x3_igemm_bf16: ring does not fit shared memory"); return 1; }
+        p.stages = stages; p.sa = 0;
+    }
     uint32_t cols = 32;
     while (cols < 2u * pl.Npad) cols <<= 1;
     p.tmem_cols = cols;
+    if (getenv("DASV_CONV_DEBUG"))
+        fprintf(stderr, "conv plan: B=%d T=%d F=%d Cin=%d Cout=%d pool=%d reuse=%d BF=%d BT=%d BB=%d N=%d Npad=%d stages=%d sa=%d stage_bytes=%u b_bytes=%u\n",
+                B, T, F, Cin, Cout, (int)pool, reuse, pl.BF, pl.BT, pl.BB, pl.N, pl.Npad, p.stages, p.sa, p.stage_bytes, p.b_bytes);
     const long long n_tiles = static_cast<long long>(p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
     if (n_tiles > 0x7fffffffLL) { set_error("conv3x3_igemm_bf16: too many tiles"); return 1; }
 
-    const size_t smem = static_cast<size_t>(stages) * p.stage_bytes + kFixed;
+    const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + static_cast<size_t>(p.sa) * kConvABytes + kFixed;
     cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
     int dev = 0, sms = 0;
