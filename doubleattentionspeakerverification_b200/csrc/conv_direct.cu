@@ -37,45 +37,73 @@ __global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restr
         if (tt >= 0 && tt < L && ff >= 0 && ff < F) v = x[(static_cast<size_t>(b) * T + tt) * F + ff];
         x_sm[i] = v;                      // input rows >= L count as zero (masking rule)
     }
-    float wr[9][8], br[8];
+    uint64_t wr2[9][4], br2[4];             // channel pairs (e, e+1) packed for fma.rn.f32x2
     if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            br[e] = bias[cg * 8 + e];
+        for (int e = 0; e < 8; e += 2) {
+            br2[e >> 1] = pack_f32x2(bias[cg * 8 + e], bias[cg * 8 + e + 1]);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) wr[tap][e] = w[(cg * 8 + e) * 9 + tap];   // reference layout [Cout,1,3,3]
+            for (int tap = 0; tap < 9; ++tap)   // reference layout [Cout,1,3,3]
+                wr2[tap][e >> 1] = pack_f32x2(w[(cg * 8 + e) * 9 + tap], w[(cg * 8 + e + 1) * 9 + tap]);
         }
     }
     __syncthreads();
     if (!active) return;
     const size_t row_elems = static_cast<size_t>(F) * Cout;
-    for (int p = pl; p < rows * F; p += PL) {
-        const int tl = p / F, f = p - tl * F;
+    // Two horizontally adjacent pixels per iteration (they share 12 of their 18 input taps); the FMAs are packed
+    // fma.rn.f32x2 (sm_100) over channel pairs: acc{c,c+1} += x{p,p} * w{c,c+1} -- half the FMA instruction issue.
+    const int halfF = F >> 1;                                  // F is even (checked by the host)
+    for (int p = pl; p < rows * halfF; p += PL) {
+        const int tl = p / halfF, f = (p - tl * halfF) * 2;
         const int t = t0 + tl;
-        float acc[8];
+        float xv[3][4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = br[e];
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xv[dy][j] = x_sm[(tl + dy) * W2 + f + j];
+        uint64_t accA[4], accB[4];               // pixel f and pixel f+1
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { accA[e] = br2[e]; accB[e] = br2[e]; }
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const float xv = x_sm[(tl + dy) * W2 + f + dx];
+                const uint64_t xa = pack_f32x2(xv[dy][dx], xv[dy][dx]);
+                const uint64_t xb = pack_f32x2(xv[dy][dx + 1], xv[dy][dx + 1]);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, wr[dy * 3 + dx][e], acc[e]);
+                for (int e = 0; e < 4; ++e) {
+                    accA[e] = fma_f32x2(xa, wr2[dy * 3 + dx][e], accA[e]);
+                    accB[e] = fma_f32x2(xb, wr2[dy * 3 + dx][e], accB[e]);
+                }
             }
         const bool valid = t < L;
+        float a0[8], a1[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = valid ? fmaxf(acc[e], 0.f) : 0.f;
+        for (int e = 0; e < 4; ++e) {
+            unpack_f32x2(accA[e], a0[2 * e], a0[2 * e + 1]);
+            unpack_f32x2(accB[e], a1[2 * e], a1[2 * e + 1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            a0[e] = valid ? fmaxf(a0[e], 0.f) : 0.f;
+            a1[e] = valid ? fmaxf(a1[e], 0.f) : 0.f;
+        }
         const size_t o = (static_cast<size_t>(b) * T + t) * row_elems + static_cast<size_t>(f) * Cout + cg * 8;
         if (OUT_BF16) {
             uint4 v;
-            v.x = pack_bf16(acc[0], acc[1]); v.y = pack_bf16(acc[2], acc[3]);
-            v.z = pack_bf16(acc[4], acc[5]); v.w = pack_bf16(acc[6], acc[7]);
+            v.x = pack_bf16(a0[0], a0[1]); v.y = pack_bf16(a0[2], a0[3]);
+            v.z = pack_bf16(a0[4], a0[5]); v.w = pack_bf16(a0[6], a0[7]);
             *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + o) = v;
+            v.x = pack_bf16(a1[0], a1[1]); v.y = pack_bf16(a1[2], a1[3]);
+            v.z = pack_bf16(a1[4], a1[5]); v.w = pack_bf16(a1[6], a1[7]);
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + o + Cout) = v;
         } else {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(y) + o);
-            op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            op[0] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+            op[1] = make_float4(a0[4], a0[5], a0[6], a0[7]);
+            float4* oq = reinterpret_cast<float4*>(static_cast<float*>(y) + o + Cout);
+            oq[0] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+            oq[1] = make_float4(a1[4], a1[5], a1[6], a1[7]);
         }
     }
 }
@@ -219,6 +247,7 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
     if (Cout % 8 != 0 || Cout <= 0) { set_error("conv11_direct: Cout=%d must be a positive multiple of 8", Cout); return 1; }
     if (y_dtype != 0 && y_dtype != 1) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
     if (Cout > 2048) { set_error("conv11_direct: Cout=%d > 2048", Cout); return 1; }
+    if (F % 2 != 0) { set_error("conv11_direct: F=%d must be even", F); return 1; }
     if (B <= 0 || T <= 0) return 0;
     const size_t smem = static_cast<size_t>(kC11Rows + 2) * (F + 2) * sizeof(float);
     if (smem > 48 * 1024) { set_error("conv11_direct: F=%d too wide", F); return 1; }
