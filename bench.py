@@ -23,6 +23,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# keep stdout to the single JSON line: NCCL's version / debug banner goes to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
 
 import numpy as np   # noqa: E402
 import torch         # noqa: E402

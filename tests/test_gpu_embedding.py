@@ -123,3 +123,77 @@ def test_training_step_through_fused_pooling():
     for n in g_ref:
         assert max_rel(g_fused[n].cpu().numpy(), g_ref[n].cpu().numpy()) < 2e-3, n
     assert 'poolingLayer.utteranceAttention.query' in g_fused and 'front_end.conv11.weight' in g_fused
+
+
+def _example_net(precision='bf16', seed=1234):
+    cfg = synth.example_config()
+    cfg.precision = precision
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, seed)).cuda().eval()
+    return net
+
+
+def test_full_size_batch_properties():
+    """BASELINE configs[2] size (256 x 400 x 80, exampleModel, bf16): size-independent properties of the extractor —
+    permutation equivariance, invariance to what sits in the padding, and agreement with small-batch runs."""
+    net = _example_net()
+    x = dev(synth.make_logmel(256, 400, seed=5))
+    with torch.no_grad():
+        e = net.getEmbedding(x)
+        assert e.shape == (256, 400) and bool(torch.isfinite(e).all())
+        perm = torch.randperm(256, generator=torch.Generator().manual_seed(0)).cuda()
+        ep = net.getEmbedding(x[perm].contiguous())
+        assert torch.equal(ep, e[perm])                              # utterances do not interact (eval-mode BN)
+        small = net.getEmbedding(x[:3].contiguous())                 # other tile shapes / summation order
+        assert min_cosine(small.cpu().numpy(), e[:3].cpu().numpy()) > 0.99999
+        lengths = torch.full((256,), 400, dtype=torch.int32, device='cuda')
+        lengths[::2] = 333
+        el = net.getEmbedding(x, lengths=lengths)
+        x2 = x.clone()
+        x2[::2, 333:] = 1e3                                          # garbage in the padding must not matter
+        el2 = net.getEmbedding(x2, lengths=lengths)
+        assert torch.equal(el, el2)
+        assert torch.equal(el[1::2], e[1::2])                        # full-length rows unchanged by their neighbours' masks
+        cut = net.getEmbedding(x[:4:2, :333].contiguous())           # masked == truncated
+        assert min_cosine(cut.cpu().numpy(), el[:4:2].cpu().numpy()) > 0.99999
+
+
+def test_variable_length_extraction_and_trials():
+    """configs[3]/[4] at reduced scale: 2-20 s utterances through the batched extractor == per-utterance batch-1
+    runs; trial scores from the batched scoring kernels == the oracle's cosine on the same embeddings."""
+    from doubleattentionspeakerverification_b200 import extract
+    net = _example_net()
+    rs = np.random.RandomState(3)
+    feats = [synth.make_logmel(1, int(T), seed=100 + i)[0] for i, T in enumerate(rs.randint(200, 2001, size=10))]
+
+    def embed(xb, L):
+        with torch.no_grad():
+            return net.getEmbedding(xb, lengths=L)
+
+    emb = extract.extract_sharded(embed, feats, 'cuda', max_frames=6000)
+    with torch.no_grad():
+        single = torch.cat([net.getEmbedding(dev(f[None])) for f in feats])
+    assert min_cosine(emb.cpu().numpy(), single.cpu().numpy()) > 0.9999
+    trials = np.stack([rs.randint(0, 10, 200), rs.randint(0, 10, 200)], 1)
+    s = extract.score_trial_list(emb, trials).cpu().numpy()
+    e = emb.cpu().numpy()
+    assert np.max(np.abs(s - po.cosine_scores(e[trials[:, 0]], e[trials[:, 1]]))) < 1e-5
+    s_single = po.cosine_scores(single.cpu().numpy()[trials[:, 0]], single.cpu().numpy()[trials[:, 1]])
+    assert np.max(np.abs(s - s_single)) < 1e-3                       # north_star trial-score bar
+    m = extract.score_cross(emb, np.arange(5), np.arange(5, 10)).cpu().numpy()
+    assert np.max(np.abs(m - po.cosine_matrix(e[:5], e[5:]))) < 1e-5
+
+
+def test_million_trial_scoring_properties():
+    """configs[4] size: 1024 x 1024 cross-product = 1 048 576 trials on synthetic embeddings; properties of the
+    score matrix (self-score 1, symmetry, range) and agreement of the pair-list kernel with the matrix kernel."""
+    g = torch.Generator(device='cuda').manual_seed(1)
+    e = torch.randn(2048, 400, device='cuda', generator=g)
+    m = utils.score_matrix(e[:1024].contiguous(), e[1024:].contiguous())
+    assert m.shape == (1024, 1024) and float(m.abs().max()) <= 1.0 + 1e-5
+    full = utils.score_matrix(e[:1024].contiguous(), e[:1024].contiguous())
+    assert float((full.diagonal() - 1).abs().max()) < 1e-5
+    assert float((full - full.t()).abs().max()) < 1e-6
+    ia = torch.arange(1024, device='cuda').repeat_interleave(1024)
+    ib = torch.arange(1024, 2048, device='cuda').repeat(1024)
+    p = utils.score_pairs(e, ia, ib)
+    assert p.numel() == 1 << 20 and float((p.view(1024, 1024) - m).abs().max()) < 1e-5
