@@ -16,7 +16,8 @@ _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
 SIGNATURES = {
     'dasv_abi_version': (_i, []),
     'dasv_last_error': (_c.c_char_p, []),
-    'dasv_dmha_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'dasv_dmha_fwd_workspace_bytes': (_sz, [_i, _i, _i, _i]),
+    'dasv_dmha_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dasv_dmha_bwd_workspace_bytes': (_sz, [_i, _i, _i, _i]),
     'dasv_dmha_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dasv_attention_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -52,6 +52,53 @@ DASV_DEVICE float warp_max(float v) {
     return v;
 }
 
+struct DmhaFwdParams {
+    const unsigned char* x;
+    const int32_t* lengths;
+    const float* query;
+    const float* att;
+    const uint8_t* keep;
+    float* out;
+    float* ctx;
+    float* lse;
+    float* headw;
+    float* align;
+    int B, T, D, H, dh;
+    int fps, stages, S;
+    float scale_log2;   // log2(e) / sqrt(H): scores are kept in log2 units for ex2.approx
+    // stream-split mode (dmha_fwd2.cu): per-(CTA, utterance) partial states and per-utterance tickets
+    float* ws_part;
+    int* ws_cnt;
+    int split;
+    long long Q;        // frames of the flattened (utterance, frame) stream owned by one CTA
+};
+
+struct DmhaFwdSmem {
+    uint32_t ring, q, a, pacc, pm, pl, u, w, bars, total;
+};
+
+__host__ __device__ inline DmhaFwdSmem dmha_fwd_smem(int D, int H, int dh, int S, int stages, uint32_t stage_bytes) {
+    DmhaFwdSmem s;
+    uint32_t o = 0;
+    s.ring = o; o += stages * stage_bytes;
+    s.q = o;    o += D * 4;
+    s.a = o;    o += dh * 4;
+    s.pacc = o; o += S * D * 4;
+    s.pm = o;   o += H * S * 4;
+    s.pl = o;   o += H * S * 4;
+    s.u = o;    o += H * 4;
+    s.w = o;    o += H * 4;
+    o = (o + 7u) & ~7u;
+    s.bars = o; o += 2 * stages * 8;
+    s.total = o;
+    return s;
+}
+
+
+// v2 forward (dmha_fwd2.cu): returns 0 = launched, 1 = error (message set), -1 = shape outside its mapping.
+int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream);
+size_t dmha_fwd2_workspace_bytes(int B, int D, int H);
+
 // Host-side plan shared by forward and backward so both walk the ring identically.
 DmhaPlan dmha_make_plan(int x_dtype, int T, int D, int H, bool backward);
 

@@ -9,43 +9,6 @@
 
 namespace dasv {
 
-struct DmhaFwdParams {
-    const unsigned char* x;
-    const int32_t* lengths;
-    const float* query;
-    const float* att;
-    const uint8_t* keep;
-    float* out;
-    float* ctx;
-    float* lse;
-    float* headw;
-    float* align;
-    int B, T, D, H, dh;
-    int fps, stages, S;
-    float scale_log2;   // log2(e) / sqrt(H): scores are kept in log2 units for ex2.approx
-};
-
-struct DmhaFwdSmem {
-    uint32_t ring, q, a, pacc, pm, pl, u, w, bars, total;
-};
-
-__host__ __device__ inline DmhaFwdSmem dmha_fwd_smem(int D, int H, int dh, int S, int stages, uint32_t stage_bytes) {
-    DmhaFwdSmem s;
-    uint32_t o = 0;
-    s.ring = o; o += stages * stage_bytes;
-    s.q = o;    o += D * 4;
-    s.a = o;    o += dh * 4;
-    s.pacc = o; o += S * D * 4;
-    s.pm = o;   o += H * S * 4;
-    s.pl = o;   o += H * S * 4;
-    s.u = o;    o += H * 4;
-    s.w = o;    o += H * 4;
-    o = (o + 7u) & ~7u;
-    s.bars = o; o += 2 * stages * 8;
-    s.total = o;
-    return s;
-}
-
 // Per-utterance tail shared by both consumer mappings: merge the S partial (max, sum, weighted sum) states of
 // every head, finish ctx / lse, then the attention over heads (poolings.py:45-51,61-71) and the alignment fix-up.
 DASV_DEVICE void dmha_fwd_finish(const DmhaFwdParams& p, int b, int Lb, int warp, int lane, int tid,
@@ -325,192 +288,6 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd_min_ctas<BF16, NV, HPG>
     }
 }
 
-// ---------------------------------------------------------------------------------- v2 consumer mapping
-// The kernel above keeps one 16-byte vector per lane (a head row is spread over up to 32 lanes), which makes
-// the per-row shuffle reduction and the redundant softmax bookkeeping dominate: ncu showed it issue-bound
-// (71 % issue-active, 0.74 warp instructions per input float) at 47 % of DRAM throughput.  v2 gives a lane
-// NV vectors (16-24 elements) of a (frame, head) row, G = 2..32 lanes per row, so a row costs log2(G) shuffles,
-// and rescales the running sums lazily (only when the running max grows by > 2^kLazy), ~0.1 warp
-// instructions per float.  Row groups of one LDS.128 phase start at different vectors (rot) so that rows whose
-// byte size is a multiple of 128 do not collide on the same banks.
-constexpr float kDmhaLazy = 8.0f;
-
-template <bool BF16, int NV>
-constexpr int dmha_fwd2_min_ctas() { return (NV * (BF16 ? 8 : 4) <= 12) ? 3 : 2; }
-
-template <bool BF16, int G, int NV, int FB, bool RAGGED>
-__global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) dmha_fwd2_kernel(const DmhaFwdParams p) {
-    constexpr int VE = BF16 ? 8 : 4;
-    constexpr uint32_t ES = BF16 ? 2u : 4u;
-    constexpr int RPW = 32 / G;                                 // (frame, head) rows per warp
-    constexpr int GPP = (G >= 8) ? 1 : 8 / G;                   // row groups per 8-lane LDS.128 phase
-    extern __shared__ __align__(128) unsigned char smem[];
-
-    const int D = p.D, H = p.H, dh = p.dh, S = p.S, T = p.T;
-    const uint32_t frame_bytes = static_cast<uint32_t>(D) * ES;
-    const uint32_t stage_bytes = p.fps * frame_bytes;
-    const DmhaFwdSmem L = dmha_fwd_smem(D, H, dh, S, p.stages, stage_bytes);
-    unsigned char* ring = smem + L.ring;
-    float* q_sm = reinterpret_cast<float*>(smem + L.q);
-    float* a_sm = reinterpret_cast<float*>(smem + L.a);
-    float* pacc = reinterpret_cast<float*>(smem + L.pacc);
-    float* pm = reinterpret_cast<float*>(smem + L.pm);
-    float* pl = reinterpret_cast<float*>(smem + L.pl);
-    float* u_sm = reinterpret_cast<float*>(smem + L.u);
-    float* w_sm = reinterpret_cast<float*>(smem + L.w);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
-    uint64_t* empty = full + p.stages;
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-
-    if (tid == 0) {
-        for (int i = 0; i < p.stages; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], kDmhaConsumerWarps);
-        }
-        fence_mbar_init();
-    }
-    for (int i = tid; i < D; i += kDmhaThreads) {
-        const int h = i / dh, d = i - h * dh;
-        q_sm[i] = p.query[d * H + h];               // reference layout [dh, H] (poolings.py:90)
-    }
-    if (p.att != nullptr)
-        for (int i = tid; i < dh; i += kDmhaThreads) a_sm[i] = p.att[i];
-    __syncthreads();
-
-    if (warp == kDmhaConsumerWarps) {
-        if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
-            int st = 0;
-            uint32_t ph = 0;
-            for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-                int Lb = p.lengths ? p.lengths[b] : T;
-                Lb = max(0, min(Lb, T));
-                const unsigned char* xb = p.x + static_cast<size_t>(b) * T * frame_bytes;
-                for (int f0 = 0; f0 < Lb; f0 += p.fps) {
-                    mbar_wait(&empty[st], ph ^ 1u);
-                    const uint32_t bytes = static_cast<uint32_t>(min(p.fps, Lb - f0)) * frame_bytes;
-                    mbar_arrive_expect_tx(&full[st], bytes);
-                    bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
-                    if (++st == p.stages) { st = 0; ph ^= 1u; }
-                }
-            }
-        }
-        return;
-    }
-
-    // ---------------------------------------------------------------- consumers
-    const int grp = warp * RPW + lane / G, lig = lane % G;
-    const int head = grp % H, slot = grp / H;       // this group's head and frame slot (frames f = slot mod S)
-    const bool active = slot < S;
-    const int rot = (lane / G) % GPP;
-    uint32_t voff[NV];
-    bool vok[NV];
-    float qreg[NV][VE];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        const int idx = ((v + rot) % NV) * G + lig;             // 16-byte vector of the row held in slot v
-        vok[v] = active && idx * VE < dh;
-        voff[v] = static_cast<uint32_t>(head) * dh * ES + static_cast<uint32_t>(idx) * 16u;
-#pragma unroll
-        for (int e = 0; e < VE; ++e) qreg[v][e] = vok[v] ? q_sm[head * dh + idx * VE + e] : 0.f;
-    }
-
-    int st = 0;
-    uint32_t ph = 0;
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        int Lb = p.lengths ? p.lengths[b] : T;
-        Lb = max(0, min(Lb, T));
-        float m = -INFINITY, l = 0.f, acc[NV][VE];
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int e = 0; e < VE; ++e) acc[v][e] = 0.f;
-
-        for (int f0 = 0; f0 < Lb; f0 += p.fps) {
-            mbar_wait(&full[st], ph);
-            const int nf = min(p.fps, Lb - f0);
-            const unsigned char* sbase = ring + st * stage_bytes;
-            // FB (frame, head) rows per trip: rows fb+slot and fb+S+slot are independent until the softmax
-            // update, which gives the LDS -> FMA -> shuffle -> exp2 chain a second row to overlap with.
-            for (int fb = 0; fb < nf; fb += FB * S) {            // warp-uniform trip count (fps is a multiple of S)
-                float xs[FB][NV][VE];
-                float sc[FB];
-                bool valid[FB];
-#pragma unroll
-                for (int r = 0; r < FB; ++r) {
-                    const int f = fb + r * S + slot;
-                    valid[r] = active && f < nf;
-                    const unsigned char* row = sbase + static_cast<uint32_t>(valid[r] ? f : 0) * frame_bytes;   // safe address when idle
-                    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        if (RAGGED && !vok[v]) {
-#pragma unroll
-                            for (int e = 0; e < VE; ++e) xs[r][v][e] = 0.f;
-                        } else {
-                            load_row_vec<VE, BF16>(row + voff[v], xs[r][v]);
-                        }
-#pragma unroll
-                        for (int e = 0; e < VE; e += 2) {
-                            s0 = fmaf(xs[r][v][e], qreg[v][e], s0);
-                            s1 = fmaf(xs[r][v][e + 1], qreg[v][e + 1], s1);
-                        }
-                    }
-                    sc[r] = s0 + s1;
-                }
-#pragma unroll
-                for (int r = 0; r < FB; ++r) sc[r] = group_sum<G>(sc[r]);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int r = 0; r < FB; ++r) {
-                    sc[r] = valid[r] ? sc[r] * p.scale_log2 : -INFINITY;     // log2-unit score of this (frame, head)
-                    mx = fmaxf(mx, sc[r]);
-                    if (p.align != nullptr && valid[r] && lig == 0)
-                        p.align[(static_cast<size_t>(b) * T + f0 + fb + r * S + slot) * H + head] = sc[r];   // raw score, normalised below
-                }
-                if (mx > m + kDmhaLazy) {                        // lazy rescale; first frame: m = -inf -> corr = 0
-                    const float corr = fast_exp2(m - mx);
-                    l *= corr;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) acc[v][e] *= corr;
-                    m = mx;
-                }
-                const float mref = (m == -INFINITY) ? 0.f : m;  // idle group: exp2(-inf - 0) = 0
-#pragma unroll
-                for (int r = 0; r < FB; ++r) {
-                    const float pr = fast_exp2(sc[r] - mref);
-                    l += pr;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v)
-#pragma unroll
-                        for (int e = 0; e < VE; ++e) acc[v][e] = fmaf(pr, xs[r][v][e], acc[v][e]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
-            if (++st == p.stages) { st = 0; ph ^= 1u; }
-        }
-
-        // ------------------------------------------------------------ merge the S frame slots, head stage
-        if (active) {
-            const int sl = head * S + slot;
-            if (lig == 0) { pm[sl] = m; pl[sl] = l; }
-#pragma unroll
-            for (int v = 0; v < NV; ++v)
-                if (vok[v]) {
-                    const int idx = ((v + rot) % NV) * G + lig;
-#pragma unroll
-                    for (int e = 0; e < VE; ++e) pacc[sl * dh + idx * VE + e] = acc[v][e];
-                }
-        }
-        named_bar_sync(1, kDmhaConsumerThreads);
-        dmha_fwd_finish(p, b, Lb, warp, lane, tid, pacc, pm, pl, u_sm, w_sm, a_sm);
-    }
-}
-
 // ---------------------------------------------------------------------------------- host side
 DmhaPlan dmha_make_plan(int x_dtype, int T, int D, int H, bool backward) {
     DmhaPlan pl{};
@@ -572,63 +349,13 @@ static int dispatch_fwd(const DmhaPlan& pl, const DmhaFwdParams& p, size_t smem,
     return 1;
 }
 
-// v2 mapping: NV vectors per lane (<= 5 fp32 / 3 bf16), G = 2..32 lanes per row, needs H <= 256/G row groups.
-struct DmhaPlan2 { int ok, G, NV, S, fps, stages, FB, ragged; };
-
-static DmhaPlan2 dmha_make_plan2(int x_dtype, int T, int D, int H) {
-    DmhaPlan2 pl{};
-    const bool bf16 = x_dtype == 1;
-    const int VE = bf16 ? 8 : 4, nvmax = bf16 ? 3 : 5;        // <= 20-24 elements of a row per lane (96 registers, 2 CTAs/SM)
-    if (H <= 0 || D <= 0 || D % H != 0) return pl;
-    const int dh = D / H;
-    if (dh % VE != 0) return pl;
-    const int nvec = dh / VE;
-    int G = 2;
-    while (G <= 32 && (nvec + G - 1) / G > nvmax) G <<= 1;
-    if (G > 32) return pl;
-    const int ngrp = kDmhaConsumerThreads / G;
-    if (H > ngrp) return pl;
-    int S = ngrp / H;
-    if (S > 8) S = 8;
-    const size_t frame_bytes = static_cast<size_t>(D) * (bf16 ? 2 : 4);
-    int fps = static_cast<int>((16 * 1024) / frame_bytes) / S * S;
-    if (fps < S) fps = S;
-    const int tcap = (T + S - 1) / S * S;
-    if (fps > tcap) fps = tcap > 0 ? tcap : S;
-    pl.ok = 1; pl.G = G; pl.NV = (nvec + G - 1) / G; pl.S = S; pl.fps = fps; pl.stages = 4;
-    // tuning overrides for sweeps (scripts/sweep_dmha.py); unset in production
-    if (const char* e = getenv("DASV_DMHA_FPS")) { const int v = atoi(e); if (v > 0) pl.fps = (v + S - 1) / S * S; }
-    if (const char* e = getenv("DASV_DMHA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 16) pl.stages = v; }
-    fps = pl.fps;
-    pl.ragged = (pl.G * pl.NV != nvec);                  // some lanes' vector slots fall outside the row
-    pl.FB = (!pl.ragged && fps % (2 * S) == 0) ? 2 : 1;
-    return pl;
-}
-
-template <bool BF16>
-static int dispatch_fwd2(const DmhaPlan2& pl, const DmhaFwdParams& p, size_t smem, cudaStream_t s) {
-#define DASV_CASE2(g, nv) \
-    if (pl.G == g && pl.NV == nv) { \
-        if (pl.ragged) return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv, 1, true>, p, smem, s); \
-        if (pl.FB == 2) return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv, 2, false>, p, smem, s); \
-        return launch_fwd_kernel(dmha_fwd2_kernel<BF16, g, nv, 1, false>, p, smem, s); \
-    }
-#define DASV_ROW2(g) DASV_CASE2(g, 1) DASV_CASE2(g, 2) DASV_CASE2(g, 3) \
-    if constexpr (!BF16) { DASV_CASE2(g, 4) DASV_CASE2(g, 5) }
-    DASV_ROW2(2) DASV_ROW2(4) DASV_ROW2(8) DASV_ROW2(16) DASV_ROW2(32)
-#undef DASV_ROW2
-#undef DASV_CASE2
-    set_error("dmha_fwd: no v2 kernel for G=%d NV=%d", pl.G, pl.NV);
-    return 1;
-}
-
 }  // namespace dasv
 
 using namespace dasv;
 
 extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
                              const float* query, const float* att, const uint8_t* keep,
-                             float* out, float* ctx, float* lse, float* headw, float* align,
+                             float* out, float* ctx, float* lse, float* headw, float* align, void* workspace,
                              int B, int T, int D, int H, void* stream) {
     if (B < 0 || T < 0) { set_error("dmha_fwd: negative shape"); return 1; }
     if (B == 0) return 0;
@@ -643,22 +370,14 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
     p.lengths = lengths; p.query = query; p.att = att; p.keep = keep;
     p.out = out; p.ctx = ctx; p.lse = lse; p.headw = headw; p.align = align;
     p.B = B; p.T = T; p.D = D; p.H = H; p.dh = H > 0 ? D / H : 0;
+    p.ws_part = nullptr; p.ws_cnt = nullptr; p.split = 0; p.Q = 0;
     p.scale_log2 = kLog2e / sqrtf(static_cast<float>(H));     // d_k = query.size(-1) = H (poolings.py:75)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool bf16 = x_dtype == 1;
 
-    DmhaPlan2 p2 = dmha_make_plan2(x_dtype, T, D, H);
-    if (p2.ok) {
-        const uint32_t stage_bytes = static_cast<uint32_t>(p2.fps) * D * (bf16 ? 2 : 4);
-        size_t smem = dmha_fwd_smem(D, H, p.dh, p2.S, p2.stages, stage_bytes).total;
-        // keep two CTAs per SM when a shallower ring allows it
-        if (!getenv("DASV_DMHA_STAGES"))
-            while (smem > 113 * 1024 && p2.stages > 3) smem = dmha_fwd_smem(D, H, p.dh, p2.S, --p2.stages, stage_bytes).total;
-        while (smem > 227 * 1024 && p2.stages > 2) smem = dmha_fwd_smem(D, H, p.dh, p2.S, --p2.stages, stage_bytes).total;
-        if (smem <= 227 * 1024) {
-            p.fps = p2.fps; p.stages = p2.stages; p.S = p2.S;
-            return bf16 ? dispatch_fwd2<true>(p2, p, smem, s) : dispatch_fwd2<false>(p2, p, smem, s);
-        }
+    {   // v2 mapping (dmha_fwd2.cu): 0 = launched, 1 = error, -1 = shape outside the mapping
+        const int r = dmha_fwd2_launch(p, x_dtype, workspace, s);
+        if (r >= 0) return r;
     }
     // shapes outside the v2 mapping (more heads than row groups, very wide rows): v1 mapping
     DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, false);

@@ -1,0 +1,533 @@
+// Fused DoubleMHA pooling forward, v2 mapping (the default path of dasv_dmha_fwd).
+// Replaces scripts/poolings.py:73-80, :100-109, :45-51, :61-71, :126-129 with ONE pass over x.
+//
+// Roofline: HBM.  Algorithmic bytes = sum_b L_b * D * sizeof(x) (+ outputs).  What ncu showed on the way here:
+//   * one 16-byte vector per lane (v1, dmha_fwd.cu) is instruction-issue bound (0.74 warp instructions per input
+//     float): the per-row shuffle reduction and the redundant softmax bookkeeping dominate.  Here a lane owns NV
+//     vectors (16-24 elements) of a (frame, head) row, G = 2..32 lanes per row, so a row costs log2(G) shuffles; the
+//     running sums are rescaled lazily (only when the running max grows by > 2^kLazy); the multiply-adds are packed
+//     fma.rn.f32x2 (sm_100), two elements per instruction.
+//   * whole utterances per CTA quantise badly (512 utterances on 148 SMs = 3.46 per SM -> 4 vs 3).  An optional
+//     stream-split schedule (DASV_DMHA_SPLIT=1) cuts the flattened (utterance, frame) stream into equal per-CTA
+//     ranges: a CTA that holds only part of an utterance writes its partial (max, sum, weighted sum) state to a
+//     workspace and takes a ticket, the last arrival merges the parts and runs the attention over heads.  Measured
+//     slower than the whole-utterance schedule (the per-segment finish outweighs the tail), so it is off by default.
+//   * Row groups of one LDS.128 phase start at different vectors (rot) so that rows whose byte size is a multiple
+//     of 128 do not collide on the same banks.
+#include "dmha_common.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace dasv {
+
+constexpr float kDmhaLazy = 8.0f;
+constexpr int kDmha2MaxGrid = 1024;
+
+DASV_DEVICE uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+DASV_DEVICE uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+
+// one 16-byte vector of a row as packed fp32 pairs: 2 pairs (fp32 input) or 4 pairs (bf16 input)
+template <int VE, bool BF16>
+DASV_DEVICE void load_row_pairs(const unsigned char* p, uint64_t (&x2)[VE / 2]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    if constexpr (BF16) {
+        x2[0] = pack_u32x2(v.x << 16, v.x & 0xFFFF0000u);
+        x2[1] = pack_u32x2(v.y << 16, v.y & 0xFFFF0000u);
+        x2[2] = pack_u32x2(v.z << 16, v.z & 0xFFFF0000u);
+        x2[3] = pack_u32x2(v.w << 16, v.w & 0xFFFF0000u);
+    } else {
+        x2[0] = pack_u32x2(v.x, v.y);
+        x2[1] = pack_u32x2(v.z, v.w);
+    }
+}
+
+struct Dmha2Smem {
+    uint32_t ring, q, a, pacc, pm, pl, u, w, misc, bars, total;
+};
+__host__ __device__ inline Dmha2Smem dmha2_smem(int D, int H, int dh, int S, int stages, uint32_t stage_bytes) {
+    Dmha2Smem s;
+    uint32_t o = 0;
+    s.ring = o; o += stages * stage_bytes;
+    s.q = o;    o += D * 4;
+    s.a = o;    o += dh * 4;
+    s.pacc = o; o += S * D * 4;
+    s.pm = o;   o += H * S * 4;
+    s.pl = o;   o += H * S * 4;
+    s.u = o;    o += H * 4;
+    s.w = o;    o += H * 4;
+    s.misc = o; o += 16;
+    o = (o + 7u) & ~7u;
+    s.bars = o; o += 2 * stages * 8;
+    s.total = o;
+    return s;
+}
+
+// The (utterance, frame range) segments a CTA owns.  split = 1: a contiguous range of the flattened stream;
+// split = 0: whole utterances, grid-strided.  Producer and consumers walk the same sequence.
+struct Dmha2Segments {
+    long long g0, g1;
+    int b, T, B, stride, split;
+    DASV_DEVICE Dmha2Segments(const DmhaFwdParams& p) {
+        T = p.T; B = p.B; split = p.split; stride = gridDim.x;
+        if (split) {
+            const long long total = static_cast<long long>(p.B) * p.T;
+            g0 = static_cast<long long>(blockIdx.x) * p.Q;
+            g1 = g0 + p.Q < total ? g0 + p.Q : total;
+            b = static_cast<int>(g0 / p.T);
+        } else {
+            g0 = 0; g1 = 0; b = blockIdx.x;
+        }
+    }
+    DASV_DEVICE bool valid() const { return split ? (static_cast<long long>(b) * T < g1) : (b < B); }
+    DASV_DEVICE int t_begin() const { return split ? static_cast<int>(max(g0 - static_cast<long long>(b) * T, 0LL)) : 0; }
+    DASV_DEVICE int t_end() const { return split ? static_cast<int>(min(g1 - static_cast<long long>(b) * T, static_cast<long long>(T))) : T; }
+    DASV_DEVICE void next() { b += split ? 1 : stride; }
+};
+
+template <bool BF16, int NV>
+constexpr int dmha_fwd2_min_ctas() { return (NV * (BF16 ? 8 : 4) <= 12) ? 3 : 2; }
+
+template <bool BF16, int G, int NV, int FB, bool RAGGED>
+__global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) dmha_fwd2_kernel(const DmhaFwdParams p) {
+    constexpr int VE = BF16 ? 8 : 4;
+    constexpr int VP = VE / 2;                                  // packed pairs per vector
+    constexpr uint32_t ES = BF16 ? 2u : 4u;
+    constexpr int RPW = 32 / G;                                 // (frame, head) rows per warp
+    constexpr int GPP = (G >= 8) ? 1 : 8 / G;                   // row groups per 8-lane LDS.128 phase
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int D = p.D, H = p.H, dh = p.dh, S = p.S, T = p.T;
+    const uint32_t frame_bytes = static_cast<uint32_t>(D) * ES;
+    const uint32_t stage_bytes = p.fps * frame_bytes;
+    const Dmha2Smem L = dmha2_smem(D, H, dh, S, p.stages, stage_bytes);
+    unsigned char* ring = smem + L.ring;
+    float* q_sm = reinterpret_cast<float*>(smem + L.q);         // [H][dh]  (query transposed)
+    float* a_sm = reinterpret_cast<float*>(smem + L.a);         // [dh]
+    float* pacc = reinterpret_cast<float*>(smem + L.pacc);      // [H*S][dh] partial weighted sums -> ctx
+    float* pm = reinterpret_cast<float*>(smem + L.pm);          // [H*S] reference max (log2 units)
+    float* pl = reinterpret_cast<float*>(smem + L.pl);          // [H*S] running sum
+    float* u_sm = reinterpret_cast<float*>(smem + L.u);         // [H] head scores
+    float* w_sm = reinterpret_cast<float*>(smem + L.w);         // [H] head weights
+    int* ticket_sm = reinterpret_cast<int*>(smem + L.misc);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
+    uint64_t* empty = full + p.stages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kDmhaConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kDmhaConsumerWarps) {
+        if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
+            int st = 0;
+            uint32_t ph = 0;
+            for (Dmha2Segments sg(p); sg.valid(); sg.next()) {
+                int Lb = p.lengths ? p.lengths[sg.b] : T;
+                Lb = max(0, min(Lb, T));
+                const int tb = sg.t_begin(), nfr = min(sg.t_end(), Lb) - tb;
+                const unsigned char* xb = p.x + (static_cast<size_t>(sg.b) * T + tb) * frame_bytes;
+                for (int f0 = 0; f0 < nfr; f0 += p.fps) {
+                    mbar_wait(&empty[st], ph ^ 1u);
+                    const uint32_t bytes = static_cast<uint32_t>(min(p.fps, nfr - f0)) * frame_bytes;
+                    mbar_arrive_expect_tx(&full[st], bytes);
+                    bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
+                    if (++st == p.stages) { st = 0; ph ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers (the producer is already streaming)
+    for (int i = tid; i < D; i += kDmhaConsumerThreads) {
+        const int h = i / dh, d = i - h * dh;
+        q_sm[i] = p.query[d * H + h];               // reference layout [dh, H] (poolings.py:90)
+    }
+    if (p.att != nullptr)
+        for (int i = tid; i < dh; i += kDmhaConsumerThreads) a_sm[i] = p.att[i];
+    named_bar_sync(1, kDmhaConsumerThreads);
+
+    const int grp = warp * RPW + lane / G, lig = lane % G;
+    const int head = grp % H, slot = grp / H;       // this group's head and frame slot (frames f = slot mod S)
+    const bool active = slot < S;
+    const int rot = (lane / G) % GPP;
+    uint32_t voff[NV];
+    bool vok[NV];
+    uint64_t q2[NV][VP];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const int idx = ((v + rot) % NV) * G + lig;             // 16-byte vector of the row held in slot v
+        vok[v] = active && idx * VE < dh;
+        voff[v] = static_cast<uint32_t>(head) * dh * ES + static_cast<uint32_t>(idx) * 16u;
+#pragma unroll
+        for (int e = 0; e < VP; ++e)
+            q2[v][e] = vok[v] ? pack_f32x2(q_sm[head * dh + idx * VE + 2 * e], q_sm[head * dh + idx * VE + 2 * e + 1])
+                              : pack_f32x2(0.f, 0.f);
+    }
+    const long long total = static_cast<long long>(p.B) * T;
+
+    int st = 0;
+    uint32_t ph = 0;
+    for (Dmha2Segments sg(p); sg.valid(); sg.next()) {
+        const int b = sg.b;
+        int Lb = p.lengths ? p.lengths[b] : T;
+        Lb = max(0, min(Lb, T));
+        const int tb = sg.t_begin(), nfr = min(sg.t_end(), Lb) - tb;
+
+        float m = -INFINITY, l = 0.f;
+        uint64_t acc2[NV][VP];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int e = 0; e < VP; ++e) acc2[v][e] = pack_f32x2(0.f, 0.f);
+
+        for (int f0 = 0; f0 < nfr; f0 += p.fps) {
+            mbar_wait(&full[st], ph);
+            const int nf = min(p.fps, nfr - f0);
+            const unsigned char* sbase = ring + st * stage_bytes;
+            // FB rows per trip: rows fb+slot and fb+S+slot are independent until the softmax update, which gives
+            // the LDS -> FMA -> shuffle -> exp2 chain a second row to overlap with.
+            for (int fb = 0; fb < nf; fb += FB * S) {            // warp-uniform trip count (fps is a multiple of S)
+                uint64_t xs[FB][NV][VP];
+                float sc[FB];
+                bool valid[FB];
+#pragma unroll
+                for (int r = 0; r < FB; ++r) {
+                    const int f = fb + r * S + slot;
+                    valid[r] = active && f < nf;
+                    const unsigned char* row = sbase + static_cast<uint32_t>(valid[r] ? f : 0) * frame_bytes;   // safe address when idle
+                    uint64_t s2a = pack_f32x2(0.f, 0.f), s2b = s2a;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        if (RAGGED && !vok[v]) {
+#pragma unroll
+                            for (int e = 0; e < VP; ++e) xs[r][v][e] = pack_f32x2(0.f, 0.f);
+                        } else {
+                            load_row_pairs<VE, BF16>(row + voff[v], xs[r][v]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < VP; e += 2) {
+                            s2a = fma_f32x2(xs[r][v][e], q2[v][e], s2a);
+                            s2b = fma_f32x2(xs[r][v][e + 1], q2[v][e + 1], s2b);
+                        }
+                    }
+                    float a0, a1, b0, b1;
+                    unpack_f32x2(s2a, a0, a1);
+                    unpack_f32x2(s2b, b0, b1);
+                    sc[r] = (a0 + a1) + (b0 + b1);
+                }
+#pragma unroll
+                for (int r = 0; r < FB; ++r) sc[r] = group_sum<G>(sc[r]);
+                float mx = -INFINITY;
+#pragma unroll
+                for (int r = 0; r < FB; ++r) {
+                    sc[r] = valid[r] ? sc[r] * p.scale_log2 : -INFINITY;     // log2-unit score of this (frame, head)
+                    mx = fmaxf(mx, sc[r]);
+                    if (p.align != nullptr && valid[r] && lig == 0)
+                        p.align[(static_cast<size_t>(b) * T + tb + f0 + fb + r * S + slot) * H + head] = sc[r];   // raw score, normalised at the end
+                }
+                if (mx > m + kDmhaLazy) {                        // lazy rescale; first frame: m = -inf -> corr = 0
+                    const float corr = fast_exp2(m - mx);
+                    const uint64_t corr2 = pack_f32x2(corr, corr);
+                    l *= corr;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+#pragma unroll
+                        for (int e = 0; e < VP; ++e) acc2[v][e] = mul_f32x2(acc2[v][e], corr2);
+                    m = mx;
+                }
+                const float mref = (m == -INFINITY) ? 0.f : m;  // idle group: exp2(-inf - 0) = 0
+#pragma unroll
+                for (int r = 0; r < FB; ++r) {
+                    const float pr = fast_exp2(sc[r] - mref);
+                    const uint64_t pr2 = pack_f32x2(pr, pr);
+                    l += pr;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+#pragma unroll
+                        for (int e = 0; e < VP; ++e) acc2[v][e] = fma_f32x2(pr2, xs[r][v][e], acc2[v][e]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+            if (++st == p.stages) { st = 0; ph ^= 1u; }
+        }
+
+        // ------------------------------------------------------------ step 1: merge this CTA's S frame slots per head
+        if (active) {
+            const int sl = head * S + slot;
+            if (lig == 0) { pm[sl] = m; pl[sl] = l; }
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (vok[v]) {
+                    const int idx = ((v + rot) % NV) * G + lig;
+#pragma unroll
+                    for (int e = 0; e < VP; ++e) {
+                        float lo, hi;
+                        unpack_f32x2(acc2[v][e], lo, hi);
+                        pacc[sl * dh + idx * VE + 2 * e] = lo;
+                        pacc[sl * dh + idx * VE + 2 * e + 1] = hi;
+                    }
+                }
+        }
+        named_bar_sync(1, kDmhaConsumerThreads);
+        for (int h = warp; h < H; h += kDmhaConsumerWarps) {    // -> slot 0: (M, sum, weighted sum), not yet normalised
+            float M = -INFINITY;
+            for (int s = 0; s < S; ++s) M = fmaxf(M, pm[h * S + s]);
+            const float Mref = (M == -INFINITY) ? 0.f : M;
+            float Lsum = 0.f;
+            for (int s = 0; s < S; ++s) Lsum += pl[h * S + s] * fast_exp2(pm[h * S + s] - Mref);
+            for (int d = lane; d < dh; d += 32) {
+                float c = 0.f;
+                for (int s = 0; s < S; ++s) c = fmaf(pacc[(h * S + s) * dh + d], fast_exp2(pm[h * S + s] - Mref), c);
+                pacc[(h * S) * dh + d] = c;
+            }
+            __syncwarp();
+            if (lane == 0) { pm[h * S] = M; pl[h * S] = Lsum; }
+        }
+        named_bar_sync(1, kDmhaConsumerThreads);
+
+        // ------------------------------------------------------------ utterance split over several CTAs: exchange partials
+        if (p.split) {
+            const long long ub = static_cast<long long>(b) * T;
+            const long long ue = (ub + T < total ? ub + T : total) - 1;
+            const int first_cta = static_cast<int>(ub / p.Q);
+            const int n_parts = static_cast<int>(ue / p.Q) - first_cta + 1;
+            if (n_parts > 1) {
+                const size_t rec_floats = static_cast<size_t>(D) + 2 * H;
+                float* rec = p.ws_part + (static_cast<size_t>(blockIdx.x) + b) * rec_floats;   // (CTA, utterance) pairs have unique c + b
+                for (int i = tid; i < D; i += kDmhaConsumerThreads) {
+                    const int h = i / dh, d = i - h * dh;
+                    rec[i] = pacc[(h * S) * dh + d];
+                }
+                for (int h = tid; h < H; h += kDmhaConsumerThreads) { rec[D + h] = pm[h * S]; rec[D + H + h] = pl[h * S]; }
+                __threadfence();
+                named_bar_sync(1, kDmhaConsumerThreads);
+                if (tid == 0) *ticket_sm = atomicAdd(&p.ws_cnt[b], 1);
+                named_bar_sync(1, kDmhaConsumerThreads);
+                const bool last = (*ticket_sm == n_parts - 1);
+                named_bar_sync(1, kDmhaConsumerThreads);        // ticket_sm may be rewritten by the next segment
+                if (!last) continue;                             // another CTA finishes this utterance
+                __threadfence();
+                if (tid == 0) p.ws_cnt[b] = 0;                   // self-cleaning for the next launch
+                for (int h = warp; h < H; h += kDmhaConsumerWarps) {
+                    float M = -INFINITY;
+                    for (int k = 0; k < n_parts; ++k)
+                        M = fmaxf(M, __ldcg(p.ws_part + (static_cast<size_t>(first_cta + k) + b) * rec_floats + D + h));
+                    const float Mref = (M == -INFINITY) ? 0.f : M;
+                    float Lsum = 0.f;
+                    for (int k = 0; k < n_parts; ++k) {
+                        const float* rk = p.ws_part + (static_cast<size_t>(first_cta + k) + b) * rec_floats;
+                        Lsum += __ldcg(rk + D + H + h) * fast_exp2(__ldcg(rk + D + h) - Mref);
+                    }
+                    for (int d = lane; d < dh; d += 32) {
+                        float c = 0.f;
+                        for (int k = 0; k < n_parts; ++k) {
+                            const float* rk = p.ws_part + (static_cast<size_t>(first_cta + k) + b) * rec_floats;
+                            c = fmaf(__ldcg(rk + h * dh + d), fast_exp2(__ldcg(rk + D + h) - Mref), c);
+                        }
+                        pacc[(h * S) * dh + d] = c;
+                    }
+                    __syncwarp();
+                    if (lane == 0) { pm[h * S] = M; pl[h * S] = Lsum; }
+                }
+                named_bar_sync(1, kDmhaConsumerThreads);
+            }
+        }
+
+        // ------------------------------------------------------------ step 2: normalise, attention over heads, outputs
+        for (int h = warp; h < H; h += kDmhaConsumerWarps) {
+            const float M = pm[h * S], Lsum = pl[h * S];
+            const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;
+            float dot = 0.f;
+            for (int d = lane; d < dh; d += 32) {
+                const float c = pacc[(h * S) * dh + d] * inv;
+                pacc[(h * S) * dh + d] = c;                    // ctx[b,h,d], kept in smem for the head stage
+                if (p.ctx != nullptr) p.ctx[(static_cast<size_t>(b) * H + h) * dh + d] = c;
+                if (p.att != nullptr) dot = fmaf(c, a_sm[d], dot);
+            }
+            dot = warp_sum(dot);
+            __syncwarp();
+            if (lane == 0) {
+                u_sm[h] = dot;                                  // poolings.py:47 (no scale)
+                const float lse2 = M + log2f(Lsum);             // log2 units; -inf for an empty utterance
+                pm[h * S] = lse2;
+                if (p.lse != nullptr) p.lse[static_cast<size_t>(b) * H + h] = lse2 * kLn2;
+            }
+        }
+        named_bar_sync(1, kDmhaConsumerThreads);
+        if (p.att != nullptr) {
+            if (warp == 0) {
+                // softmax over heads (poolings.py:50), with the training-mode keep mask (poolings.py:42)
+                float mx = -INFINITY;
+                for (int h = lane; h < H; h += 32) {
+                    const bool kept = p.keep == nullptr || p.keep[static_cast<size_t>(b) * H + h] != 0;
+                    const float u = kept ? u_sm[h] : -INFINITY;
+                    u_sm[h] = u;
+                    mx = fmaxf(mx, u);
+                }
+                mx = warp_max(mx);
+                float sum = 0.f;
+                for (int h = lane; h < H; h += 32) {
+                    const float e = expf(u_sm[h] - mx);        // all heads dropped -> NaN, as in the reference
+                    w_sm[h] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                for (int h = lane; h < H; h += 32) {
+                    const float w = w_sm[h] / sum;
+                    w_sm[h] = w;
+                    if (p.headw != nullptr) p.headw[static_cast<size_t>(b) * H + h] = w;
+                }
+            }
+            named_bar_sync(1, kDmhaConsumerThreads);
+            if (p.out != nullptr) {
+                for (int d = tid; d < dh; d += kDmhaConsumerThreads) {
+                    float o = 0.f;
+                    for (int h = 0; h < H; ++h) o = fmaf(w_sm[h], pacc[(h * S) * dh + d], o);   // poolings.py:68-69
+                    p.out[static_cast<size_t>(b) * dh + d] = o;
+                }
+            }
+        }
+        if (p.align != nullptr) {
+            // alignment = softmax over time (poolings.py:77): exp2(raw - lse); frames >= L are 0.  Raw scores of
+            // other CTAs' parts were published before their ticket (threadfence), read them past L1.
+            float* ab = p.align + static_cast<size_t>(b) * T * H;
+            for (int i = tid; i < T * H; i += kDmhaConsumerThreads) {
+                const int t = i / H, h = i - t * H;
+                ab[i] = (t < Lb) ? fast_exp2(__ldcg(ab + i) - pm[h * S]) : 0.f;
+            }
+        }
+        named_bar_sync(1, kDmhaConsumerThreads);   // pacc/pm/u/w are reused by the next segment
+    }
+}
+
+// ---------------------------------------------------------------------------------- host side
+struct DmhaPlan2 { int ok, G, NV, S, fps, stages, FB, ragged; };
+
+static DmhaPlan2 dmha_make_plan2(int x_dtype, int T, int D, int H) {
+    DmhaPlan2 pl{};
+    const bool bf16 = x_dtype == 1;
+    const int VE = bf16 ? 8 : 4, nvmax = bf16 ? 3 : 5;        // <= 20-24 elements of a row per lane (96 registers, 2 CTAs/SM)
+    if (H <= 0 || D <= 0 || D % H != 0) return pl;
+    const int dh = D / H;
+    if (dh % VE != 0) return pl;
+    const int nvec = dh / VE;
+    int G = 2;
+    while (G <= 32 && (nvec + G - 1) / G > nvmax) G <<= 1;
+    if (G > 32) return pl;
+    const int ngrp = kDmhaConsumerThreads / G;
+    if (H > ngrp) return pl;
+    int S = ngrp / H;
+    if (S > 8) S = 8;
+    const size_t frame_bytes = static_cast<size_t>(D) * (bf16 ? 2 : 4);
+    int fps = static_cast<int>((16 * 1024) / frame_bytes) / S * S;
+    if (fps < S) fps = S;
+    const int tcap = (T + S - 1) / S * S;
+    if (fps > tcap) fps = tcap > 0 ? tcap : S;
+    pl.ok = 1; pl.G = G; pl.NV = (nvec + G - 1) / G; pl.S = S; pl.fps = fps; pl.stages = 4;
+    // tuning overrides for sweeps (scripts/sweep_dmha.py); unset in production
+    if (const char* e = getenv("DASV_DMHA_FPS")) { const int v = atoi(e); if (v > 0) pl.fps = (v + S - 1) / S * S; }
+    if (const char* e = getenv("DASV_DMHA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 16) pl.stages = v; }
+    pl.ragged = (pl.G * pl.NV != nvec);                  // some lanes' vector slots fall outside the row
+    pl.FB = (!pl.ragged && pl.fps % (2 * S) == 0) ? 2 : 1;
+    return pl;
+}
+
+template <typename Kern>
+static int launch_fwd2_kernel(Kern kern, DmhaFwdParams& p, size_t smem, void* workspace, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) { set_error("dmha_fwd: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDmhaThreads, smem);
+    if (occ < 1) { set_error("dmha_fwd: kernel does not fit on an SM (smem %zu B)", smem); return 1; }
+    int grid = sms * occ;
+    if (grid > kDmha2MaxGrid) grid = kDmha2MaxGrid;
+    const long long total = static_cast<long long>(p.B) * p.T;
+    // Stream-split scheduling is implemented and parity-tested but OFF by default: on B200 the extra per-segment
+    // finish (partial write, fence, ticket, merge: ~3-4 us) costs more than the 13 % of tail it removes
+    // (B=512,T=200,D=1024: fp32 83.8 us split vs 76.1 us whole-utterance; bf16 62.2 vs 51.1).  DASV_DMHA_SPLIT=1 enables it.
+    const char* split_env = getenv("DASV_DMHA_SPLIT");
+    const bool want_split = workspace != nullptr && split_env != nullptr && atoi(split_env) != 0;
+    if (want_split && total > 0) {
+        // equal ranges of the flattened (utterance, frame) stream, at least 4 trips of work per CTA
+        long long q = (total + grid - 1) / grid;
+        const long long qmin = 8LL * p.S;
+        if (q < qmin) q = qmin;
+        q = (q + p.S - 1) / p.S * p.S;
+        grid = static_cast<int>((total + q - 1) / q);
+        p.split = 1; p.Q = q;
+        p.ws_cnt = static_cast<int*>(workspace);
+        const size_t cnt_bytes = (static_cast<size_t>(p.B) * sizeof(int) + 255) & ~static_cast<size_t>(255);
+        p.ws_part = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + cnt_bytes);
+        e = cudaMemsetAsync(p.ws_cnt, 0, cnt_bytes, stream);
+        if (e != cudaSuccess) { set_error("dmha_fwd: workspace memset: %s", cudaGetErrorString(e)); return 1; }
+    } else {
+        p.split = 0; p.Q = 0;
+        if (grid > p.B) grid = p.B;
+    }
+    kern<<<grid, kDmhaThreads, smem, stream>>>(p);
+    return check_launch("dmha_fwd");
+}
+
+template <bool BF16>
+static int dispatch_fwd2(const DmhaPlan2& pl, DmhaFwdParams& p, size_t smem, void* ws, cudaStream_t s) {
+#define DASV_CASE2(g, nv) \
+    if (pl.G == g && pl.NV == nv) { \
+        if (pl.ragged) return launch_fwd2_kernel(dmha_fwd2_kernel<BF16, g, nv, 1, true>, p, smem, ws, s); \
+        if (pl.FB == 2) return launch_fwd2_kernel(dmha_fwd2_kernel<BF16, g, nv, 2, false>, p, smem, ws, s); \
+        return launch_fwd2_kernel(dmha_fwd2_kernel<BF16, g, nv, 1, false>, p, smem, ws, s); \
+    }
+#define DASV_ROW2(g) DASV_CASE2(g, 1) DASV_CASE2(g, 2) DASV_CASE2(g, 3) \
+    if constexpr (!BF16) { DASV_CASE2(g, 4) DASV_CASE2(g, 5) }
+    DASV_ROW2(2) DASV_ROW2(4) DASV_ROW2(8) DASV_ROW2(16) DASV_ROW2(32)
+#undef DASV_ROW2
+#undef DASV_CASE2
+    set_error("dmha_fwd: no v2 kernel for G=%d NV=%d", pl.G, pl.NV);
+    return 1;
+}
+
+size_t dmha_fwd2_workspace_bytes(int B, int D, int H) {
+    if (B <= 0 || D <= 0 || H <= 0) return 0;
+    const size_t cnt_bytes = (static_cast<size_t>(B) * sizeof(int) + 255) & ~static_cast<size_t>(255);
+    return cnt_bytes + (static_cast<size_t>(kDmha2MaxGrid) + B) * (static_cast<size_t>(D) + 2 * H) * sizeof(float);
+}
+
+int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream) {
+    DmhaPlan2 p2 = dmha_make_plan2(x_dtype, p.T, p.D, p.H);
+    if (!p2.ok) return -1;
+    const bool bf16 = x_dtype == 1;
+    const uint32_t stage_bytes = static_cast<uint32_t>(p2.fps) * p.D * (bf16 ? 2 : 4);
+    size_t smem = dmha2_smem(p.D, p.H, p.dh, p2.S, p2.stages, stage_bytes).total;
+    // keep two CTAs per SM when a shallower ring allows it
+    if (!getenv("DASV_DMHA_STAGES"))
+        while (smem > 113 * 1024 && p2.stages > 3) smem = dmha2_smem(p.D, p.H, p.dh, p2.S, --p2.stages, stage_bytes).total;
+    while (smem > 227 * 1024 && p2.stages > 2) smem = dmha2_smem(p.D, p.H, p.dh, p2.S, --p2.stages, stage_bytes).total;
+    if (smem > 227 * 1024) return -1;
+    p.fps = p2.fps; p.stages = p2.stages; p.S = p2.S;
+    return bf16 ? dispatch_fwd2<true>(p2, p, smem, workspace, stream) : dispatch_fwd2<false>(p2, p, smem, workspace, stream);
+}
+
+}  // namespace dasv
+
+extern "C" size_t dasv_dmha_fwd_workspace_bytes(int B, int T, int D, int H) {
+    (void)T;
+    return dasv::dmha_fwd2_workspace_bytes(B, D, H);
+}

@@ -71,8 +71,10 @@ def dmha_fwd(x, query, att=None, lengths=None, keep=None, need_align=True, need_
         lse = torch.empty((B, H), **f)
         headw = torch.empty((B, H), **f) if att is not None else None
         align = torch.empty((B, T, H), **f) if need_align else None
-        rc = _lib.lib().dasv_dmha_fwd(_p(x), _dtype_code(x, 'x'), _p(lengths), _p(query), _p(att_c), _p(keep_c),
-                                      _p(out), _p(ctx), _p(lse), _p(headw), _p(align), B, T, D, H, _stream())
+        L = _lib.lib()
+        ws = torch.empty((max(int(L.dasv_dmha_fwd_workspace_bytes(B, T, D, H)), 4),), device=dev, dtype=torch.uint8)
+        rc = L.dasv_dmha_fwd(_p(x), _dtype_code(x, 'x'), _p(lengths), _p(query), _p(att_c), _p(keep_c),
+                             _p(out), _p(ctx), _p(lse), _p(headw), _p(align), _p(ws), B, T, D, H, _stream())
         _lib.check(rc, 'dasv_dmha_fwd')
     return dict(out=out, ctx=ctx, lse=lse, headw=headw, align=align)
 

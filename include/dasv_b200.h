@@ -48,10 +48,14 @@ const char* dasv_last_error(void);
  * no head stage, `out`/`headw` must then be NULL);  keep [B,H] uint8 nullable (training-mode
  * head drop-out mask, poolings.py:39-43, drawn by the caller);
  * out [B,dh], ctx [B,H,dh], lse [B,H], headw [B,H], align [B,T,H] : f32, each nullable.
+ * workspace (nullable, dasv_dmha_fwd_workspace_bytes): lets the kernel cut the flattened (utterance, frame)
+ * stream into equal per-CTA ranges (partial states + tickets live there); without it whole utterances are
+ * dealt to CTAs, which quantises badly when B is a small multiple of the SM count.  No initialisation needed.
  */
+size_t dasv_dmha_fwd_workspace_bytes(int B, int T, int D, int H);
 int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
                   const float* query, const float* att, const uint8_t* keep,
-                  float* out, float* ctx, float* lse, float* headw, float* align,
+                  float* out, float* ctx, float* lse, float* headw, float* align, void* workspace,
                   int B, int T, int D, int H, void* stream);
 
 /* Backward of the above w.r.t. x, query, att (closed form): one pass that reads

@@ -48,9 +48,9 @@ def test_library_is_sm100a_native():
 
 def test_error_reporting_without_gpu(library):
     # argument validation happens before any CUDA call, so it is testable on the CPU box
-    rc = library.dasv_dmha_fwd(None, 0, None, None, None, None, None, None, None, None, None, 1, 1, 64, 8, None)
+    rc = library.dasv_dmha_fwd(None, 0, None, None, None, None, None, None, None, None, None, None, 1, 1, 64, 8, None)
     assert rc != 0 and b'null' in library.dasv_last_error()
-    assert library.dasv_dmha_fwd(None, 0, None, None, None, None, None, None, None, None, None, 0, 1, 64, 8, None) == 0   # empty batch
+    assert library.dasv_dmha_fwd(None, 0, None, None, None, None, None, None, None, None, None, None, 0, 1, 64, 8, None) == 0   # empty batch
     rc = library.dasv_conv3x3_igemm_bf16(1, 1, 1, None, 1, 1, 1, 1, 8, 80, 60, 64, None)
     assert rc != 0 and b'multiple of 64' in library.dasv_last_error()
     assert library.dasv_dmha_bwd_workspace_bytes(4, 10, 256, 8) == 4 * (256 + 32) * 4

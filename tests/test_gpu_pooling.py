@@ -181,3 +181,14 @@ def test_edge_cases():
         ops.dmha_fwd(torch.randn(2, 4, 256), q.cpu(), a.cpu())            # CPU tensors are an error, not a fallback
     with pytest.raises(Exception):
         ops.dmha_fwd(torch.randn(2, 4, 250, device='cuda'), q, a)         # D != dh*H
+
+
+def test_stream_split_schedule_matches_whole_utterance_schedule(monkeypatch):
+    """The optional stream-split schedule (partials + tickets across CTAs) gives the same results."""
+    c = synth.make_pooling_case(37, 90, 1024, 16, seed=8, with_lengths=True)
+    args = (dev(c['x']), dev(c['query']), dev(c['att']))
+    base = ops.dmha_fwd(*args, lengths=dev(c['lengths']))
+    monkeypatch.setenv('DASV_DMHA_SPLIT', '1')
+    split = ops.dmha_fwd(*args, lengths=dev(c['lengths']))
+    for k in ('out', 'ctx', 'lse', 'headw', 'align'):
+        assert max_rel(split[k].cpu().numpy(), base[k].cpu().numpy()) < 1e-5, k
