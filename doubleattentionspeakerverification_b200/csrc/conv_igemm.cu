@@ -442,7 +442,7 @@ struct ConvPlan {
 
 // Pick the patch shape that minimises the modelled time of the whole layer.  Per 16-deep K step a 128 x Npad
 // MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
-// ~15 TB/s chip-wide), so a step also costs its operand bytes / 64.  `halo` = 2 in tap-row reuse mode (patches carry
+// ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
 static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo) {
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
@@ -453,14 +453,14 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo) {
         for (int BT = pool ? 2 : 1; BT <= bt_max; BT += pool ? 2 : 1) {
             if (BT > T + 1 && BT > 2) break;
             const int n_tt = (T + BT - 1) / BT;
-            const int bb_max = (n_tt == 1) ? 256 / (BF * BT) : 1;
+            const int bb_max = 256 / (BF * BT);          // several utterances per patch when one utterance's rows leave room
             for (int BB = 1; BB <= bb_max && BB <= B; ++BB) {
                 const int N = (BB - 1) * (BT + halo) * BF + BT * BF;      // accumulator columns incl. halo gaps
                 const int Npad = (N + 15) / 16 * 16;
                 if (Npad > 256) continue;
                 const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB);
                 const double b_rows = halo ? BB * (BT + 2.0) * BF / 3.0 : BB * BT * BF;   // activation rows fetched per tap
-                const double ingest = (128.0 + b_rows) * 32.0 / 64.0;                   // bytes per 16-deep step / 64 B/clk
+                const double ingest = (128.0 + b_rows) * 32.0 / 52.0;                   // bytes per 16-deep step / ~52 B/clk effective
                 const double step = Npad / 2.0 > ingest ? Npad / 2.0 : ingest;
                 const double cost = tiles * (step * ksteps + 700.0);
                 if (cost < best.cost) best = ConvPlan{BF, BT, BB, N, Npad, cost};
@@ -496,7 +496,14 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     // tap-row reuse is the default; DASV_CONV_REUSE=0 selects one TMA box per tap (A/B comparisons, debugging)
     int reuse = 1;
     if (const char* e = getenv("DASV_CONV_REUSE")) reuse = atoi(e) != 0;
-    const ConvPlan pl = conv_plan(B, T, F, Cin, pool, reuse ? 2 : 0);
+    ConvPlan pl = conv_plan(B, T, F, Cin, pool, reuse ? 2 : 0);
+    if (const char* e = getenv("DASV_CONV_PLAN")) {             // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
+        int bf = 0, bt = 0, bb = 0;
+        if (sscanf(e, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
+            const int n = (bb - 1) * (bt + (reuse ? 2 : 0)) * bf + bt * bf;
+            if ((n + 15) / 16 * 16 <= 256) pl = ConvPlan{bf, bt, bb, n, (n + 15) / 16 * 16, 0.0};
+        }
+    }
     if (pl.N == 0) { set_error("conv3x3_igemm_bf16: no patch shape for T=%d F=%d", T, F); return 1; }
     const int cout_pad = (Cout + kConvTileM - 1) / kConvTileM * kConvTileM;
     const int box_t = pl.BT + (reuse ? 2 : 0);
