@@ -170,7 +170,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py --impl b200 needs a CUDA device (there is no CPU fallback)')
-    from doubleattentionspeakerverification_b200 import _lib, model, ops, synth
+    from doubleattentionspeakerverification_b200 import _lib, extract, model, ops, synth
     _lib.lib()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -185,7 +185,6 @@ def main():
     Bn = args.batch
     xs = [torch.from_numpy(synth.make_logmel(Bn, FRAMES, seed=100 + rank * 7 + i)).to(dev) for i in range(2)]
     x_host = torch.from_numpy(synth.make_logmel(Bn, FRAMES, seed=300 + rank)).pin_memory()
-    x_stage = torch.empty_like(xs[0])
     emb_host = torch.empty((Bn, cfg.embedding_size), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world * Bn, cfg.embedding_size), device=dev) if world > 1 else None
 
@@ -205,13 +204,20 @@ def main():
         with torch.no_grad():
             return net.getEmbedding(xs[i & 1])
 
-    def step_e2e(i):
+    def post(emb):
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, emb)           # the path's only collective (cosine scoring needs all embeddings)
+        return emb
+
+    def embed(xd):
         with torch.no_grad():
-            x_stage.copy_(x_host, non_blocking=True)
-            emb = net.getEmbedding(x_stage)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, emb)
-            emb_host.copy_(emb, non_blocking=True)
+            return net.getEmbedding(xd)
+
+    pipe = extract.HostPipeline(embed, (Bn, FRAMES, BINS), cfg.embedding_size, dev, post=post)
+
+    def step_e2e(i):
+        # public API: pinned host batch in, pinned host embeddings out; the H2D of step i+1 overlaps step i's kernels
+        pipe.submit(x_host, emb_host)
 
     def timed(fn, steps):
         barrier()
@@ -227,13 +233,13 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
-    _lib.LAUNCHES.clear()
-    with ClockSampler(local) as clk:
-        ms = timed(step_resident, args.steps)
-    launches = sum(_lib.LAUNCHES.values())
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    with ClockSampler(local) as clk:                 # clocks / throttle reasons over both timed regions
+        _lib.LAUNCHES.clear()
+        ms = timed(step_resident, args.steps)
+        launches = sum(_lib.LAUNCHES.values())
+        ms_e2e = timed(step_e2e, args.steps)
     value = world * Bn * args.steps / (ms * 1e-3)
     e2e_value = world * Bn * args.steps / (ms_e2e * 1e-3)
 

@@ -102,6 +102,8 @@ class _VGG(nn.Module):
         c11 = getattr(self, self._names[0])
         nblocks = len(self._names) // 2
         if prec == 'bf16':
+            # conv11 is bound by its NHWC bf16 write (2.1 GB per 256 x 4 s batch at the 3.95 TB/s pure-write bandwidth):
+            # the CUDA-core kernel reaches 79 % of that; the tensor-core variant (ops.conv11_tc) measured slower.
             h = ops.conv11_direct(x, c11.weight, c11.bias, L, out_dtype=torch.bfloat16)
             for blk in range(nblocks):
                 if blk > 0:

@@ -446,6 +446,7 @@ static DmhaPlan2 dmha_make_plan2(int x_dtype, int T, int D, int H) {
     if (const char* e = getenv("DASV_DMHA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 16) pl.stages = v; }
     pl.ragged = (pl.G * pl.NV != nvec);                  // some lanes' vector slots fall outside the row
     pl.FB = (!pl.ragged && pl.fps % (2 * S) == 0) ? 2 : 1;
+    if (const char* e = getenv("DASV_DMHA_FB")) { if (atoi(e) == 1) pl.FB = 1; }
     return pl;
 }
 

@@ -106,6 +106,42 @@ def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, m
     return out
 
 
+class HostPipeline:
+    """Double-buffered host -> device -> host streaming of fixed-shape batches: the H2D copy of batch i+1 runs on a
+    copy stream while batch i is being embedded on the compute stream, and the embeddings return to pinned host
+    memory asynchronously.  Usage:  pipe = HostPipeline(embed_fn, (B, T, F), E, device);  pipe.submit(x_pinned, out_pinned)
+    per batch, then pipe.finish().  ``embed_fn(x_dev) -> [B, E]``; an optional ``post(emb)`` hook runs on the compute
+    stream between the extraction and the D2H copy (e.g. the NCCL all-gather)."""
+
+    def __init__(self, embed_fn, shape, embedding_size, device, post=None):
+        self.embed_fn, self.post, self.device = embed_fn, post, torch.device(device)
+        self.stage = [torch.empty(shape, device=self.device, dtype=torch.float32) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+
+    def submit(self, x_host, out_host):
+        k = self.i & 1
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.i >= 2:
+                self.copy_stream.wait_event(self.consumed[k])      # the staging buffer's previous batch has been read
+            self.stage[k].copy_(x_host, non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+        compute.wait_event(self.copied[k])
+        emb = self.embed_fn(self.stage[k])
+        self.consumed[k].record(compute)
+        if self.post is not None:
+            emb = self.post(emb)
+        out_host.copy_(emb, non_blocking=True)
+        self.i += 1
+        return emb
+
+    def finish(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+
 def score_trial_list(emb, trials, device=None):
     """``trials``: ``[M,2]`` integer array of (utterance A, utterance B) indices -> ``[M]`` cosine scores."""
     t = torch.as_tensor(np.asarray(trials), device=emb.device if device is None else device)
