@@ -304,6 +304,22 @@ def main():
                 us = e0.elapsed_time(e1) * 1e3 / reps
                 gbs = nbytes / (us * 1e-6) / 1e9
                 dmha['%s_%s' % (dt_name, case)] = {'us': us, 'gbs': gbs, 'frac': gbs / pk['hbm_gbs'], 'bytes': nbytes}
+            # backward (read x, write dx): 2x the forward's bytes
+            r = ops.dmha_fwd(bufs[0], q, a, need_align=False)
+            gout = torch.randn(Bp, Dp // Hp, device=dev, generator=gen)
+            for i in range(3):
+                ops.dmha_bwd(bufs[0], q, a, gout, None, r['ctx'], r['lse'], r['headw'])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(10):
+                ops.dmha_bwd(bufs[0], q, a, gout, None, r['ctx'], r['lse'], r['headw'])
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / 10
+            nbytes = 2 * Bp * Tp * Dp * es
+            dmha['%s_bwd' % dt_name] = {'us': us, 'gbs': nbytes / (us * 1e-6) / 1e9, 'frac': nbytes / (us * 1e-6) / 1e9 / pk['hbm_gbs'],
+                                        'bytes': nbytes, 'note': 'includes the dquery/datt reduce kernel'}
             del bufs
         dmha['peak_gbs'] = pk['hbm_gbs']
         dmha['shape'] = 'B=512 T=200 D=1024 H=16; 2 rotating inputs (each > L2); no alignment output'

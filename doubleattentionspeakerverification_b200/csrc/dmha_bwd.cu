@@ -11,24 +11,6 @@ namespace dasv {
 
 constexpr int kDmhaBwdMaxGrid = 1184;   // 148 SMs x 8: bounds the per-CTA partial workspace
 
-struct DmhaBwdParams {
-    const unsigned char* x;
-    const int32_t* lengths;
-    const float* query;
-    const float* att;
-    const float* g_out;
-    const float* g_ctx;
-    const float* ctx;
-    const float* lse;
-    const float* headw;
-    unsigned char* dx;
-    float* ws_dq;      // [grid][D]
-    float* ws_da;      // [grid][dh]
-    int B, T, D, H, dh;
-    int fps, stages, S;
-    float scale_log2, inv_sqrt_h;
-};
-
 struct DmhaBwdSmem {
     uint32_t ring, q, a, dc, dq, da, dw, du, dcc, lse2, bars, total;
 };
@@ -307,19 +289,32 @@ __global__ void __launch_bounds__(kDmhaThreads) dmha_bwd_kernel(const DmhaBwdPar
 }
 
 // Fixed-order reduction of the per-CTA partials: dquery[d,h] (reference layout [dh,H]) and datt[d].
-__global__ void dmha_bwd_reduce_kernel(const float* ws_dq, const float* ws_da, int nparts,
-                                       float* dquery, float* datt, int D, int H, int dh) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Block = 32 outputs x 8 slices of the partial list: coalesced column sums, then the 8 slice sums are added in a
+// fixed order, so the result is deterministic (and the kernel takes a few microseconds instead of tens).
+constexpr int kBwdRedSlices = 8;
+__global__ void __launch_bounds__(32 * kBwdRedSlices) dmha_bwd_reduce_kernel(const float* ws_dq, const float* ws_da, int nparts,
+                                                                            float* dquery, float* datt, int D, int H, int dh) {
+    __shared__ float red[kBwdRedSlices][33];
+    const int tx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx;
+    float s = 0.f;
     if (i < D) {
-        float s = 0.f;
-        for (int c = 0; c < nparts; ++c) s += ws_dq[static_cast<size_t>(c) * D + i];
-        const int h = i / dh, d = i - h * dh;
-        dquery[d * H + h] = s;
-    } else if (i < D + dh && datt != nullptr) {
-        const int d = i - D;
-        float s = 0.f;
-        for (int c = 0; c < nparts; ++c) s += ws_da[static_cast<size_t>(c) * dh + d];
-        datt[d] = s;
+        for (int c = sl; c < nparts; c += kBwdRedSlices) s += ws_dq[static_cast<size_t>(c) * D + i];
+    } else if (i < D + dh) {
+        for (int c = sl; c < nparts; c += kBwdRedSlices) s += ws_da[static_cast<size_t>(c) * dh + (i - D)];
+    }
+    red[sl][tx] = s;
+    __syncthreads();
+    if (sl == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < kBwdRedSlices; ++k) tot += red[k][tx];
+        if (i < D) {
+            const int h = i / dh, d = i - h * dh;
+            dquery[d * H + h] = tot;
+        } else if (i < D + dh && datt != nullptr) {
+            datt[i - D] = tot;
+        }
     }
 }
 
@@ -339,7 +334,7 @@ static int launch_bwd(DmhaBwdParams& p, size_t smem, float* dquery, float* datt,
     kern<<<grid, kDmhaThreads, smem, stream>>>(p);
     if (check_launch("dmha_bwd")) return 1;
     const int n = p.D + p.dh;
-    dmha_bwd_reduce_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p.ws_dq, p.ws_da, grid, dquery, datt, p.D, p.H, p.dh);
+    dmha_bwd_reduce_kernel<<<(n + 31) / 32, 32 * kBwdRedSlices, 0, stream>>>(p.ws_dq, p.ws_da, grid, dquery, datt, p.D, p.H, p.dh);
     return check_launch("dmha_bwd_reduce");
 }
 
@@ -379,23 +374,34 @@ extern "C" int dasv_dmha_bwd(const void* x, int x_dtype, const int32_t* lengths,
     if (x_dtype != 0 && x_dtype != 1) { set_error("dmha_bwd: bad dtype %d", x_dtype); return 1; }
     if (att != nullptr && (!g_out || !headw || !datt)) { set_error("dmha_bwd: att given but g_out/headw/datt missing"); return 1; }
     if (att == nullptr && !g_ctx) { set_error("dmha_bwd: MultiHeadAttention-only mode needs g_ctx"); return 1; }
-    DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, true);
-    if (pl.err) { set_error("dmha_bwd: unsupported shape D=%d H=%d dtype=%d (plan error %d)", D, H, x_dtype, pl.err); return 1; }
     DmhaBwdParams p{};
     p.x = static_cast<const unsigned char*>(x);
     p.lengths = lengths; p.query = query; p.att = att; p.g_out = g_out; p.g_ctx = g_ctx;
     p.ctx = ctx; p.lse = lse; p.headw = headw; p.dx = static_cast<unsigned char*>(dx);
+    if (H <= 0 || D <= 0 || D % H != 0) { set_error("dmha_bwd: D=%d must be a positive multiple of H=%d", D, H); return 1; }
     p.B = B; p.T = T; p.D = D; p.H = H; p.dh = D / H;
     p.inv_sqrt_h = 1.0f / sqrtf(static_cast<float>(H));
     p.scale_log2 = kLog2e * p.inv_sqrt_h;
     const size_t parts = static_cast<size_t>(B < kDmhaBwdMaxGrid ? B : kDmhaBwdMaxGrid);
     p.ws_dq = static_cast<float*>(workspace);
     p.ws_da = p.ws_dq + parts * D;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {   // v2 mapping (dmha_bwd2.cu): 0 = launched, 1 = error, -1 = shape outside the mapping
+        int grid = 0;
+        const int r = dmha_bwd2_launch(p, x_dtype, kDmhaBwdMaxGrid, &grid, s);
+        if (r == 0) {
+            const int n = D + p.dh;
+            dmha_bwd_reduce_kernel<<<(n + 31) / 32, 32 * kBwdRedSlices, 0, s>>>(p.ws_dq, p.ws_da, grid, dquery, datt, D, H, p.dh);
+            return check_launch("dmha_bwd_reduce");
+        }
+        if (r > 0) return r;
+    }
+    DmhaPlan pl = dmha_make_plan(x_dtype, T, D, H, true);
+    if (pl.err) { set_error("dmha_bwd: unsupported shape D=%d H=%d dtype=%d (plan error %d)", D, H, x_dtype, pl.err); return 1; }
     const uint32_t stage_bytes = static_cast<uint32_t>(pl.fps) * D * (pl.bf16 ? 2 : 4);
     size_t smem = dmha_bwd_smem(D, H, p.dh, pl.stages, stage_bytes).total;
     while (smem > 227 * 1024 && pl.stages > 2) smem = dmha_bwd_smem(D, H, p.dh, --pl.stages, stage_bytes).total;   // very wide features: shallower ring
     p.fps = pl.fps; p.stages = pl.stages; p.S = pl.S;
     if (smem > 227 * 1024) { set_error("dmha_bwd: D=%d needs %zu B of shared memory (> 227 KB)", D, smem); return 1; }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     return pl.bf16 ? dispatch_bwd<true>(pl, p, smem, dquery, datt, s) : dispatch_bwd<false>(pl, p, smem, dquery, datt, s);
 }

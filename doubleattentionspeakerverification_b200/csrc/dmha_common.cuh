@@ -99,6 +99,27 @@ __host__ __device__ inline DmhaFwdSmem dmha_fwd_smem(int D, int H, int dh, int S
 int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream);
 size_t dmha_fwd2_workspace_bytes(int B, int D, int H);
 
+struct DmhaBwdParams {
+    const unsigned char* x;
+    const int32_t* lengths;
+    const float* query;
+    const float* att;
+    const float* g_out;
+    const float* g_ctx;
+    const float* ctx;
+    const float* lse;
+    const float* headw;
+    unsigned char* dx;
+    float* ws_dq;      // [grid][D]
+    float* ws_da;      // [grid][dh]
+    int B, T, D, H, dh;
+    int fps, stages, S;
+    float scale_log2, inv_sqrt_h;
+};
+
+// v2 backward (dmha_bwd2.cu): same return convention as dmha_fwd2_launch; *grid_out = number of per-CTA partials written.
+int dmha_bwd2_launch(DmhaBwdParams p, int x_dtype, int max_grid, int* grid_out, cudaStream_t stream);
+
 // Host-side plan shared by forward and backward so both walk the ring identically.
 DmhaPlan dmha_make_plan(int x_dtype, int T, int D, int H, bool backward);
 
