@@ -44,6 +44,73 @@ def batch_plan(lengths, max_frames, max_batch=None, multiple=1):
     return batches
 
 
+class PackedUtterances:
+    """Every utterance's frames in ONE (pinned) host buffer ``[sum T_i, F]`` plus offsets -- the form a feature loader
+    should hand over: no per-batch host padding, the device builds padded batches itself with one gather."""
+
+    def __init__(self, feats, pin=True):
+        self.lengths = np.array([f.shape[0] for f in feats], np.int64)
+        self.offsets = np.concatenate([[0], np.cumsum(self.lengths)])
+        F = feats[0].shape[1]
+        self.data = torch.empty((int(self.offsets[-1]), F), dtype=torch.float32)
+        if pin and torch.cuda.is_available():
+            self.data = self.data.pin_memory()
+        view = self.data.numpy()
+        for f, o in zip(feats, self.offsets[:-1]):
+            view[o:o + f.shape[0]] = f
+
+    def __len__(self):
+        return len(self.lengths)
+
+
+def bucket_plan(lengths, max_frames, min_ratio=0.8, max_batch=None):
+    """Batches over the length-sorted list whose padded size stays <= max_frames AND whose shortest utterance is at
+    least ``min_ratio`` of the longest, which bounds the padding waste of a batch by 1/min_ratio - 1."""
+    idx = np.argsort(-np.asarray(lengths), kind='stable')
+    batches, cur = [], []
+    for i in idx:
+        if cur:
+            Tmax = int(lengths[cur[0]])
+            if (len(cur) + 1) * Tmax > max_frames or lengths[i] < min_ratio * Tmax or (max_batch and len(cur) >= max_batch):
+                batches.append(np.array(cur))
+                cur = []
+        cur.append(int(i))
+    if cur:
+        batches.append(np.array(cur))
+    return batches
+
+
+def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400, min_ratio=0.8, max_batch=None):
+    """Embed ``packed`` utterances ``indices``: their frames go to the device once (one async copy per utterance from
+    the pinned buffer, no host padding), then every batch is ONE device gather into ``[B, Tmax, F]`` with frame indices
+    clamped to the utterance (the kernels ignore frames >= length, so the padding content does not matter).
+    Returns ``[len(indices), E]`` in the order of ``indices``."""
+    indices = np.asarray(indices)
+    if len(indices) == 0:
+        return None
+    dev = torch.device(device)
+    L = packed.lengths[indices]
+    starts = np.concatenate([[0], np.cumsum(L)])
+    frames = torch.empty((int(starts[-1]), packed.data.shape[1]), device=dev, dtype=torch.float32)
+    for j, i in enumerate(indices):
+        o = int(packed.offsets[i])
+        frames[int(starts[j]):int(starts[j + 1])].copy_(packed.data[o:o + int(L[j])], non_blocking=True)
+    starts_d = torch.from_numpy(starts[:-1]).to(dev)
+    L_d = torch.from_numpy(L).to(dev)
+    out = None
+    for b in bucket_plan(L, max_frames, min_ratio, max_batch):
+        bt = torch.from_numpy(b).to(dev)
+        Tmax = int(L[b].max())
+        t = torch.arange(Tmax, device=dev)
+        rows = starts_d[bt, None] + torch.minimum(t[None, :], L_d[bt, None] - 1)          # [B, Tmax] source frame of every slot
+        x = frames[rows]                                                                   # one gather: padded batch
+        emb = embed_fn(x, L_d[bt].to(torch.int32))
+        if out is None:
+            out = torch.empty((len(indices), emb.shape[1]), device=emb.device, dtype=emb.dtype)
+        out[bt] = emb
+    return out
+
+
 def pad_batch(feats, idx, multiple=1):
     """Stack ``feats[i]`` (``[T_i, F]`` arrays) into a zero-padded ``[len(idx), Tmax, F]`` float32 array + lengths."""
     L = np.array([feats[i].shape[0] for i in idx], np.int32)
@@ -76,15 +143,20 @@ def extract_local(embed_fn, feats, indices, device, max_frames=256 * 400, max_ba
 
 def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, max_batch=None, embedding_size=None):
     """Every rank embeds its shard, then one all-gather; returns ``[N, E]`` embeddings of ALL utterances, in
-    the original order, on every rank.  Without an initialised process group it is the single-GPU path."""
+    the original order, on every rank.  Without an initialised process group it is the single-GPU path.
+    ``feats``: list of ``[T_i, F]`` arrays (host-padded batches) or a ``PackedUtterances`` (device-built batches)."""
     import torch.distributed as dist
     N = len(feats)
-    lengths = np.array([f.shape[0] for f in feats])
+    is_packed = isinstance(feats, PackedUtterances)
+    lengths = feats.lengths if is_packed else np.array([f.shape[0] for f in feats])
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     rank = dist.get_rank(group) if distributed else 0
     plan = shard_plan(lengths, world)
-    local = extract_local(embed_fn, feats, plan[rank], device, max_frames, max_batch)
+    if is_packed:
+        local = extract_local_packed(embed_fn, feats, plan[rank], device, max_frames, max_batch=max_batch)
+    else:
+        local = extract_local(embed_fn, feats, plan[rank], device, max_frames, max_batch)
     if world == 1:
         out = torch.empty_like(local)
         out[torch.from_numpy(plan[0]).to(local.device)] = local

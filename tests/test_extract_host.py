@@ -48,6 +48,19 @@ def test_batch_plan_respects_budget_and_covers_all():
     assert x.shape[0] == 3 and x.shape[1] == L.max() and np.all(x[1, L[1]:] == 0)
 
 
+def test_packed_path_and_bucket_plan():
+    lengths = np.random.RandomState(6).randint(200, 2000, size=64)
+    batches = extract.bucket_plan(lengths, max_frames=20000, min_ratio=0.8)
+    assert np.array_equal(np.sort(np.concatenate(batches)), np.arange(64))
+    for b in batches:
+        assert lengths[b].min() >= 0.8 * lengths[b].max() and (len(b) == 1 or len(b) * lengths[b].max() <= 20000)
+    feats = make_feats(19, seed=7)
+    packed = extract.PackedUtterances(feats, pin=False)
+    emb = extract.extract_sharded(stub_embed, packed, 'cpu', max_frames=700)
+    want = torch.cat([stub_embed(torch.from_numpy(f)[None], torch.tensor([f.shape[0]])) for f in feats])
+    assert torch.allclose(emb, want, rtol=1e-5, atol=1e-5)
+
+
 def test_single_process_matches_per_utterance():
     feats = make_feats(23, seed=3)
     emb = extract.extract_sharded(stub_embed, feats, 'cpu', max_frames=600)

@@ -174,6 +174,8 @@ def test_variable_length_extraction_and_trials():
             return net.getEmbedding(xb, lengths=L)
 
     emb = extract.extract_sharded(embed, feats, 'cuda', max_frames=6000)
+    emb_packed = extract.extract_sharded(embed, extract.PackedUtterances(feats), 'cuda', max_frames=6000)   # device-built batches
+    assert min_cosine(emb_packed.cpu().numpy(), emb.cpu().numpy()) > 0.99999
     with torch.no_grad():
         single = torch.cat([net.getEmbedding(dev(f[None])) for f in feats])
     assert min_cosine(emb.cpu().numpy(), single.cpu().numpy()) > 0.9999
