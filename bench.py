@@ -24,7 +24,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # keep stdout to the single JSON line: NCCL's version / debug banner goes to stderr
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+# stdout carries ONLY the JSON line(s): everything else any library prints (e.g. NCCL's version banner, which goes to
+# the C-level stdout) is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout aside for the result
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (line + '\n').encode())
+
 
 import numpy as np   # noqa: E402
 import torch         # noqa: E402
@@ -145,7 +153,7 @@ def run_reference(args, rank):
                                    'utterances, random-init (BASELINE configs[2])', 'batch_per_gpu': BATCH},
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def main():
@@ -342,7 +350,7 @@ def main():
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'dmha_microbench': dmha, 'cpu_baseline': cpu}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

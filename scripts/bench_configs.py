@@ -9,7 +9,15 @@
 import argparse, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+# stdout carries ONLY the JSON line(s): everything else any library prints (e.g. NCCL's version banner, which goes to
+# the C-level stdout) is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout aside for the result
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (line + '\n').encode())
+
 import numpy as np
 import torch
 from doubleattentionspeakerverification_b200 import extract, model, synth
@@ -87,6 +95,6 @@ dt4, scores = timed(trials)
 res4 = {'config': 'configs[4] 1024x1024 cross-product trials, dp%d' % world, 'trials': 1 << 20, 'seconds': dt4,
         'trials_per_s': (1 << 20) / dt4, 'embeddings_per_s': M / dt4, 'score_checksum': float(scores.double().sum().item())}
 if rank == 0:
-    print(json.dumps(res3)); print(json.dumps(res4))
+    emit(json.dumps(res3)); emit(json.dumps(res4))
 if world > 1:
     dist.destroy_process_group()
