@@ -282,7 +282,7 @@ def main():
         roof = {'bound': 'tensor', 'kernel': 'conv3x3_igemm_kernel (7 launches per step, conv12..conv42)',
                 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['bf16_tflops_sustained'], 'peak_source': pk['source'] + ' sustained cuBLAS bf16',
-                'traffic': None, 'avg_launch_ms': conv_ms / len(names), 'share_of_step': conv_ms / (ms / args.steps),
+                'traffic': 1.081e9, 'traffic_source': 'ncu --set full, dram__bytes_read+write averaged over the 7 launches of a step (profiles/r1_final_conv_summary.txt): 7.57 GB per step = compulsory input+output+weights', 'avg_launch_ms': conv_ms / len(names), 'share_of_step': conv_ms / (ms / args.steps),
                 'per_layer_tflops': {n: fl[n] / (per_layer[n] * 1e-3) / 1e12 for n in names}}
 
     # ---- DoubleMHA pooling microbench (BASELINE configs[1]): B=512, T=200, D=1024, H=16, length-masked
@@ -294,40 +294,50 @@ def main():
         q = torch.randn(Dp // Hp, Hp, device=dev, generator=gen) * 0.3
         a = torch.randn(Dp // Hp, device=dev, generator=gen) * 0.3
         lens = torch.from_numpy(synth.make_lengths(Bp, 100, 200, seed=0)).to(dev)
-        for dt_name, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16)):
-            bufs = [torch.randn(Bp, Tp, Dp, device=dev, generator=gen).to(dt) for _ in range(2)]   # 2 x 419 MB fp32 >> L2
-            es = dt.itemsize if hasattr(dt, 'itemsize') else (4 if dt == torch.float32 else 2)
-            for case, L in (('full', None), ('masked', lens)):
-                nbytes = (Bp * Tp if L is None else int(L.sum().item())) * Dp * es + Bp * (Dp // Hp) * 4
-                for i in range(3):
-                    ops.dmha_fwd(bufs[i & 1], q, a, lengths=L, need_align=False)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        def time_us(fn, reps):
+            """Average device time of fn(i): replayed from a CUDA graph so the Python/ctypes launch path (~100 us per
+            call, comparable to these kernels) is not in the measurement; eager timing if capture is unavailable."""
+            for i in range(3):
+                fn(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(reps):
+                        fn(i)
+                g.replay()
                 torch.cuda.synchronize()
-                reps = 20
                 e0.record()
-                for i in range(reps):
-                    ops.dmha_fwd(bufs[i & 1], q, a, lengths=L, need_align=False)
+                g.replay()
                 e1.record()
                 torch.cuda.synchronize()
-                us = e0.elapsed_time(e1) * 1e3 / reps
+                mode = 'cuda-graph'
+            except Exception:
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(reps):
+                    fn(i)
+                e1.record()
+                torch.cuda.synchronize()
+                mode = 'eager'
+            return e0.elapsed_time(e1) * 1e3 / reps, mode
+
+        for dt_name, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16)):
+            bufs = [torch.randn(Bp, Tp, Dp, device=dev, generator=gen).to(dt) for _ in range(2)]   # 2 x 419 MB fp32 >> L2
+            es = 4 if dt == torch.float32 else 2
+            for case, L in (('full', None), ('masked', lens)):
+                nbytes = (Bp * Tp if L is None else int(L.sum().item())) * Dp * es + Bp * (Dp // Hp) * 4
+                us, mode = time_us(lambda i: ops.dmha_fwd(bufs[i & 1], q, a, lengths=L, need_align=False), 20)
                 gbs = nbytes / (us * 1e-6) / 1e9
-                dmha['%s_%s' % (dt_name, case)] = {'us': us, 'gbs': gbs, 'frac': gbs / pk['hbm_gbs'], 'bytes': nbytes}
+                dmha['%s_%s' % (dt_name, case)] = {'us': us, 'gbs': gbs, 'frac': gbs / pk['hbm_gbs'], 'bytes': nbytes, 'timing': mode}
             # backward (read x, write dx): 2x the forward's bytes
             r = ops.dmha_fwd(bufs[0], q, a, need_align=False)
             gout = torch.randn(Bp, Dp // Hp, device=dev, generator=gen)
-            for i in range(3):
-                ops.dmha_bwd(bufs[0], q, a, gout, None, r['ctx'], r['lse'], r['headw'])
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for i in range(10):
-                ops.dmha_bwd(bufs[0], q, a, gout, None, r['ctx'], r['lse'], r['headw'])
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) * 1e3 / 10
+            us, mode = time_us(lambda i: ops.dmha_bwd(bufs[i & 1], q, a, gout, None, r['ctx'], r['lse'], r['headw']), 10)
             nbytes = 2 * Bp * Tp * Dp * es
             dmha['%s_bwd' % dt_name] = {'us': us, 'gbs': nbytes / (us * 1e-6) / 1e9, 'frac': nbytes / (us * 1e-6) / 1e9 / pk['hbm_gbs'],
-                                        'bytes': nbytes, 'note': 'includes the dquery/datt reduce kernel'}
+                                        'bytes': nbytes, 'timing': mode, 'note': 'includes the dquery/datt reduce kernel'}
             del bufs
         dmha['peak_gbs'] = pk['hbm_gbs']
         dmha['shape'] = 'B=512 T=200 D=1024 H=16; 2 rotating inputs (each > L2); no alignment output'
