@@ -203,3 +203,21 @@ def test_million_trial_scoring_properties():
     ib = torch.arange(1024, 2048, device='cuda').repeat(1024)
     p = utils.score_pairs(e, ia, ib)
     assert p.numel() == 1 << 20 and float((p.view(1024, 1024) - m).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize('front,K,H,pm', [('VGG3L', 512, 16, 'DoubleMHA'), ('VGG4L', 512, 8, 'MHA'), ('VGG3L', 1024, 32, 'DoubleMHA')])
+def test_other_front_ends_and_poolings_bf16(front, K, H, pm):
+    """VGG3L (scripts/CNNs.py:22-52) and the MHA pooling through the tensor-core path, against the torch port of the
+    reference on CPU (fp32).  dh = 320 / 640 here, i.e. the pooling shapes outside the exampleModel's."""
+    from oracle import torch_port as tp
+    cfg = synth.example_config(front_end=front, kernel_size=K, embedding_size=64, heads_number=H, pooling_method=pm, num_spkrs=3)
+    cfg.precision = 'bf16'
+    sd = synth.make_state_dict(cfg, 77)
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), sd).cuda().eval()
+    assert net.front_end.resolved_precision() == 'bf16'
+    x = synth.make_logmel(2, 56, seed=78)
+    want = tp.get_embedding(torch.from_numpy(x), tp.as_torch(sd), cfg).numpy()
+    with torch.no_grad():
+        got = net.getEmbedding(dev(x)).cpu().numpy()
+    assert got.shape == want.shape
+    assert min_cosine(got, want) > 0.9995
