@@ -32,6 +32,7 @@ SIGNATURES = {
     'dasv_fc_tail_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'dasv_cosine_pairs': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     'dasv_cosine_matrix_workspace_bytes': (_sz, [_i, _i]),
+    'dasv_threshold_counts': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     'dasv_cosine_matrix': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 

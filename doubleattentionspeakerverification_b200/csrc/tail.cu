@@ -155,6 +155,32 @@ __global__ void __launch_bounds__(256) cosine_matrix_kernel(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------ EER threshold counts
+// ge[k] = #{ i : scores[i] >= thresholds[k] } for the validation sweep of scripts/train.py:135-150 (200 thresholds,
+// scripts/utils.py:5-15 `Score`): comparisons in double, like the reference's float(sc) >= float(th).  Each thread owns
+// a score and walks the (shared-memory) threshold list; warp ballots keep the integer atomics to one per warp.
+__global__ void __launch_bounds__(256) threshold_counts_kernel(const float* __restrict__ scores, int n,
+                                                              const double* __restrict__ thresholds, int n_th,
+                                                              unsigned long long* __restrict__ ge) {
+    extern __shared__ double th_sm[];
+    unsigned int* cnt_sm = reinterpret_cast<unsigned int*>(th_sm + n_th);
+    for (int k = threadIdx.x; k < n_th; k += blockDim.x) { th_sm[k] = thresholds[k]; cnt_sm[k] = 0u; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < n; base += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const bool have = i < n;
+        const double sc = have ? static_cast<double>(scores[i]) : 0.0;
+        for (int k = 0; k < n_th; ++k) {
+            const unsigned int m = __ballot_sync(0xffffffffu, have && sc >= th_sm[k]);
+            if (lane == 0 && m) atomicAdd(&cnt_sm[k], __popc(m));
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_th; k += blockDim.x)
+        if (cnt_sm[k]) atomicAdd(&ge[k], static_cast<unsigned long long>(cnt_sm[k]));
+}
+
 // ------------------------------------------------------------------------------ Attention pooling
 // scores: one warp per frame
 __global__ void attention_scores_kernel(const unsigned char* __restrict__ x, int bf16, const float* __restrict__ att,
@@ -267,6 +293,21 @@ extern "C" int dasv_cosine_matrix(const float* enrol, const float* test, float* 
     dim3 grid((Nt + 63) / 64, (Ne + 63) / 64);
     cosine_matrix_kernel<<<grid, 256, 0, s>>>(enrol, test, inv_e, inv_t, scores, Ne, Nt, E);
     return check_launch("cosine_matrix");
+}
+
+extern "C" int dasv_threshold_counts(const float* scores, int n, const double* thresholds, int n_th,
+                                     unsigned long long* ge_counts, void* stream) {
+    if (!thresholds || !ge_counts || (n > 0 && !scores)) { set_error("threshold_counts: null argument"); return 1; }
+    if (n_th <= 0 || n_th > 4096) { set_error("threshold_counts: n_th=%d must be in 1..4096", n_th); return 1; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(ge_counts, 0, static_cast<size_t>(n_th) * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) { set_error("threshold_counts: memset: %s", cudaGetErrorString(e)); return 1; }
+    if (n <= 0) return 0;
+    int grid = (n + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    const size_t smem = static_cast<size_t>(n_th) * (sizeof(double) + sizeof(unsigned int));
+    threshold_counts_kernel<<<grid, 256, smem, s>>>(scores, n, thresholds, n_th, ge_counts);
+    return check_launch("threshold_counts");
 }
 
 extern "C" int dasv_attention_fwd(const void* x, int x_dtype, const int32_t* lengths, const uint8_t* keep,

@@ -225,3 +225,14 @@ def score_cross(emb, enrol_idx, test_idx):
     e = emb[torch.as_tensor(np.asarray(enrol_idx), device=emb.device)].contiguous()
     t = emb[torch.as_tensor(np.asarray(test_idx), device=emb.device)].contiguous()
     return utils.score_matrix(e, t)
+
+
+def validate(embed_fn, utterances, client_trials, impostor_trials, device, **kw):
+    """The reference's validation pass (scripts/train.py:158-184: __extract_scores on the client and impostor
+    trial lists, then __calculate_EER) without its per-trial forwards: every utterance is embedded once (sharded over
+    the ranks when a process group is up), both trial lists are scored by one kernel each, and the 200-threshold
+    FAR/FRR sweep runs on the device.  ``*_trials``: ``[M,2]`` utterance-index pairs.  Returns (EER, CL, IM)."""
+    emb = extract_sharded(embed_fn, utterances, device, **kw)
+    CL = score_trial_list(emb, client_trials)
+    IM = score_trial_list(emb, impostor_trials)
+    return utils.calculate_EER(CL, IM), CL, IM

@@ -251,3 +251,14 @@ def cosine_matrix(enrol, test):
         ws = torch.empty((Ne + Nt,), device=enrol.device, dtype=torch.float32)
         _lib.check(_lib.lib().dasv_cosine_matrix(_p(enrol), _p(test), _p(scores), _p(ws), Ne, Nt, E, _stream()), 'dasv_cosine_matrix')
     return scores
+
+
+def threshold_counts(scores, thresholds):
+    """counts[k] = #{scores >= thresholds[k]} (double comparison).  scores f32 [n], thresholds f64 [n_th] -> int64 [n_th]."""
+    scores = _f32(scores.reshape(-1), 'scores')
+    with torch.cuda.device(scores.device):
+        th = torch.as_tensor(thresholds, device=scores.device, dtype=torch.float64).contiguous()
+        out = torch.empty((th.numel(),), device=scores.device, dtype=torch.int64)
+        rc = _lib.lib().dasv_threshold_counts(_p(scores) if scores.numel() else None, scores.numel(), _p(th), th.numel(), _p(out), _stream())
+        _lib.check(rc, 'dasv_threshold_counts')
+    return out

@@ -1,8 +1,9 @@
-"""Trial scoring (reference ``scripts/utils.py:18-21``) on the sm_100a kernels.
+"""Trial scoring (reference ``scripts/utils.py:18-21``) and the EER sweep (``scripts/train.py:135-150``) on the sm_100a kernels.
 
 ``scoreCosineDistance`` keeps the reference signature; ``score_pairs`` / ``score_matrix`` are the
 batched forms the validation loop (scripts/train.py:117-133) is replaced with.
 """
+import numpy as np
 import torch
 
 from . import ops
@@ -28,3 +29,20 @@ def score_pairs(emb, idx_a, idx_b):
 def score_matrix(enrol, test):
     """scores[i,j] = cos(enrol[i], test[j]) — the cross-product form."""
     return ops.cosine_matrix(enrol, test)
+
+
+def calculate_EER(CL, IM):
+    """Trainer.__calculate_EER (scripts/train.py:135-150) with Score (scripts/utils.py:5-15): 200 thresholds
+    np.arange(-1, 1, 0.01), FRR = % of client scores < th, FAR = % of impostor scores >= th (both rounded to 4
+    decimals), EER at the first sign change of FAR - FRR, else 50.  ``CL`` / ``IM`` are CUDA score tensors; the
+    2 x 200 x N comparisons run in one kernel each instead of 400 Python loops."""
+    thresholds = np.arange(-1, 1, 0.01)
+    n_cl, n_im = CL.numel(), IM.numel()
+    ge_cl = ops.threshold_counts(CL, thresholds).cpu().numpy()
+    ge_im = ops.threshold_counts(IM, thresholds).cpu().numpy()
+    FRR = np.array([round((n_cl - g) * 100 / float(n_cl), 4) for g in ge_cl])
+    FAR = np.array([round(g * 100 / float(n_im), 4) for g in ge_im])
+    idx = np.argwhere(np.diff(np.sign(FAR - FRR)) != 0).reshape(-1)
+    if len(idx) > 0:
+        return round((FAR[int(idx[0])] + FRR[int(idx[0])]) / 2, 4)
+    return 50.00

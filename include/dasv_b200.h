@@ -149,6 +149,12 @@ size_t dasv_cosine_matrix_workspace_bytes(int Ne, int Nt);
 int dasv_cosine_matrix(const float* enrol, const float* test, float* scores, void* workspace,
                        int Ne, int Nt, int E, void* stream);
 
+/* EER sweep counts (scripts/train.py:135-150 with scripts/utils.py:5-15): ge_counts[k] = #{scores[i] >= thresholds[k]},
+ * compared in double like the reference; FAR = 100*ge/n on impostor scores, FRR = 100*(n-ge)/n on client scores.
+ * scores [n] f32, thresholds [n_th] f64 (device), ge_counts [n_th] u64 (device, overwritten). */
+int dasv_threshold_counts(const float* scores, int n, const double* thresholds, int n_th,
+                          unsigned long long* ge_counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

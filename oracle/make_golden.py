@@ -164,10 +164,36 @@ def scoring_case():
     np.savez_compressed(os.path.join(OUT, 'cosine_0.npz'), seed=np.array(51), scores=s)
 
 
+def eer_synthetic_scores(seed, n_cl, n_im, sep):
+    rs = np.random.RandomState(seed)
+    CL = (0.5 + sep + 0.2 * rs.standard_normal(n_cl)).clip(-1, 1).astype(np.float32)
+    IM = (0.5 - sep + 0.2 * rs.standard_normal(n_im)).clip(-1, 1).astype(np.float32)
+    return CL, IM
+
+
+def eer_case():
+    """Trainer.__calculate_EER (scripts/train.py:135-150) from the live reference.  train.py imports data.py, which
+    imports soundfile (not installed, unused by the EER code): an empty stub module lets the import through."""
+    import types
+    sys.modules.setdefault('soundfile', types.ModuleType('soundfile'))
+    import train as ref_train    # reference scripts/train.py
+    specs = [(61, 500, 700, 0.2), (62, 1000, 3000, 0.05), (63, 64, 64, 0.6), (64, 200, 100, -0.1)]
+    eers = []
+    for seed, n_cl, n_im, sep in specs:
+        CL, IM = eer_synthetic_scores(seed, n_cl, n_im, sep)
+        eers.append(ref_train.Trainer._Trainer__calculate_EER(None, [float(v) for v in CL], [float(v) for v in IM]))
+    np.savez_compressed(os.path.join(OUT, 'eer_0.npz'), specs=np.array(specs, np.float64), eer=np.array(eers, np.float64))
+    print('eer', eers)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'eer':
+        eer_case()
+        sys.exit(0)
     pooling_cases()
     frontend_cases()
     embedding_cases()
     scoring_case()
+    eer_case()
     print('golden fixtures written to', OUT)

@@ -207,3 +207,16 @@ def cosine_matrix(enrol, test, eps=1e-8):
     a = enrol / np.maximum(np.linalg.norm(enrol, axis=-1, keepdims=True), eps)
     b = test / np.maximum(np.linalg.norm(test, axis=-1, keepdims=True), eps)
     return a @ b.T
+
+
+def calculate_eer(CL, IM):
+    """Trainer.__calculate_EER (scripts/train.py:135-150) over Score (scripts/utils.py:5-15), vectorised."""
+    CL = np.asarray(CL, np.float64)
+    IM = np.asarray(IM, np.float64)
+    thresholds = np.arange(-1, 1, 0.01)
+    FRR = np.array([round(float(np.sum(CL < th)) * 100 / float(len(CL)), 4) for th in thresholds])
+    FAR = np.array([round(float(np.sum(IM >= th)) * 100 / float(len(IM)), 4) for th in thresholds])
+    idx = np.argwhere(np.diff(np.sign(FAR - FRR)) != 0).reshape(-1)
+    if len(idx) > 0:
+        return round((FAR[int(idx[0])] + FRR[int(idx[0])]) / 2, 4)
+    return 50.00

@@ -187,6 +187,9 @@ def test_variable_length_extraction_and_trials():
     assert np.max(np.abs(s - s_single)) < 1e-3                       # north_star trial-score bar
     m = extract.score_cross(emb, np.arange(5), np.arange(5, 10)).cpu().numpy()
     assert np.max(np.abs(m - po.cosine_matrix(e[:5], e[5:]))) < 1e-5
+    # whole validation pass (train.py:158-184): EER from the same embeddings == the oracle's sweep on the same scores
+    eer, CL, IM = extract.validate(embed, extract.PackedUtterances(feats), trials[:120], trials[120:], 'cuda', max_frames=6000)
+    assert eer == po.calculate_eer(CL.cpu().numpy(), IM.cpu().numpy())
 
 
 def test_million_trial_scoring_properties():
@@ -221,3 +224,19 @@ def test_other_front_ends_and_poolings_bf16(front, K, H, pm):
         got = net.getEmbedding(dev(x)).cpu().numpy()
     assert got.shape == want.shape
     assert min_cosine(got, want) > 0.9995
+
+
+def test_eer_sweep_matches_reference_golden():
+    """utils.calculate_EER (GPU threshold counts) == Trainer.__calculate_EER of the live reference (golden) and the oracle."""
+    g = golden('eer_0.npz')
+    for (seed, n_cl, n_im, sep), want in zip(g['specs'], g['eer']):
+        rs = np.random.RandomState(int(seed))
+        CL = (0.5 + sep + 0.2 * rs.standard_normal(int(n_cl))).clip(-1, 1).astype(np.float32)
+        IM = (0.5 - sep + 0.2 * rs.standard_normal(int(n_im))).clip(-1, 1).astype(np.float32)
+        assert utils.calculate_EER(dev(CL), dev(IM)) == want == po.calculate_eer(CL, IM)
+    # 1 M scores: counts agree with numpy exactly
+    rs = np.random.RandomState(9)
+    sc = rs.uniform(-1, 1, size=1 << 20).astype(np.float32)
+    th = np.arange(-1, 1, 0.01)
+    cnt = ops.threshold_counts(dev(sc), th).cpu().numpy()
+    assert np.array_equal(cnt, np.array([np.sum(sc.astype(np.float64) >= t) for t in th]))

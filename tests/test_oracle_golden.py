@@ -115,3 +115,12 @@ def test_cosine():
     assert np.max(np.abs(po.cosine_scores(e1, e2) - g['scores'])) < 1e-6
     assert np.max(np.abs(np.diag(po.cosine_matrix(e1, e2)) - g['scores'])) < 1e-6
     assert np.max(np.abs(tp.cosine(torch.from_numpy(e1), torch.from_numpy(e2)).numpy() - g['scores'])) < 1e-6
+
+
+def test_eer():
+    g = golden('eer_0.npz')
+    for (seed, n_cl, n_im, sep), want in zip(g['specs'], g['eer']):
+        rs = np.random.RandomState(int(seed))
+        CL = (0.5 + sep + 0.2 * rs.standard_normal(int(n_cl))).clip(-1, 1).astype(np.float32)
+        IM = (0.5 - sep + 0.2 * rs.standard_normal(int(n_im))).clip(-1, 1).astype(np.float32)
+        assert po.calculate_eer(CL, IM) == want
