@@ -63,7 +63,12 @@ class Attention(nn.Module):
 
     def forward(self, ht, lengths=None):
         if torch.is_grad_enabled() and (ht.requires_grad or self.att.requires_grad):
-            raise NotImplementedError('Attention pooling has a forward kernel only; run it under torch.no_grad()')
+            # training path: stock torch ops + autograd (like the conv stack; only DoubleMHA / MHA have hand-written
+            # backward kernels).  Same math as the reference, without its batch-collapsing squeeze().
+            if lengths is not None:
+                raise NotImplementedError('length masking is an inference-only capability')
+            score = torch.softmax(torch.matmul(ht, self.att).squeeze(-1), dim=-1).unsqueeze(-1)
+            return torch.sum(ht * score, dim=1), score
         ct, p = ops.attention_fwd(ht, self.att, lengths=lengths)
         return ct, p.view(ht.size(0), ht.size(1), 1)
 
@@ -86,10 +91,15 @@ class HeadAttention(nn.Module):
         return torch.randint(0, self.mask_prob, (batch, heads), device=device) > 0
 
     def forward(self, ht, keep=None):
-        if torch.is_grad_enabled() and (ht.requires_grad or self.att.requires_grad):
-            raise NotImplementedError('stand-alone HeadAttention has a forward kernel only; DoubleMHA fuses it with its backward')
         if self.training and keep is None:
             keep = self.draw_keep_mask(ht.size(0), ht.size(1), ht.device)
+        if torch.is_grad_enabled() and (ht.requires_grad or self.att.requires_grad):
+            # stand-alone use under autograd: stock torch ops (DoubleMHA fuses this stage with its own backward kernel)
+            score = torch.matmul(ht, self.att).squeeze(-1)
+            if keep is not None:
+                score = score.masked_fill(~keep.bool(), float('-inf'))
+            score = torch.softmax(score, dim=-1).unsqueeze(-1)
+            return torch.sum(ht * score, dim=1), score
         ct, w = ops.attention_fwd(ht, self.att, keep=keep)
         return ct, w.view(ht.size(0), ht.size(1), 1)
 

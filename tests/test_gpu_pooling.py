@@ -192,3 +192,25 @@ def test_stream_split_schedule_matches_whole_utterance_schedule(monkeypatch):
     split = ops.dmha_fwd(*args, lengths=dev(c['lengths']))
     for k in ('out', 'ctx', 'lse', 'headw', 'align'):
         assert max_rel(split[k].cpu().numpy(), base[k].cpu().numpy()) < 1e-5, k
+
+
+def test_attention_and_head_attention_train_under_autograd():
+    """pooling_method='Attention' (scripts/model.py:35-36) and the stand-alone HeadAttention are trainable: under
+    autograd they use torch ops; values equal the forward kernels, gradients flow to input and parameter."""
+    c = synth.make_pooling_case(3, 17, 320, 8, seed=4)
+    m = poolings.Attention(320).cuda()
+    x = dev(c['x']).requires_grad_(True)
+    ct, p = m(x)
+    ct.sum().backward()
+    assert x.grad is not None and m.att.grad is not None and p.shape == (3, 17, 1)
+    with torch.no_grad():
+        ct2, p2 = m(x.detach())
+    assert max_rel(ct.detach().cpu().numpy(), ct2.cpu().numpy()) < 1e-5
+    ha = poolings.HeadAttention(320, 8, mask_prob=0.3).cuda().train()
+    h = dev(c['x'][:, :8, :40].copy()).requires_grad_(True)
+    keep = dev(c['keep'])
+    out, w = ha(h, keep=keep)
+    out.sum().backward()
+    with torch.no_grad():
+        out2, w2 = ha(h.detach(), keep=keep)
+    assert max_rel(out.detach().cpu().numpy(), out2.cpu().numpy()) < 1e-5 and h.grad is not None
