@@ -111,8 +111,11 @@ class _VGG(nn.Module):
                     h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk], 'bf16'), c.bias, c.out_channels, L)
                 c = getattr(self, self._names[2 * blk + 1])
                 last = blk == nblocks - 1
+                # CTA pairs (cta_group::2) measured faster on the pooled layers with >= 256 input channels (conv22 +3 %,
+                # conv32 +9 %, conv42 +1 %) and slower elsewhere; results are bit-identical either way
+                pair = c.in_channels >= 256 and c.out_channels % 256 == 0
                 h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk + 1], 'bf16'), c.bias, c.out_channels, L,
-                                           pool=True, ref_layout=last, out_dtype=torch.float32)
+                                           pool=True, ref_layout=last, out_dtype=torch.float32, pair=pair)
                 if L is not None:
                     L = (L + 1) // 2
             return h

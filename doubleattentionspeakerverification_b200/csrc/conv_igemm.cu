@@ -44,18 +44,23 @@ struct ConvParams {
     uint32_t stage_bytes;    // per ring-1 stage: A + B(padded) (per-tap mode) or one B patch (tap-row reuse mode)
     uint32_t tmem_cols;
     int reuse;               // 1: B patches carry a +-1 frame halo and serve the three taps of a column (dy = -1,0,1)
-    int tgap;                // halo rows per utterance in accumulator-column space (2 in reuse mode, else 0)
+    int gap_cols;            // unused accumulator columns between the blocks of consecutive utterances of a patch
+                             // (2*BF halo rows in single-CTA reuse mode; the 8-row padding of a half in pair mode; else 0)
     int sa;                  // reuse mode: stages of the separate A (weight tile) ring
+    int pair;                // 1: CTA pairs (cta_group::2): 256 channels x N pixels per pair, each CTA loads half of the patch
+    int RT;                  // pair mode: frames of the patch half one CTA loads (without halo)
+    int split_t;             // pair mode: halves split along t (BB == 1) or along the utterance (BB == 2)
 };
 
 struct ConvTile {
     int m, f0, t0, b0;
 };
 
-DASV_DEVICE ConvTile conv_decode_tile(const ConvParams& p, int tile) {
+DASV_DEVICE ConvTile conv_decode_tile(const ConvParams& p, int tile, int n_mt_eff, int rank) {
     ConvTile c;
-    c.m = tile % p.n_mt;
-    int pt = tile / p.n_mt;
+    c.m = tile % n_mt_eff;
+    if (p.pair) c.m = c.m * 2 + rank;        // a pair owns two adjacent 128-channel tiles
+    int pt = tile / n_mt_eff;
     c.f0 = (pt % p.n_ft) * p.BF; pt /= p.n_ft;
     c.t0 = (pt % p.n_tt) * p.BT; pt /= p.n_tt;
     c.b0 = pt * p.BB;
@@ -97,6 +102,7 @@ DASV_DEVICE void conv_store(void* y, size_t idx, float v) {
     else static_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -115,19 +121,27 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = p.n_mt * p.n_ft * p.n_tt * p.n_bt;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                  // 0 = leader of the CTA pair
+    const int n_mt_eff = PAIR ? p.n_mt / 2 : p.n_mt;
+    const int n_tiles = n_mt_eff * p.n_ft * p.n_tt * p.n_bt;
+    const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int ksteps = 9 * p.kchunks;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < p.sa; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 16 : 8); }
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
-    if (warp == 2) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) { tmem_alloc_2sm(tmem_slot, p.tmem_cols); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();       // the peer's barriers must exist before remote arrivals / TMA completions reach them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -137,20 +151,35 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // tap-row reuse: per (64-channel slice, dx) ONE activation patch with a +-1 frame halo, then the three
             // weight tiles of that tap column (dy = -1, 0, +1); 3x less activation traffic than one box per tap.
             uint32_t sb = 0, bph = 0, sa = 0, aph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const ConvTile c = conv_decode_tile(p, tile);
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+                const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
                 if (conv_tile_masked(p, c)) continue;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     for (int dxi = 0; dxi < 3; ++dxi) {
                         mbar_wait(&empty[sb], bph ^ 1u);
-                        mbar_arrive_expect_tx(&full[sb], p.b_bytes);
-                        tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kc * kConvKC, c.f0 + dxi - 1, c.t0 - 1, c.b0);
+                        if (PAIR) {
+                            // each CTA fetches ITS half of the patch (+ halo) into its own SMEM; both loads complete on
+                            // the leader's barrier, which the leader arms for the bytes of both
+                            const int tq = c.t0 + (p.split_t ? static_cast<int>(rank) * p.RT : 0);
+                            const int bq = c.b0 + (p.split_t ? 0 : static_cast<int>(rank));
+                            if (rank == 0) mbar_arrive_expect_tx(&full[sb], 2u * p.b_bytes);
+                            tma_load_4d_2sm(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kc * kConvKC, c.f0 + dxi - 1, tq - 1, bq);
+                        } else {
+                            mbar_arrive_expect_tx(&full[sb], p.b_bytes);
+                            tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kc * kConvKC, c.f0 + dxi - 1, c.t0 - 1, c.b0);
+                        }
                         if (++sb == static_cast<uint32_t>(p.stages)) { sb = 0; bph ^= 1u; }
                         for (int dyi = 0; dyi < 3; ++dyi) {
                             mbar_wait(&aempty[sa], aph ^ 1u);
-                            mbar_arrive_expect_tx(&afull[sa], kConvABytes);
-                            tma_load_2d(ring_a + static_cast<size_t>(sa) * kConvABytes, &tmA, &afull[sa],
-                                        (dyi * 3 + dxi) * p.Cin + kc * kConvKC, c.m * kConvTileM);
+                            if (PAIR) {
+                                if (rank == 0) mbar_arrive_expect_tx(&afull[sa], 2u * kConvABytes);
+                                tma_load_2d_2sm(ring_a + static_cast<size_t>(sa) * kConvABytes, &tmA, &afull[sa],
+                                                (dyi * 3 + dxi) * p.Cin + kc * kConvKC, c.m * kConvTileM);
+                            } else {
+                                mbar_arrive_expect_tx(&afull[sa], kConvABytes);
+                                tma_load_2d(ring_a + static_cast<size_t>(sa) * kConvABytes, &tmA, &afull[sa],
+                                            (dyi * 3 + dxi) * p.Cin + kc * kConvKC, c.m * kConvTileM);
+                            }
                             if (++sa == static_cast<uint32_t>(p.sa)) { sa = 0; aph ^= 1u; }
                         }
                     }
@@ -158,8 +187,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         } else if (lane == 0) {
             uint32_t st = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const ConvTile c = conv_decode_tile(p, tile);
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+                const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
                 if (conv_tile_masked(p, c)) continue;
                 for (int tap = 0; tap < 9; ++tap) {
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -176,11 +205,11 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kConvTileM, static_cast<uint32_t>(p.Npad));
+        if (lane == 0 && rank == 0) {           // in pair mode only the leader issues (for both CTAs)
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kConvTileM : kConvTileM, static_cast<uint32_t>(p.Npad));
             uint32_t st = 0, ph = 0, sa = 0, aph = 0, acc_it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const ConvTile c = conv_decode_tile(p, tile);
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+                const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
                 if (conv_tile_masked(p, c)) continue;
                 const uint32_t as = acc_it & 1u, accph = (acc_it >> 1) & 1u;
                 mbar_wait(&acc_empty[as], accph ^ 1u);
@@ -200,14 +229,17 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             //  measured on B200 -- the descriptor's base-offset field must stay 0 for this)
                             const uint64_t b_desc = umma_desc_k128(b_addr + static_cast<uint32_t>(dyi * p.BF) * 128u);
 #pragma unroll
-                            for (int k = 0; k < kConvKC / 16; ++k)
-                                umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
-                                          (first && k == 0) ? 0u : 1u);
+                            for (int k = 0; k < kConvKC / 16; ++k) {
+                                if (PAIR) umma_bf16_2sm(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                                                        (first && k == 0) ? 0u : 1u);
+                                else umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                                               (first && k == 0) ? 0u : 1u);
+                            }
                             first = 0u;
-                            umma_commit(&aempty[sa]);
+                            if (PAIR) umma_commit_2sm(&aempty[sa], 3); else umma_commit(&aempty[sa]);
                             if (++sa == static_cast<uint32_t>(p.sa)) { sa = 0; aph ^= 1u; }
                         }
-                        umma_commit(&empty[st]);               // patch free once its three tap rows have retired
+                        if (PAIR) umma_commit_2sm(&empty[st], 3); else umma_commit(&empty[st]);   // patch free once its three tap rows have retired
                         if (++st == static_cast<uint32_t>(p.stages)) { st = 0; ph ^= 1u; }
                     }
                 } else {
@@ -225,7 +257,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         if (++st == static_cast<uint32_t>(p.stages)) { st = 0; ph ^= 1u; }
                     }
                 }
-                umma_commit(&acc_full[as]);                    // accumulator complete -> epilogue
+                if (PAIR) umma_commit_2sm(&acc_full[as], 3); else umma_commit(&acc_full[as]);   // accumulator complete -> epilogue(s)
                 ++acc_it;
             }
         }
@@ -244,14 +276,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int OBF = p.pool ? BF / 2 : BF, OBT = p.pool ? BT / 2 : BT;   // output patch
         const int OT = p.pool ? T2 : T, OF = p.pool ? F2 : F;
         const int OPP = OBT * OBF;                              // output pixels per utterance of the patch
-        const int PR = BT + p.tgap;                             // accumulator-column rows per utterance (halo rows leave gaps)
+        const int UC = BT * BF + p.gap_cols;                    // accumulator columns per utterance of the patch (incl. gap)
         const int NO = p.BB * OPP;                              // output pixels per tile
         const float inv_obf = 1.0f / static_cast<float>(OBF), inv_opp = 1.0f / static_cast<float>(OPP);
         const int ch = q * 32 + lane;                           // channel within the 128-wide tile
         unsigned char* my_stage = stage + half * (2 * kConvEpiBytes);
         uint32_t acc_it = 0, chunk_it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const ConvTile c = conv_decode_tile(p, tile);
+        for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+            const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
             const int n = c.m * kConvTileM + ch;
             const bool n_ok = n < Cout;
             const bool masked = conv_tile_masked(p, c);
@@ -274,7 +306,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const int t = c.t0 + 2 * tp;
                     if (b >= p.B || t >= T) continue;           // warp-uniform
                     const bool r0_ok = !masked && t < Lb, r1_ok = !masked && (t + 1) < Lb;
-                    const uint32_t col0 = tcol + static_cast<uint32_t>((bb * PR + 2 * tp) * BF);
+                    const uint32_t col0 = tcol + static_cast<uint32_t>(bb * UC + 2 * tp * BF);
                     const size_t row = (static_cast<size_t>(b) * T2 + (t >> 1)) * (static_cast<size_t>(Cout) * F2) +
                                        static_cast<size_t>(n) * F2 + (c.f0 >> 1);
                     for (int fp0 = 0; fp0 < BF / 2; fp0 += 4) {
@@ -304,7 +336,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (!masked) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
+                    if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&acc_empty[acc_it & 1u], 0); else mbar_arrive(&acc_empty[acc_it & 1u]); }
                     ++acc_it;
                 }
                 continue;
@@ -320,7 +352,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     // phase 1: this thread's channel of `cnt` output pixels -> staging[pixel][ch]
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + ch;
                     if (!p.pool) {
-                        // output o of utterance bb sits in accumulator column o + bb * tgap * BF
+                        // output o of utterance bb sits in accumulator column o + bb * gap_cols
 #pragma unroll
                         for (int g16 = 0; g16 < kConvEpiChunk / 16; ++g16) {
                             const int oa = o0 + g16 * 16;
@@ -328,14 +360,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 uint32_t r[16];
                                 const int bba = __float2int_rz((static_cast<float>(oa) + 0.5f) * inv_opp);
                                 const int bbz = __float2int_rz((static_cast<float>(min(oa + 15, NO - 1)) + 0.5f) * inv_opp);
-                                const int cola = oa + bba * p.tgap * BF;
+                                const int cola = oa + bba * p.gap_cols;
                                 if (bba == bbz && cola + 16 <= p.Npad) {
                                     tmem_ld_x16(tcol + cola, r);
                                 } else {                        // group straddles an utterance boundary (or the accumulator's end)
 #pragma unroll
                                     for (int j = 0; j < 16; ++j) {
                                         const int bbj = __float2int_rz((static_cast<float>(min(oa + j, NO - 1)) + 0.5f) * inv_opp);
-                                        tmem_ld_x1(tcol + min(oa + j + bbj * p.tgap * BF, p.Npad - 1), r[j]);
+                                        tmem_ld_x1(tcol + min(oa + j + bbj * p.gap_cols, p.Npad - 1), r[j]);
                                     }
                                 }
                                 tc_wait_ld();
@@ -357,7 +389,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (j0 + u < cnt) {             // warp-uniform
-                                    const uint32_t col = tcol + static_cast<uint32_t>((bb * PR + 2 * tp) * BF + 2 * fp);
+                                    const uint32_t col = tcol + static_cast<uint32_t>(bb * UC + 2 * tp * BF + 2 * fp);
                                     r1[u] = (c.t0 + 2 * tp + 1) < Lcur;     // ceil-mode / masked second row
                                     tmem_ld_x2(col, v[u][0], v[u][1]);
                                     tmem_ld_x2(col + BF, v[u][2], v[u][3]);
@@ -407,14 +439,18 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (!masked) {                                      // all of this warp's TMEM reads of the tile are done
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
+                if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&acc_empty[acc_it & 1u], 0); else mbar_arrive(&acc_empty[acc_it & 1u]); }
                 ++acc_it;
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, p.tmem_cols); }
+    if (PAIR) cluster_sync_all();       // nobody leaves (or frees TMEM) while the peer may still signal into this CTA
+    else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        if (PAIR) tmem_dealloc_2sm(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
+    }
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -444,7 +480,7 @@ struct ConvPlan {
 // MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
 // ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
-static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo) {
+static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo, bool pair) {
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
     for (int BF = 2; BF <= F && BF <= 256; BF += 2) {
@@ -455,11 +491,20 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo) {
             const int n_tt = (T + BT - 1) / BT;
             const int bb_max = 256 / (BF * BT);          // several utterances per patch when one utterance's rows leave room
             for (int BB = 1; BB <= bb_max && BB <= B; ++BB) {
-                const int N = (BB - 1) * (BT + halo) * BF + BT * BF;      // accumulator columns incl. halo gaps
+                int N = (BB - 1) * (BT + halo) * BF + BT * BF;            // accumulator columns incl. halo gaps
+                double b_rows = halo ? BB * (BT + 2.0) * BF / 3.0 : BB * BT * BF;   // activation rows fetched per tap (per CTA)
+                if (pair) {
+                    // CTA pairs: the patch is cut in two equal halves (along t, or one utterance each); every half
+                    // carries its own halo, so there are no gap columns, and N must split on an 8-row boundary
+                    if (!((BB == 1 && BT % 2 == 0) || BB == 2)) continue;
+                    if (BB == 1) { N = BT * BF; if (N % 16 != 0) continue; }      // halves split along t: no room for padding
+                    else N = 2 * ((BT * BF + 7) / 8 * 8);                          // one utterance per CTA, each half padded to 8 rows
+                    const int RT = BB == 1 ? BT / 2 : BT;
+                    b_rows = (RT + 2.0) * BF / 3.0;
+                }
                 const int Npad = (N + 15) / 16 * 16;
                 if (Npad > 256) continue;
                 const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB);
-                const double b_rows = halo ? BB * (BT + 2.0) * BF / 3.0 : BB * BT * BF;   // activation rows fetched per tap
                 const double ingest = (128.0 + b_rows) * 32.0 / 52.0;                   // bytes per 16-deep step / ~52 B/clk effective
                 const double step = Npad / 2.0 > ingest ? Npad / 2.0 : ingest;
                 const double cost = tiles * (step * ksteps + 700.0);
@@ -496,17 +541,26 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     // tap-row reuse is the default; DASV_CONV_REUSE=0 selects one TMA box per tap (A/B comparisons, debugging)
     int reuse = 1;
     if (const char* e = getenv("DASV_CONV_REUSE")) reuse = atoi(e) != 0;
-    ConvPlan pl = conv_plan(B, T, F, Cin, pool, reuse ? 2 : 0);
+    const int cout_pad = (Cout + kConvTileM - 1) / kConvTileM * kConvTileM;
+    // CTA pairs (cta_group::2, 256 channels per pair) need an even number of 128-channel tiles; DASV_CONV_PAIR=0/1 overrides
+    int pair = (flags & 8) != 0;                                 // DASV_CONV_PAIR
+    if (const char* e = getenv("DASV_CONV_PAIR")) pair = atoi(e) != 0;
+    if (!reuse || cout_pad % (2 * kConvTileM) != 0) pair = 0;
+    ConvPlan pl = conv_plan(B, T, F, Cin, pool, reuse ? 2 : 0, pair != 0);
+    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Cin, pool, 2, false); }
     if (const char* e = getenv("DASV_CONV_PLAN")) {             // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
         int bf = 0, bt = 0, bb = 0;
         if (sscanf(e, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
-            const int n = (bb - 1) * (bt + (reuse ? 2 : 0)) * bf + bt * bf;
-            if ((n + 15) / 16 * 16 <= 256) pl = ConvPlan{bf, bt, bb, n, (n + 15) / 16 * 16, 0.0};
+            int n = (bb - 1) * (bt + (reuse ? 2 : 0)) * bf + bt * bf;
+            bool ok = true;
+            if (pair) { ok = (bb == 1 && bt % 2 == 0 && (bt * bf) % 16 == 0) || bb == 2; n = bb == 1 ? bt * bf : 2 * ((bt * bf + 7) / 8 * 8); }
+            if (ok && (n + 15) / 16 * 16 <= 256) pl = ConvPlan{bf, bt, bb, n, (n + 15) / 16 * 16, 0.0};
         }
     }
     if (pl.N == 0) { set_error("conv3x3_igemm_bf16: no patch shape for T=%d F=%d", T, F); return 1; }
-    const int cout_pad = (Cout + kConvTileM - 1) / kConvTileM * kConvTileM;
-    const int box_t = pl.BT + (reuse ? 2 : 0);
+    const int pair_rt = pl.BB == 1 ? pl.BT / 2 : pl.BT;           // frames per CTA half in pair mode
+    const int box_t = pair ? pair_rt + 2 : pl.BT + (reuse ? 2 : 0);
+    const int box_b = pair ? 1 : pl.BB;
 
     CUtensorMap tmA, tmB;
     {
@@ -525,7 +579,7 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cin) * 2, static_cast<cuuint64_t>(F) * Cin * 2,
                                        static_cast<cuuint64_t>(T) * F * Cin * 2};
         const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(box_t),
-                                   static_cast<cuuint32_t>(pl.BB)};
+                                   static_cast<cuuint32_t>(box_b)};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -540,13 +594,16 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     p.n_ft = F / pl.BF; p.n_tt = (T + pl.BT - 1) / pl.BT; p.n_bt = (B + pl.BB - 1) / pl.BB; p.n_mt = cout_pad / kConvTileM;
     p.kchunks = Cin / kConvKC;
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
-    p.reuse = reuse; p.tgap = reuse ? 2 : 0;
-    p.b_bytes = static_cast<uint32_t>(pl.BB) * box_t * pl.BF * 128u;
+    p.reuse = reuse;
+    p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
+    p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;
+    p.b_bytes = static_cast<uint32_t>(box_b) * box_t * pl.BF * 128u;
     const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512;     // staging + alignment slack + barriers
     const uint32_t kAvail = 227u * 1024u - kFixed;
     if (reuse) {
         // ring 1 = activation patches (+ the rows a 16-padded, 2-frame-shifted MMA view may touch), ring 2 = weight tiles
-        p.stage_bytes = ((static_cast<uint32_t>(pl.Npad) + 2u * pl.BF) * 128u + 1023u) & ~1023u;
+        const uint32_t view_rows = pair ? static_cast<uint32_t>(pl.Npad) / 2u : static_cast<uint32_t>(pl.Npad);   // rows one CTA's MMA view spans
+        p.stage_bytes = ((view_rows + 2u * pl.BF) * 128u + 1023u) & ~1023u;
         if (p.stage_bytes < p.b_bytes) p.stage_bytes = (p.b_bytes + 1023u) & ~1023u;
         int sb = 3;
         int sa = (static_cast<int>(kAvail) - sb * static_cast<int>(p.stage_bytes)) / static_cast<int>(kConvABytes);
@@ -566,18 +623,37 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     while (cols < 2u * pl.Npad) cols <<= 1;
     p.tmem_cols = cols;
     if (getenv("DASV_CONV_DEBUG"))
-        fprintf(stderr, "conv plan: B=%d T=%d F=%d Cin=%d Cout=%d pool=%d reuse=%d BF=%d BT=%d BB=%d N=%d Npad=%d stages=%d sa=%d stage_bytes=%u b_bytes=%u\n",
-                B, T, F, Cin, Cout, (int)pool, reuse, pl.BF, pl.BT, pl.BB, pl.N, pl.Npad, p.stages, p.sa, p.stage_bytes, p.b_bytes);
-    const long long n_tiles = static_cast<long long>(p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
+        fprintf(stderr, "conv plan: B=%d T=%d F=%d Cin=%d Cout=%d pool=%d reuse=%d pair=%d BF=%d BT=%d BB=%d N=%d Npad=%d stages=%d sa=%d stage_bytes=%u b_bytes=%u\n",
+                B, T, F, Cin, Cout, (int)pool, reuse, pair, pl.BF, pl.BT, pl.BB, pl.N, pl.Npad, p.stages, p.sa, p.stage_bytes, p.b_bytes);
+    const long long n_tiles = static_cast<long long>(pair ? p.n_mt / 2 : p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
     if (n_tiles > 0x7fffffffLL) { set_error("conv3x3_igemm_bf16: too many tiles"); return 1; }
 
     const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + static_cast<size_t>(p.sa) * kConvABytes + kFixed;
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = static_cast<int>(n_tiles < sms ? n_tiles : sms);
-    conv3x3_igemm_kernel<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+    if (pair) {
+        auto kern = conv3x3_igemm_kernel<true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
+        const int clusters = static_cast<int>(n_tiles < sms / 2 ? n_tiles : sms / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
+        cfg.blockDim = dim3(kConvThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+        if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: pair launch failed: %s", cudaGetErrorString(e)); return 1; }
+    } else {
+        auto kern = conv3x3_igemm_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
+        const int grid = static_cast<int>(n_tiles < sms ? n_tiles : sms);
+        kern<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+    }
     return check_launch("conv3x3_igemm_bf16");
 }

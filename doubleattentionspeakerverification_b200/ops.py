@@ -7,7 +7,7 @@ import torch
 from . import _lib
 
 F32, BF16 = 0, 1
-CONV_RELU, CONV_POOL, CONV_REF_LAYOUT = 1, 2, 4
+CONV_RELU, CONV_POOL, CONV_REF_LAYOUT, CONV_PAIR = 1, 2, 4, 8
 
 
 def _dev(t, name):
@@ -196,14 +196,14 @@ def maxpool2x2(x, ref_layout=False, out_dtype=None):
     return y
 
 
-def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16):
+def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False):
     """bf16 tcgen05 implicit-GEMM conv3x3 + bias + ReLU (+ fused 2x2 ceil max-pool) on NHWC bf16."""
     _dev(x, 'x')
     if x.dtype != torch.bfloat16:
         raise _lib.DasvError('conv3x3_igemm_bf16: x must be bfloat16')
     x = x.contiguous()
     B, T, Fq, Cin = x.shape
-    flags = CONV_RELU | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0)
+    flags = CONV_RELU | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0) | (CONV_PAIR if pair else 0)
     with torch.cuda.device(x.device):
         lengths = _lengths(lengths, B, x.device)
         if pool:

@@ -32,6 +32,7 @@ extern "C" {
 #define DASV_CONV_RELU 1        /* apply ReLU after bias (always set by the VGG blocks)            */
 #define DASV_CONV_POOL 2        /* fuse max_pool2d(2, stride 2, ceil_mode) into the epilogue         */
 #define DASV_CONV_REF_LAYOUT 4  /* with POOL: write [B,T',C*F'] with feature = c*F'+f (CNNs.py:88-89) */
+#define DASV_CONV_PAIR 8        /* run on CTA pairs (tcgen05 cta_group::2, 256 channels x N pixels per pair); same results */
 
 int dasv_abi_version(void);
 const char* dasv_last_error(void);

@@ -62,8 +62,23 @@ CASES = [  # B, T, F, Cin, Cout, pool, ref, with_lengths
 ]
 
 
+PAIR_CASES = [  # Cout multiple of 256: eligible for CTA pairs (cta_group::2)
+    (3, 13, 20, 128, 256, False, False, True),
+    (3, 12, 20, 256, 256, True, False, False),
+    (4, 50, 10, 64, 256, True, True, False),
+    (5, 7, 10, 128, 512, True, True, True),
+    (2, 30, 40, 64, 256, True, False, True),
+    (7, 9, 10, 64, 256, False, False, True),
+]
+
+
+@pytest.mark.parametrize('B,T,F,Cin,Cout,pool,ref,with_len', PAIR_CASES)
+def test_igemm_cta_pairs_vs_oracle(B, T, F, Cin, Cout, pool, ref, with_len):
+    test_igemm_vs_oracle(B, T, F, Cin, Cout, pool, ref, with_len, pair=True)
+
+
 @pytest.mark.parametrize('B,T,F,Cin,Cout,pool,ref,with_len', CASES)
-def test_igemm_vs_oracle(B, T, F, Cin, Cout, pool, ref, with_len):
+def test_igemm_vs_oracle(B, T, F, Cin, Cout, pool, ref, with_len, pair=False):
     rs = np.random.RandomState(B * 100 + T + Cin)
     x = bf16_round(np.maximum(rs.standard_normal((B, T, F, Cin)), 0).astype(np.float32))
     w = bf16_round((rs.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32))
@@ -81,7 +96,7 @@ def test_igemm_vs_oracle(B, T, F, Cin, Cout, pool, ref, with_len):
             ref_y = ref_y.transpose(0, 1, 3, 2).reshape(Bq, T2, C * F2)
     y = ops.conv3x3_igemm_bf16(dev(x, torch.bfloat16), ops.pack_conv_weight_bf16(dev(w)), dev(bias), Cout,
                                lengths=None if lengths is None else dev(lengths), pool=pool, ref_layout=ref,
-                               out_dtype=torch.float32)
+                               out_dtype=torch.float32, pair=pair)
     assert tuple(y.shape) == ref_y.shape
     # inputs are bf16-exact and accumulation is fp32: only the summation order and, for the NHWC
     # bf16 outputs, the final rounding to bf16 (2^-9 relative) differ from the oracle
