@@ -66,11 +66,7 @@ struct DmhaFwdParams {
     int B, T, D, H, dh;
     int fps, stages, S;
     float scale_log2;   // log2(e) / sqrt(H): scores are kept in log2 units for ex2.approx
-    // stream-split mode (dmha_fwd2.cu): per-(CTA, utterance) partial states and per-utterance tickets
-    float* ws_part;
-    int* ws_cnt;
-    int split;
-    long long Q;        // frames of the flattened (utterance, frame) stream owned by one CTA
+    int* ws_cnt;        // dmha_fwd2.cu: utterance counter for the dynamic deal (NULL = static round-robin)
 };
 
 struct DmhaFwdSmem {

@@ -370,7 +370,7 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
     p.lengths = lengths; p.query = query; p.att = att; p.keep = keep;
     p.out = out; p.ctx = ctx; p.lse = lse; p.headw = headw; p.align = align;
     p.B = B; p.T = T; p.D = D; p.H = H; p.dh = H > 0 ? D / H : 0;
-    p.ws_part = nullptr; p.ws_cnt = nullptr; p.split = 0; p.Q = 0;
+    p.ws_cnt = nullptr;
     p.scale_log2 = kLog2e / sqrtf(static_cast<float>(H));     // d_k = query.size(-1) = H (poolings.py:75)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool bf16 = x_dtype == 1;

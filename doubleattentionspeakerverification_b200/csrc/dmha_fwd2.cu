@@ -7,13 +7,16 @@
 //     vectors (16-24 elements) of a (frame, head) row, G = 2..32 lanes per row, so a row costs log2(G) shuffles; the
 //     running sums are rescaled lazily (only when the running max grows by > 2^kLazy); the multiply-adds are packed
 //     fma.rn.f32x2 (sm_100), two elements per instruction.
-//   * whole utterances per CTA quantise badly (512 utterances on 148 SMs = 3.46 per SM -> 4 vs 3).  An optional
-//     stream-split schedule (DASV_DMHA_SPLIT=1) cuts the flattened (utterance, frame) stream into equal per-CTA
-//     ranges: a CTA that holds only part of an utterance writes its partial (max, sum, weighted sum) state to a
-//     workspace and takes a ticket, the last arrival merges the parts and runs the attention over heads.  Measured
-//     slower than the whole-utterance schedule (the per-segment finish outweighs the tail), so it is off by default.
 //   * Row groups of one LDS.128 phase start at different vectors (rot) so that rows whose byte size is a multiple
 //     of 128 do not collide on the same banks.
+//   * Utterances are handed out DYNAMICALLY: the producer thread of a CTA takes the next utterance from an atomic
+//     counter (in the caller's workspace) whenever it is ready to stream a new one and tells the consumers through a
+//     per-stage descriptor (utterance, first frame, frame count, last-stage flag) written before the stage's mbarrier
+//     is armed.  With ragged lengths this removes the makespan penalty of a static round-robin deal (a CTA that drew
+//     two long utterances no longer decides the kernel time).  Without a workspace the deal is static.
+//   * Tried and dropped: cutting the flattened (utterance, frame) stream into equal per-CTA ranges with partial
+//     states + tickets in the workspace (bit-exact, but the per-segment finish -- partial write, fence, ticket, merge,
+//     ~3-4 us -- cost more than the 13 % tail it removed: fp32 83.8 us vs 76.1 us at B=512,T=200,D=1024,H=16).
 #include "dmha_common.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -50,7 +53,7 @@ DASV_DEVICE void load_row_pairs(const unsigned char* p, uint64_t (&x2)[VE / 2]) 
 }
 
 struct Dmha2Smem {
-    uint32_t ring, q, a, pacc, pm, pl, u, w, misc, bars, total;
+    uint32_t ring, q, a, pacc, pm, pl, u, w, meta, bars, total;
 };
 __host__ __device__ inline Dmha2Smem dmha2_smem(int D, int H, int dh, int S, int stages, uint32_t stage_bytes) {
     Dmha2Smem s;
@@ -63,33 +66,17 @@ __host__ __device__ inline Dmha2Smem dmha2_smem(int D, int H, int dh, int S, int
     s.pl = o;   o += H * S * 4;
     s.u = o;    o += H * 4;
     s.w = o;    o += H * 4;
-    s.misc = o; o += 16;
-    o = (o + 7u) & ~7u;
+    o = (o + 15u) & ~15u;
+    s.meta = o; o += stages * 16;
     s.bars = o; o += 2 * stages * 8;
     s.total = o;
     return s;
 }
 
-// The (utterance, frame range) segments a CTA owns.  split = 1: a contiguous range of the flattened stream;
-// split = 0: whole utterances, grid-strided.  Producer and consumers walk the same sequence.
-struct Dmha2Segments {
-    long long g0, g1;
-    int b, T, B, stride, split;
-    DASV_DEVICE Dmha2Segments(const DmhaFwdParams& p) {
-        T = p.T; B = p.B; split = p.split; stride = gridDim.x;
-        if (split) {
-            const long long total = static_cast<long long>(p.B) * p.T;
-            g0 = static_cast<long long>(blockIdx.x) * p.Q;
-            g1 = g0 + p.Q < total ? g0 + p.Q : total;
-            b = static_cast<int>(g0 / p.T);
-        } else {
-            g0 = 0; g1 = 0; b = blockIdx.x;
-        }
-    }
-    DASV_DEVICE bool valid() const { return split ? (static_cast<long long>(b) * T < g1) : (b < B); }
-    DASV_DEVICE int t_begin() const { return split ? static_cast<int>(max(g0 - static_cast<long long>(b) * T, 0LL)) : 0; }
-    DASV_DEVICE int t_end() const { return split ? static_cast<int>(min(g1 - static_cast<long long>(b) * T, static_cast<long long>(T))) : T; }
-    DASV_DEVICE void next() { b += split ? 1 : stride; }
+// What a ring stage holds: frames [t0, t0 + nf) of utterance b; `last` marks the utterance's final stage.  b < 0 ends
+// the CTA's work.  Written by the producer before it arms the stage's barrier, read by the consumers after their wait.
+struct __align__(16) Dmha2Stage {
+    int b, t0, nf, last;
 };
 
 template <bool BF16, int NV>
@@ -116,7 +103,7 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
     float* pl = reinterpret_cast<float*>(smem + L.pl);          // [H*S] running sum
     float* u_sm = reinterpret_cast<float*>(smem + L.u);         // [H] head scores
     float* w_sm = reinterpret_cast<float*>(smem + L.w);         // [H] head weights
-    int* ticket_sm = reinterpret_cast<int*>(smem + L.misc);
+    Dmha2Stage* meta = reinterpret_cast<Dmha2Stage*>(smem + L.meta);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bars);
     uint64_t* empty = full + p.stages;
 
@@ -136,19 +123,31 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
         if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
             int st = 0;
             uint32_t ph = 0;
-            for (Dmha2Segments sg(p); sg.valid(); sg.next()) {
-                int Lb = p.lengths ? p.lengths[sg.b] : T;
+            int b = p.ws_cnt ? atomicAdd(p.ws_cnt, 1) : static_cast<int>(blockIdx.x);
+            while (b < p.B) {
+                int Lb = p.lengths ? p.lengths[b] : T;
                 Lb = max(0, min(Lb, T));
-                const int tb = sg.t_begin(), nfr = min(sg.t_end(), Lb) - tb;
-                const unsigned char* xb = p.x + (static_cast<size_t>(sg.b) * T + tb) * frame_bytes;
-                for (int f0 = 0; f0 < nfr; f0 += p.fps) {
+                const unsigned char* xb = p.x + static_cast<size_t>(b) * T * frame_bytes;
+                int f0 = 0;
+                do {                                // an empty utterance still gets one (empty) stage so that it is finished
+                    const int nf = min(p.fps, Lb - f0);
                     mbar_wait(&empty[st], ph ^ 1u);
-                    const uint32_t bytes = static_cast<uint32_t>(min(p.fps, nfr - f0)) * frame_bytes;
-                    mbar_arrive_expect_tx(&full[st], bytes);
-                    bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
+                    meta[st] = Dmha2Stage{b, f0, nf, f0 + p.fps >= Lb ? 1 : 0};
+                    if (nf > 0) {
+                        const uint32_t bytes = static_cast<uint32_t>(nf) * frame_bytes;
+                        mbar_arrive_expect_tx(&full[st], bytes);
+                        bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
+                    } else {
+                        mbar_arrive(&full[st]);
+                    }
                     if (++st == p.stages) { st = 0; ph ^= 1u; }
-                }
+                    f0 += p.fps;
+                } while (f0 < Lb);
+                b = p.ws_cnt ? atomicAdd(p.ws_cnt, 1) : b + static_cast<int>(gridDim.x);
             }
+            mbar_wait(&empty[st], ph ^ 1u);         // terminator stage
+            meta[st] = Dmha2Stage{-1, 0, 0, 0};
+            mbar_arrive(&full[st]);
         }
         return;
     }
@@ -179,96 +178,94 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
             q2[v][e] = vok[v] ? pack_f32x2(q_sm[head * dh + idx * VE + 2 * e], q_sm[head * dh + idx * VE + 2 * e + 1])
                               : pack_f32x2(0.f, 0.f);
     }
-    const long long total = static_cast<long long>(p.B) * T;
 
     int st = 0;
     uint32_t ph = 0;
-    for (Dmha2Segments sg(p); sg.valid(); sg.next()) {
-        const int b = sg.b;
+    float m = -INFINITY, l = 0.f;
+    uint64_t acc2[NV][VP];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int e = 0; e < VP; ++e) acc2[v][e] = pack_f32x2(0.f, 0.f);
+
+    while (true) {
+        mbar_wait(&full[st], ph);
+        const Dmha2Stage sg = meta[st];             // read before the stage is released
+        if (sg.b < 0) break;
+        const int b = sg.b, nf = sg.nf;
+        const unsigned char* sbase = ring + st * stage_bytes;
+        // FB rows per trip: rows fb+slot and fb+S+slot are independent until the softmax update, which gives
+        // the LDS -> FMA -> shuffle -> exp2 chain a second row to overlap with.
+        for (int fb = 0; fb < nf; fb += FB * S) {               // warp-uniform trip count (fps is a multiple of S)
+            uint64_t xs[FB][NV][VP];
+            float sc[FB];
+            bool valid[FB];
+#pragma unroll
+            for (int r = 0; r < FB; ++r) {
+                const int f = fb + r * S + slot;
+                valid[r] = active && f < nf;
+                const unsigned char* row = sbase + static_cast<uint32_t>(valid[r] ? f : 0) * frame_bytes;   // safe address when idle
+                uint64_t s2a = pack_f32x2(0.f, 0.f), s2b = s2a;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    if (RAGGED && !vok[v]) {
+#pragma unroll
+                        for (int e = 0; e < VP; ++e) xs[r][v][e] = pack_f32x2(0.f, 0.f);
+                    } else {
+                        load_row_pairs<VE, BF16>(row + voff[v], xs[r][v]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < VP; e += 2) {
+                        s2a = fma_f32x2(xs[r][v][e], q2[v][e], s2a);
+                        s2b = fma_f32x2(xs[r][v][e + 1], q2[v][e + 1], s2b);
+                    }
+                }
+                float a0, a1, b0, b1;
+                unpack_f32x2(s2a, a0, a1);
+                unpack_f32x2(s2b, b0, b1);
+                sc[r] = (a0 + a1) + (b0 + b1);
+            }
+#pragma unroll
+            for (int r = 0; r < FB; ++r) sc[r] = group_sum<G>(sc[r]);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < FB; ++r) {
+                sc[r] = valid[r] ? sc[r] * p.scale_log2 : -INFINITY;     // log2-unit score of this (frame, head)
+                mx = fmaxf(mx, sc[r]);
+                if (p.align != nullptr && valid[r] && lig == 0)
+                    p.align[(static_cast<size_t>(b) * T + sg.t0 + fb + r * S + slot) * H + head] = sc[r];   // raw score, normalised at the end
+            }
+            if (mx > m + kDmhaLazy) {                            // lazy rescale; first frame: m = -inf -> corr = 0
+                const float corr = fast_exp2(m - mx);
+                const uint64_t corr2 = pack_f32x2(corr, corr);
+                l *= corr;
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+#pragma unroll
+                    for (int e = 0; e < VP; ++e) acc2[v][e] = mul_f32x2(acc2[v][e], corr2);
+                m = mx;
+            }
+            const float mref = (m == -INFINITY) ? 0.f : m;      // idle group: exp2(-inf - 0) = 0
+#pragma unroll
+            for (int r = 0; r < FB; ++r) {
+                const float pr = fast_exp2(sc[r] - mref);
+                const uint64_t pr2 = pack_f32x2(pr, pr);
+                l += pr;
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+#pragma unroll
+                    for (int e = 0; e < VP; ++e) acc2[v][e] = fma_f32x2(pr2, xs[r][v][e], acc2[v][e]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
+        if (!sg.last) continue;
+
+        // ============================================================ end of utterance b
         int Lb = p.lengths ? p.lengths[b] : T;
         Lb = max(0, min(Lb, T));
-        const int tb = sg.t_begin(), nfr = min(sg.t_end(), Lb) - tb;
-
-        float m = -INFINITY, l = 0.f;
-        uint64_t acc2[NV][VP];
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int e = 0; e < VP; ++e) acc2[v][e] = pack_f32x2(0.f, 0.f);
-
-        for (int f0 = 0; f0 < nfr; f0 += p.fps) {
-            mbar_wait(&full[st], ph);
-            const int nf = min(p.fps, nfr - f0);
-            const unsigned char* sbase = ring + st * stage_bytes;
-            // FB rows per trip: rows fb+slot and fb+S+slot are independent until the softmax update, which gives
-            // the LDS -> FMA -> shuffle -> exp2 chain a second row to overlap with.
-            for (int fb = 0; fb < nf; fb += FB * S) {            // warp-uniform trip count (fps is a multiple of S)
-                uint64_t xs[FB][NV][VP];
-                float sc[FB];
-                bool valid[FB];
-#pragma unroll
-                for (int r = 0; r < FB; ++r) {
-                    const int f = fb + r * S + slot;
-                    valid[r] = active && f < nf;
-                    const unsigned char* row = sbase + static_cast<uint32_t>(valid[r] ? f : 0) * frame_bytes;   // safe address when idle
-                    uint64_t s2a = pack_f32x2(0.f, 0.f), s2b = s2a;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        if (RAGGED && !vok[v]) {
-#pragma unroll
-                            for (int e = 0; e < VP; ++e) xs[r][v][e] = pack_f32x2(0.f, 0.f);
-                        } else {
-                            load_row_pairs<VE, BF16>(row + voff[v], xs[r][v]);
-                        }
-#pragma unroll
-                        for (int e = 0; e < VP; e += 2) {
-                            s2a = fma_f32x2(xs[r][v][e], q2[v][e], s2a);
-                            s2b = fma_f32x2(xs[r][v][e + 1], q2[v][e + 1], s2b);
-                        }
-                    }
-                    float a0, a1, b0, b1;
-                    unpack_f32x2(s2a, a0, a1);
-                    unpack_f32x2(s2b, b0, b1);
-                    sc[r] = (a0 + a1) + (b0 + b1);
-                }
-#pragma unroll
-                for (int r = 0; r < FB; ++r) sc[r] = group_sum<G>(sc[r]);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int r = 0; r < FB; ++r) {
-                    sc[r] = valid[r] ? sc[r] * p.scale_log2 : -INFINITY;     // log2-unit score of this (frame, head)
-                    mx = fmaxf(mx, sc[r]);
-                    if (p.align != nullptr && valid[r] && lig == 0)
-                        p.align[(static_cast<size_t>(b) * T + tb + f0 + fb + r * S + slot) * H + head] = sc[r];   // raw score, normalised at the end
-                }
-                if (mx > m + kDmhaLazy) {                        // lazy rescale; first frame: m = -inf -> corr = 0
-                    const float corr = fast_exp2(m - mx);
-                    const uint64_t corr2 = pack_f32x2(corr, corr);
-                    l *= corr;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v)
-#pragma unroll
-                        for (int e = 0; e < VP; ++e) acc2[v][e] = mul_f32x2(acc2[v][e], corr2);
-                    m = mx;
-                }
-                const float mref = (m == -INFINITY) ? 0.f : m;  // idle group: exp2(-inf - 0) = 0
-#pragma unroll
-                for (int r = 0; r < FB; ++r) {
-                    const float pr = fast_exp2(sc[r] - mref);
-                    const uint64_t pr2 = pack_f32x2(pr, pr);
-                    l += pr;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v)
-#pragma unroll
-                        for (int e = 0; e < VP; ++e) acc2[v][e] = fma_f32x2(pr2, xs[r][v][e], acc2[v][e]);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
-            if (++st == p.stages) { st = 0; ph ^= 1u; }
-        }
-
-        // ------------------------------------------------------------ step 1: merge this CTA's S frame slots per head
+        // ------------------------------------------------------------ merge the S frame slots per head
         if (active) {
             const int sl = head * S + slot;
             if (lig == 0) { pm[sl] = m; pl[sl] = l; }
@@ -285,78 +282,24 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
                     }
                 }
         }
+        m = -INFINITY; l = 0.f;                                  // state for the next utterance
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int e = 0; e < VP; ++e) acc2[v][e] = pack_f32x2(0.f, 0.f);
         named_bar_sync(1, kDmhaConsumerThreads);
-        for (int h = warp; h < H; h += kDmhaConsumerWarps) {    // -> slot 0: (M, sum, weighted sum), not yet normalised
+        for (int h = warp; h < H; h += kDmhaConsumerWarps) {
             float M = -INFINITY;
             for (int s = 0; s < S; ++s) M = fmaxf(M, pm[h * S + s]);
             const float Mref = (M == -INFINITY) ? 0.f : M;
             float Lsum = 0.f;
             for (int s = 0; s < S; ++s) Lsum += pl[h * S + s] * fast_exp2(pm[h * S + s] - Mref);
-            for (int d = lane; d < dh; d += 32) {
-                float c = 0.f;
-                for (int s = 0; s < S; ++s) c = fmaf(pacc[(h * S + s) * dh + d], fast_exp2(pm[h * S + s] - Mref), c);
-                pacc[(h * S) * dh + d] = c;
-            }
-            __syncwarp();
-            if (lane == 0) { pm[h * S] = M; pl[h * S] = Lsum; }
-        }
-        named_bar_sync(1, kDmhaConsumerThreads);
-
-        // ------------------------------------------------------------ utterance split over several CTAs: exchange partials
-        if (p.split) {
-            const long long ub = static_cast<long long>(b) * T;
-            const long long ue = (ub + T < total ? ub + T : total) - 1;
-            const int first_cta = static_cast<int>(ub / p.Q);
-            const int n_parts = static_cast<int>(ue / p.Q) - first_cta + 1;
-            if (n_parts > 1) {
-                const size_t rec_floats = static_cast<size_t>(D) + 2 * H;
-                float* rec = p.ws_part + (static_cast<size_t>(blockIdx.x) + b) * rec_floats;   // (CTA, utterance) pairs have unique c + b
-                for (int i = tid; i < D; i += kDmhaConsumerThreads) {
-                    const int h = i / dh, d = i - h * dh;
-                    rec[i] = pacc[(h * S) * dh + d];
-                }
-                for (int h = tid; h < H; h += kDmhaConsumerThreads) { rec[D + h] = pm[h * S]; rec[D + H + h] = pl[h * S]; }
-                __threadfence();
-                named_bar_sync(1, kDmhaConsumerThreads);
-                if (tid == 0) *ticket_sm = atomicAdd(&p.ws_cnt[b], 1);
-                named_bar_sync(1, kDmhaConsumerThreads);
-                const bool last = (*ticket_sm == n_parts - 1);
-                named_bar_sync(1, kDmhaConsumerThreads);        // ticket_sm may be rewritten by the next segment
-                if (!last) continue;                             // another CTA finishes this utterance
-                __threadfence();
-                if (tid == 0) p.ws_cnt[b] = 0;                   // self-cleaning for the next launch
-                for (int h = warp; h < H; h += kDmhaConsumerWarps) {
-                    float M = -INFINITY;
-                    for (int k = 0; k < n_parts; ++k)
-                        M = fmaxf(M, __ldcg(p.ws_part + (static_cast<size_t>(first_cta + k) + b) * rec_floats + D + h));
-                    const float Mref = (M == -INFINITY) ? 0.f : M;
-                    float Lsum = 0.f;
-                    for (int k = 0; k < n_parts; ++k) {
-                        const float* rk = p.ws_part + (static_cast<size_t>(first_cta + k) + b) * rec_floats;
-                        Lsum += __ldcg(rk + D + H + h) * fast_exp2(__ldcg(rk + D + h) - Mref);
-                    }
-                    for (int d = lane; d < dh; d += 32) {
-                        float c = 0.f;
-                        for (int k = 0; k < n_parts; ++k) {
-                            const float* rk = p.ws_part + (static_cast<size_t>(first_cta + k) + b) * rec_floats;
-                            c = fmaf(__ldcg(rk + h * dh + d), fast_exp2(__ldcg(rk + D + h) - Mref), c);
-                        }
-                        pacc[(h * S) * dh + d] = c;
-                    }
-                    __syncwarp();
-                    if (lane == 0) { pm[h * S] = M; pl[h * S] = Lsum; }
-                }
-                named_bar_sync(1, kDmhaConsumerThreads);
-            }
-        }
-
-        // ------------------------------------------------------------ step 2: normalise, attention over heads, outputs
-        for (int h = warp; h < H; h += kDmhaConsumerWarps) {
-            const float M = pm[h * S], Lsum = pl[h * S];
             const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;
             float dot = 0.f;
             for (int d = lane; d < dh; d += 32) {
-                const float c = pacc[(h * S) * dh + d] * inv;
+                float c = 0.f;
+                for (int s = 0; s < S; ++s) c = fmaf(pacc[(h * S + s) * dh + d], fast_exp2(pm[h * S + s] - Mref), c);
+                c *= inv;
                 pacc[(h * S) * dh + d] = c;                    // ctx[b,h,d], kept in smem for the head stage
                 if (p.ctx != nullptr) p.ctx[(static_cast<size_t>(b) * H + h) * dh + d] = c;
                 if (p.att != nullptr) dot = fmaf(c, a_sm[d], dot);
@@ -405,15 +348,14 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
             }
         }
         if (p.align != nullptr) {
-            // alignment = softmax over time (poolings.py:77): exp2(raw - lse); frames >= L are 0.  Raw scores of
-            // other CTAs' parts were published before their ticket (threadfence), read them past L1.
+            // alignment = softmax over time (poolings.py:77): exp2(raw - lse); frames >= L are 0
             float* ab = p.align + static_cast<size_t>(b) * T * H;
             for (int i = tid; i < T * H; i += kDmhaConsumerThreads) {
                 const int t = i / H, h = i - t * H;
-                ab[i] = (t < Lb) ? fast_exp2(__ldcg(ab + i) - pm[h * S]) : 0.f;
+                ab[i] = (t < Lb) ? fast_exp2(ab[i] - pm[h * S]) : 0.f;
             }
         }
-        named_bar_sync(1, kDmhaConsumerThreads);   // pacc/pm/u/w are reused by the next segment
+        named_bar_sync(1, kDmhaConsumerThreads);   // pacc/pm/u/w are reused by the next utterance
     }
 }
 
@@ -461,28 +403,13 @@ static int launch_fwd2_kernel(Kern kern, DmhaFwdParams& p, size_t smem, void* wo
     if (occ < 1) { set_error("dmha_fwd: kernel does not fit on an SM (smem %zu B)", smem); return 1; }
     int grid = sms * occ;
     if (grid > kDmha2MaxGrid) grid = kDmha2MaxGrid;
-    const long long total = static_cast<long long>(p.B) * p.T;
-    // Stream-split scheduling is implemented and parity-tested but OFF by default: on B200 the extra per-segment
-    // finish (partial write, fence, ticket, merge: ~3-4 us) costs more than the 13 % of tail it removes
-    // (B=512,T=200,D=1024: fp32 83.8 us split vs 76.1 us whole-utterance; bf16 62.2 vs 51.1).  DASV_DMHA_SPLIT=1 enables it.
-    const char* split_env = getenv("DASV_DMHA_SPLIT");
-    const bool want_split = workspace != nullptr && split_env != nullptr && atoi(split_env) != 0;
-    if (want_split && total > 0) {
-        // equal ranges of the flattened (utterance, frame) stream, at least 4 trips of work per CTA
-        long long q = (total + grid - 1) / grid;
-        const long long qmin = 8LL * p.S;
-        if (q < qmin) q = qmin;
-        q = (q + p.S - 1) / p.S * p.S;
-        grid = static_cast<int>((total + q - 1) / q);
-        p.split = 1; p.Q = q;
+    if (grid > p.B) grid = p.B;
+    p.ws_cnt = nullptr;
+    if (workspace != nullptr && !getenv("DASV_DMHA_STATIC")) {
+        // dynamic deal: the first `grid` utterances are claimed through the same counter, so it starts at zero
         p.ws_cnt = static_cast<int*>(workspace);
-        const size_t cnt_bytes = (static_cast<size_t>(p.B) * sizeof(int) + 255) & ~static_cast<size_t>(255);
-        p.ws_part = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + cnt_bytes);
-        e = cudaMemsetAsync(p.ws_cnt, 0, cnt_bytes, stream);
+        e = cudaMemsetAsync(p.ws_cnt, 0, sizeof(int), stream);
         if (e != cudaSuccess) { set_error("dmha_fwd: workspace memset: %s", cudaGetErrorString(e)); return 1; }
-    } else {
-        p.split = 0; p.Q = 0;
-        if (grid > p.B) grid = p.B;
     }
     kern<<<grid, kDmhaThreads, smem, stream>>>(p);
     return check_launch("dmha_fwd");
@@ -506,9 +433,8 @@ static int dispatch_fwd2(const DmhaPlan2& pl, DmhaFwdParams& p, size_t smem, voi
 }
 
 size_t dmha_fwd2_workspace_bytes(int B, int D, int H) {
-    if (B <= 0 || D <= 0 || H <= 0) return 0;
-    const size_t cnt_bytes = (static_cast<size_t>(B) * sizeof(int) + 255) & ~static_cast<size_t>(255);
-    return cnt_bytes + (static_cast<size_t>(kDmha2MaxGrid) + B) * (static_cast<size_t>(D) + 2 * H) * sizeof(float);
+    (void)D; (void)H;
+    return B > 0 ? 256 : 0;          // the utterance counter (padded)
 }
 
 int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream) {
