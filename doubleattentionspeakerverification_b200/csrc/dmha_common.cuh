@@ -66,8 +66,21 @@ struct DmhaFwdParams {
     int B, T, D, H, dh;
     int fps, stages, S;
     float scale_log2;   // log2(e) / sqrt(H): scores are kept in log2 units for ex2.approx
+    int pitch3, rowcopy3; // dmha_fwd3.cu: smem row pitch (bytes), 1 = one bulk copy per frame
     int* ws_cnt;        // dmha_fwd2.cu: utterance counter for the dynamic deal (NULL = static round-robin)
 };
+
+// The dynamic deal's workspace: [0] next utterance, [1] CTAs that have left.  The caller provides it zeroed; the last CTA
+// to leave (every CTA has taken its last ticket by then) zeroes it again for the next launch on the same stream.
+DASV_DEVICE void dmha_release_counter(int* ws_cnt) {
+    if (ws_cnt == nullptr) return;
+    __threadfence();
+    if (atomicAdd(ws_cnt + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+        ws_cnt[0] = 0;
+        ws_cnt[1] = 0;
+        __threadfence();
+    }
+}
 
 struct DmhaFwdSmem {
     uint32_t ring, q, a, pacc, pm, pl, u, w, bars, total;
@@ -94,6 +107,8 @@ __host__ __device__ inline DmhaFwdSmem dmha_fwd_smem(int D, int H, int dh, int S
 // v2 forward (dmha_fwd2.cu): returns 0 = launched, 1 = error (message set), -1 = shape outside its mapping.
 int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream);
 size_t dmha_fwd2_workspace_bytes(int B, int D, int H);
+// v3 forward for bf16 features (dmha_fwd3.cu, warp-level MMA); same return convention and workspace.
+int dmha_fwd3_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream);
 
 struct DmhaBwdParams {
     const unsigned char* x;

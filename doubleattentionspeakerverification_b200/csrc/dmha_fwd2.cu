@@ -18,6 +18,7 @@
 //     states + tickets in the workspace (bit-exact, but the per-segment finish -- partial write, fence, ticket, merge,
 //     ~3-4 us -- cost more than the 13 % tail it removed: fp32 83.8 us vs 76.1 us at B=512,T=200,D=1024,H=16).
 #include "dmha_common.cuh"
+#include "dmha_finish.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -61,11 +62,11 @@ __host__ __device__ inline Dmha2Smem dmha2_smem(int D, int H, int dh, int S, int
     s.ring = o; o += stages * stage_bytes;
     s.q = o;    o += D * 4;
     s.a = o;    o += dh * 4;
-    s.pacc = o; o += S * D * 4;
-    s.pm = o;   o += H * S * 4;
-    s.pl = o;   o += H * S * 4;
-    s.u = o;    o += H * 4;
-    s.w = o;    o += H * 4;
+    s.pacc = o; o += 2 * S * D * 4;                  // scratch is double-buffered by utterance parity
+    s.pm = o;   o += 2 * H * S * 4;
+    s.pl = o;   o += 2 * H * S * 4;
+    s.u = o;    o += 2 * H * 4;
+    s.w = o;    o += 2 * H * 4;
     o = (o + 15u) & ~15u;
     s.meta = o; o += stages * 16;
     s.bars = o; o += 2 * stages * 8;
@@ -73,10 +74,10 @@ __host__ __device__ inline Dmha2Smem dmha2_smem(int D, int H, int dh, int S, int
     return s;
 }
 
-// What a ring stage holds: frames [t0, t0 + nf) of utterance b; `last` marks the utterance's final stage.  b < 0 ends
-// the CTA's work.  Written by the producer before it arms the stage's barrier, read by the consumers after their wait.
+// What a ring stage holds: frames [t0, t0 + nf) of utterance b, whose (clamped) length is Lb.  b < 0 ends the CTA's
+// work.  Written by the producer before it arms the stage's barrier, read by the consumers after their wait.
 struct __align__(16) Dmha2Stage {
-    int b, t0, nf, last;
+    int b, t0, nf, Lb;
 };
 
 template <bool BF16, int NV>
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
                 do {                                // an empty utterance still gets one (empty) stage so that it is finished
                     const int nf = min(p.fps, Lb - f0);
                     mbar_wait(&empty[st], ph ^ 1u);
-                    meta[st] = Dmha2Stage{b, f0, nf, f0 + p.fps >= Lb ? 1 : 0};
+                    meta[st] = Dmha2Stage{b, f0, nf, Lb};
                     if (nf > 0) {
                         const uint32_t bytes = static_cast<uint32_t>(nf) * frame_bytes;
                         mbar_arrive_expect_tx(&full[st], bytes);
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
             mbar_wait(&empty[st], ph ^ 1u);         // terminator stage
             meta[st] = Dmha2Stage{-1, 0, 0, 0};
             mbar_arrive(&full[st]);
+            dmha_release_counter(p.ws_cnt);
         }
         return;
     }
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
                               : pack_f32x2(0.f, 0.f);
     }
 
-    int st = 0;
+    int st = 0, par = 0;
     uint32_t ph = 0;
     float m = -INFINITY, l = 0.f;
     uint64_t acc2[NV][VP];
@@ -260,15 +262,16 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
         if (++st == p.stages) { st = 0; ph ^= 1u; }
-        if (!sg.last) continue;
+        if (sg.t0 + sg.nf < sg.Lb) continue;
 
         // ============================================================ end of utterance b
-        int Lb = p.lengths ? p.lengths[b] : T;
-        Lb = max(0, min(Lb, T));
+        float* pacc_b = pacc + par * (S * D);
+        float* pm_b = pm + par * (S * H);
+        float* pl_b = pl + par * (S * H);
         // ------------------------------------------------------------ merge the S frame slots per head
         if (active) {
             const int sl = head * S + slot;
-            if (lig == 0) { pm[sl] = m; pl[sl] = l; }
+            if (lig == 0) { pm_b[sl] = m; pl_b[sl] = l; }
 #pragma unroll
             for (int v = 0; v < NV; ++v)
                 if (vok[v]) {
@@ -277,8 +280,8 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
                     for (int e = 0; e < VP; ++e) {
                         float lo, hi;
                         unpack_f32x2(acc2[v][e], lo, hi);
-                        pacc[sl * dh + idx * VE + 2 * e] = lo;
-                        pacc[sl * dh + idx * VE + 2 * e + 1] = hi;
+                        pacc_b[sl * dh + idx * VE + 2 * e] = lo;
+                        pacc_b[sl * dh + idx * VE + 2 * e + 1] = hi;
                     }
                 }
         }
@@ -287,75 +290,8 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
         for (int v = 0; v < NV; ++v)
 #pragma unroll
             for (int e = 0; e < VP; ++e) acc2[v][e] = pack_f32x2(0.f, 0.f);
-        named_bar_sync(1, kDmhaConsumerThreads);
-        for (int h = warp; h < H; h += kDmhaConsumerWarps) {
-            float M = -INFINITY;
-            for (int s = 0; s < S; ++s) M = fmaxf(M, pm[h * S + s]);
-            const float Mref = (M == -INFINITY) ? 0.f : M;
-            float Lsum = 0.f;
-            for (int s = 0; s < S; ++s) Lsum += pl[h * S + s] * fast_exp2(pm[h * S + s] - Mref);
-            const float inv = Lsum > 0.f ? 1.f / Lsum : 0.f;
-            float dot = 0.f;
-            for (int d = lane; d < dh; d += 32) {
-                float c = 0.f;
-                for (int s = 0; s < S; ++s) c = fmaf(pacc[(h * S + s) * dh + d], fast_exp2(pm[h * S + s] - Mref), c);
-                c *= inv;
-                pacc[(h * S) * dh + d] = c;                    // ctx[b,h,d], kept in smem for the head stage
-                if (p.ctx != nullptr) p.ctx[(static_cast<size_t>(b) * H + h) * dh + d] = c;
-                if (p.att != nullptr) dot = fmaf(c, a_sm[d], dot);
-            }
-            dot = warp_sum(dot);
-            __syncwarp();
-            if (lane == 0) {
-                u_sm[h] = dot;                                  // poolings.py:47 (no scale)
-                const float lse2 = M + log2f(Lsum);             // log2 units; -inf for an empty utterance
-                pm[h * S] = lse2;
-                if (p.lse != nullptr) p.lse[static_cast<size_t>(b) * H + h] = lse2 * kLn2;
-            }
-        }
-        named_bar_sync(1, kDmhaConsumerThreads);
-        if (p.att != nullptr) {
-            if (warp == 0) {
-                // softmax over heads (poolings.py:50), with the training-mode keep mask (poolings.py:42)
-                float mx = -INFINITY;
-                for (int h = lane; h < H; h += 32) {
-                    const bool kept = p.keep == nullptr || p.keep[static_cast<size_t>(b) * H + h] != 0;
-                    const float u = kept ? u_sm[h] : -INFINITY;
-                    u_sm[h] = u;
-                    mx = fmaxf(mx, u);
-                }
-                mx = warp_max(mx);
-                float sum = 0.f;
-                for (int h = lane; h < H; h += 32) {
-                    const float e = expf(u_sm[h] - mx);        // all heads dropped -> NaN, as in the reference
-                    w_sm[h] = e;
-                    sum += e;
-                }
-                sum = warp_sum(sum);
-                for (int h = lane; h < H; h += 32) {
-                    const float w = w_sm[h] / sum;
-                    w_sm[h] = w;
-                    if (p.headw != nullptr) p.headw[static_cast<size_t>(b) * H + h] = w;
-                }
-            }
-            named_bar_sync(1, kDmhaConsumerThreads);
-            if (p.out != nullptr) {
-                for (int d = tid; d < dh; d += kDmhaConsumerThreads) {
-                    float o = 0.f;
-                    for (int h = 0; h < H; ++h) o = fmaf(w_sm[h], pacc[(h * S) * dh + d], o);   // poolings.py:68-69
-                    p.out[static_cast<size_t>(b) * dh + d] = o;
-                }
-            }
-        }
-        if (p.align != nullptr) {
-            // alignment = softmax over time (poolings.py:77): exp2(raw - lse); frames >= L are 0
-            float* ab = p.align + static_cast<size_t>(b) * T * H;
-            for (int i = tid; i < T * H; i += kDmhaConsumerThreads) {
-                const int t = i / H, h = i - t * H;
-                ab[i] = (t < Lb) ? fast_exp2(ab[i] - pm[h * S]) : 0.f;
-            }
-        }
-        named_bar_sync(1, kDmhaConsumerThreads);   // pacc/pm/u/w are reused by the next utterance
+        dmha_finish_utterance2<kDmhaConsumerWarps>(p, b, sg.Lb, S, pacc_b, pm_b, pl_b, u_sm + par * H, w_sm + par * H, a_sm, tid, warp, lane);
+        par ^= 1;
     }
 }
 
@@ -406,10 +342,9 @@ static int launch_fwd2_kernel(Kern kern, DmhaFwdParams& p, size_t smem, void* wo
     if (grid > p.B) grid = p.B;
     p.ws_cnt = nullptr;
     if (workspace != nullptr && !getenv("DASV_DMHA_STATIC")) {
-        // dynamic deal: the first `grid` utterances are claimed through the same counter, so it starts at zero
+        // dynamic deal: every utterance is claimed through the counter, which starts at zero (the caller zeroes the
+        // workspace once; the last CTA to leave puts it back to zero, see dmha_release_counter)
         p.ws_cnt = static_cast<int*>(workspace);
-        e = cudaMemsetAsync(p.ws_cnt, 0, sizeof(int), stream);
-        if (e != cudaSuccess) { set_error("dmha_fwd: workspace memset: %s", cudaGetErrorString(e)); return 1; }
     }
     kern<<<grid, kDmhaThreads, smem, stream>>>(p);
     return check_launch("dmha_fwd");

@@ -72,11 +72,27 @@ def dmha_fwd(x, query, att=None, lengths=None, keep=None, need_align=True, need_
         headw = torch.empty((B, H), **f) if att is not None else None
         align = torch.empty((B, T, H), **f) if need_align else None
         L = _lib.lib()
-        ws = torch.empty((max(int(L.dasv_dmha_fwd_workspace_bytes(B, T, D, H)), 4),), device=dev, dtype=torch.uint8)
+        ws = _zeroed_workspace(dev, max(int(L.dasv_dmha_fwd_workspace_bytes(B, T, D, H)), 4))
         rc = L.dasv_dmha_fwd(_p(x), _dtype_code(x, 'x'), _p(lengths), _p(query), _p(att_c), _p(keep_c),
                              _p(out), _p(ctx), _p(lse), _p(headw), _p(align), _p(ws), B, T, D, H, _stream())
+        if rc != 0:
+            _ws_cache.clear()                          # a failed launch may leave the counter dirty
         _lib.check(rc, 'dasv_dmha_fwd')
     return dict(out=out, ctx=ctx, lse=lse, headw=headw, align=align)
+
+
+_ws_cache = {}
+
+
+def _zeroed_workspace(dev, nbytes):
+    """Per (device, stream) workspace for dasv_dmha_fwd: zeroed once, the kernel hands it back zeroed
+    (include/dasv_b200.h), so calls on the same stream can share it without a memset per call."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros((max(nbytes, 256),), device=dev, dtype=torch.uint8)
+        _ws_cache[key] = ws
+    return ws
 
 
 def dmha_bwd(x, query, att, g_out, g_ctx, ctx, lse, headw, lengths=None):

@@ -49,9 +49,10 @@ const char* dasv_last_error(void);
  * no head stage, `out`/`headw` must then be NULL);  keep [B,H] uint8 nullable (training-mode
  * head drop-out mask, poolings.py:39-43, drawn by the caller);
  * out [B,dh], ctx [B,H,dh], lse [B,H], headw [B,H], align [B,T,H] : f32, each nullable.
- * workspace (nullable, dasv_dmha_fwd_workspace_bytes): lets the kernel cut the flattened (utterance, frame)
- * stream into equal per-CTA ranges (partial states + tickets live there); without it whole utterances are
- * dealt to CTAs, which quantises badly when B is a small multiple of the SM count.  No initialisation needed.
+ * workspace (nullable, dasv_dmha_fwd_workspace_bytes): the utterance counter of the dynamic deal (CTAs claim the
+ * next utterance when they are ready for one, so ragged lengths do not leave a CTA with two long utterances);
+ * without it utterances are dealt round-robin.  The caller ZEROES it once; every launch leaves it zeroed again,
+ * so one buffer can be reused by consecutive calls on the same stream (not by concurrent streams).
  */
 size_t dasv_dmha_fwd_workspace_bytes(int B, int T, int D, int H);
 int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
