@@ -278,3 +278,26 @@ def threshold_counts(scores, thresholds):
         rc = _lib.lib().dasv_threshold_counts(_p(scores) if scores.numel() else None, scores.numel(), _p(th), th.numel(), _p(out), _stream())
         _lib.check(rc, 'dasv_threshold_counts')
     return out
+
+
+# ------------------------------------------------------------------------------------ features
+def logmel(wave, n_samples, frames, Tmax, window, hop, melw, mel_range, preem, scale, cmn=True):
+    """Log mel-filterbank features (+ CMN) of a padded waveform batch (csrc/features.cu).  All tensors on the device:
+    wave [B,N] f32, n_samples/frames [B] i32, window [win_length] f32, melw [n_mels,257] f32, mel_range [n_mels,2] i32.
+    Returns [B,Tmax,n_mels] f32; rows t >= frames[b] are zero."""
+    _dev(wave, 'wave')
+    wave = wave.contiguous()
+    B, N = wave.shape
+    n_mels = melw.shape[0]
+    with torch.cuda.device(wave.device):
+        out = torch.zeros((B, Tmax, n_mels), device=wave.device, dtype=torch.float32)
+        if B == 0 or Tmax == 0:
+            return out
+        L = _lib.lib()
+        rc = L.dasv_logmel_f32(_p(wave), _p(n_samples), B, N, _p(window), window.numel(), hop, _p(melw), _p(mel_range), n_mels,
+                               preem, scale, _p(out), Tmax, _stream())
+        _lib.check(rc, 'dasv_logmel_f32')
+        if cmn:
+            rc = L.dasv_cmn_f32(_p(out), _p(frames), B, Tmax, n_mels, _stream())
+            _lib.check(rc, 'dasv_cmn_f32')
+    return out

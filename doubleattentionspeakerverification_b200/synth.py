@@ -127,6 +127,20 @@ def make_lengths(batch, lo, hi, seed=0):
     return rs.randint(lo, hi + 1, size=(batch,)).astype(np.int32)
 
 
+def make_waveform(n_samples, sfr=16000, seed=0):
+    """A speech-like synthetic waveform in [-1, 1): a few drifting harmonics under a slow envelope plus noise
+    (float64, like ``soundfile.read``)."""
+    rs = np.random.RandomState(seed)
+    t = np.arange(n_samples) / float(sfr)
+    y = np.zeros(n_samples)
+    f0 = 90.0 + 80.0 * rs.rand()
+    for k in range(1, 12):
+        y += (rs.rand() / k) * np.sin(2 * np.pi * k * f0 * t * (1.0 + 0.05 * np.sin(2 * np.pi * 1.7 * t)) + 6.28 * rs.rand())
+    env = 0.5 + 0.5 * np.sin(2 * np.pi * 3.1 * t + rs.rand())
+    y = 0.2 * env * y / max(np.abs(y).max(), 1e-9) + 0.01 * rs.standard_normal(n_samples)
+    return np.clip(y, -1.0, 1.0 - 1.0 / 32768)
+
+
 def make_pooling_case(batch, frames, dim, heads, seed=0, with_lengths=False):
     """Inputs for a DoubleMHA pooling test: x ``[B,T,D]``, query ``[dh,H]``, att ``[dh,1]``,
     upstream gradient g ``[B,dh]``, keep mask ``[B,H]`` (>=1 head kept per row), lengths."""

@@ -157,6 +157,22 @@ int dasv_cosine_matrix(const float* enrol, const float* test, float* scores, voi
 int dasv_threshold_counts(const float* scores, int n, const double* thresholds, int n_th,
                           unsigned long long* ge_counts, void* stream);
 
+/* ---------------------------------------------------------------- feature extraction (in front of the path)
+ * scripts/featureExtractor.py:8-23 (`mfsc`): y*scale, pre-emphasis over the whole signal (first sample times 1 - preem),
+ * frames of 512 samples (the reference's n_fft) every `hop`, `window` [win_length <= 512] centred in the frame
+ * (librosa.stft(center=False)), |rfft|, mel = melw [n_mels,257] . |S| (librosa.filters.mel, built by the caller for its
+ * sample rate; mel_range [n_mels,2] = first / one-past-last bin with a non-zero weight), log(max(1, mel)).
+ * wave [B][wave_stride] f32, n_samples [B] int32; out [B,Tmax,n_mels] f32: frame t of utterance b is written iff
+ * t < 1 + (n_samples[b] - 512) / hop, other rows are left untouched. */
+int dasv_logmel_f32(const float* wave, const int32_t* n_samples, int B, long long wave_stride,
+                    const float* window, int win_length, int hop,
+                    const float* melw, const int32_t* mel_range, int n_mels,
+                    float preem, float scale, float* out, int Tmax, void* stream);
+
+/* scripts/featureExtractor.py:25-26 (`normalize`) / data.py:21-30 ('cmn'), in place: per utterance and mel bin subtract
+ * the mean over its frames[b] frames; rows t >= frames[b] are set to zero. */
+int dasv_cmn_f32(float* feat, const int32_t* frames, int B, int Tmax, int n_mels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,8 +199,10 @@ def test_dynamic_schedule_is_bit_identical_to_static_deal(monkeypatch):
 @pytest.mark.parametrize('B,T,D,H', [(7, 53, 1024, 8), (5, 100, 256, 16), (3, 47, 2048, 32), (4, 16, 128, 4),
                                      (6, 130, 1536, 24), (300, 37, 512, 16)])
 def test_bf16_tensor_core_path(B, T, D, H, monkeypatch):
-    """bf16 features take the warp-MMA kernel (dmha_fwd3.cu): same answers as the oracle and as the CUDA-core kernel,
-    whatever sits in the frames past an utterance's length (NaN included), ragged tiles, empty utterances."""
+    """The opt-in warp-MMA kernel for bf16 features (dmha_fwd3.cu, DASV_DMHA_MMA=1): same answers as the oracle and as
+    the default CUDA-core kernel, whatever sits in the frames past an utterance's length (NaN included), ragged tiles,
+    empty utterances."""
+    monkeypatch.setenv('DASV_DMHA_MMA', '1')
     c = synth.make_pooling_case(B, T, D, H, seed=B + T, with_lengths=True)
     lengths = c['lengths'].copy()
     lengths[0] = 0 if B > 2 else lengths[0]                       # an empty utterance
@@ -214,11 +216,13 @@ def test_bf16_tensor_core_path(B, T, D, H, monkeypatch):
     t = torch.arange(T, device='cuda')[None, :, None]
     xn = torch.where(t < L[:, None, None], x, torch.full_like(x, float('nan')))
     rn = ops.dmha_fwd(xn, q, a, lengths=L)
-    monkeypatch.setenv('DASV_DMHA_NO_MMA', '1')
+    monkeypatch.delenv('DASV_DMHA_MMA')
     rc = ops.dmha_fwd(x, q, a, lengths=L)
+    rcn = ops.dmha_fwd(xn, q, a, lengths=L)
     for k in ('out', 'ctx', 'lse', 'headw', 'align'):
         assert torch.equal(rn[k][1:], r[k][1:]), k                  # padding content is never read into the math
         assert max_rel(r[k][1:].cpu().numpy(), rc[k][1:].cpu().numpy()) < 2e-5, k
+        assert torch.equal(rcn[k][1:], rc[k][1:]), k
 
 
 def test_attention_and_head_attention_train_under_autograd():

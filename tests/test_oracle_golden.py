@@ -124,3 +124,31 @@ def test_eer():
         CL = (0.5 + sep + 0.2 * rs.standard_normal(int(n_cl))).clip(-1, 1).astype(np.float32)
         IM = (0.5 - sep + 0.2 * rs.standard_normal(int(n_im))).clip(-1, 1).astype(np.float32)
         assert po.calculate_eer(CL, IM) == want
+
+
+# ------------------------------------------------------------------------------------ features
+@pytest.mark.parametrize('idx', range(3))
+def test_feature_oracle_matches_independent_implementation(idx):
+    """oracle/feature_oracle.py (restated librosa 0.7.2 stft + filters.mel) vs vectors made with transformers.audio_utils
+    (oracle/make_golden_features.py)."""
+    from oracle import feature_oracle as fo
+    g = golden('logmel_%d.npz' % idx)
+    sfr, n, seed = [int(v) for v in g['shape']]
+    y = synth.make_waveform(n, sfr, seed)
+    assert np.abs(fo.mel_filterbank(sfr) - g['melw']).max() < 1e-7
+    assert np.abs(fo.mfsc(y, sfr) - g['mfsc']).max() < 1e-5
+    assert np.abs(fo.extract(y, sfr) - g['feat']).max() < 1e-5
+
+
+def test_feature_host_tables_match_the_oracle():
+    """The product's own window / mel-filterbank construction (featureExtractor._tables) against the oracle's."""
+    from oracle import feature_oracle as fo
+    from doubleattentionspeakerverification_b200 import featureExtractor as fe
+    for sfr, n_mels, window in ((16000, 80, 'hamming'), (8000, 40, 'hann'), (16000, 24, 'hamming')):
+        win_length = int(sfr * 0.025)
+        taps, melw, rng = fe._tables(sfr, win_length, window, n_mels)
+        lpad = (512 - win_length) // 2
+        assert np.abs(fo.fft_window(window, win_length)[lpad:lpad + win_length] - taps).max() < 1e-7
+        assert np.abs(melw - fo.mel_filterbank(sfr, 512, n_mels)).max() < 1e-6
+        assert np.array_equal(rng, fo.mel_ranges(melw))
+    assert fe.frames_for(np.array([511, 512, 671, 672, 16000]), 160).tolist() == [0, 1, 1, 2, 97]
