@@ -111,6 +111,33 @@ def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400
     return out
 
 
+def extract_local_audio(embed_fn, waves, indices, sfr, device, max_samples=256 * 64352, max_batch=None, min_ratio=0.8, **feature_kw):
+    """Waveform -> embedding without the host in between (getEmbeddingExample.py:22-36 = extractFeatures + getEmbedding):
+    ``waves[i]`` (1-D float arrays in [-1, 1)) go to the device in zero-padded batches of similar length, the log-mel
+    features + CMN are computed there (``featureExtractor.logmel_batch``) and handed to ``embed_fn(x [B,T,80], frames
+    [B])`` with the frame counts as lengths.  Returns ``[len(indices), E]`` in the order of ``indices``."""
+    from . import featureExtractor as fe
+    indices = np.asarray(indices)
+    if len(indices) == 0:
+        return None
+    dev = torch.device(device)
+    n = np.array([len(waves[i]) for i in indices])
+    if (n < fe.N_FFT).any():
+        raise ValueError('a waveform is shorter than one analysis frame (%d samples)' % fe.N_FFT)
+    out = None
+    for b in bucket_plan(n, max_samples, min_ratio, max_batch):
+        nb = n[b]
+        host = torch.zeros((len(b), int(nb.max())), dtype=torch.float32, pin_memory=True)
+        for j, i in enumerate(b):
+            host[j, :nb[j]] = torch.from_numpy(np.asarray(waves[indices[i]], dtype=np.float32))
+        feat, frames = fe.logmel_batch(host.to(dev, non_blocking=True), nb, sfr, **feature_kw)
+        emb = embed_fn(feat, frames)
+        if out is None:
+            out = torch.empty((len(indices), emb.shape[1]), device=emb.device, dtype=emb.dtype)
+        out[torch.from_numpy(b).to(emb.device)] = emb
+    return out
+
+
 def pad_batch(feats, idx, multiple=1):
     """Stack ``feats[i]`` (``[T_i, F]`` arrays) into a zero-padded ``[len(idx), Tmax, F]`` float32 array + lengths."""
     L = np.array([feats[i].shape[0] for i in idx], np.int32)

@@ -54,6 +54,18 @@ def _tables(sfr, win_length, window, n_mels):
     return taps, melw, rng
 
 
+_dev_tables = {}
+
+
+def _device_tables(device, sfr, win_length, window, n_mels):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), sfr, win_length, window, n_mels)
+    t = _dev_tables.get(key)
+    if t is None:
+        t = tuple(torch.from_numpy(a).to(device) for a in _tables(sfr, win_length, window, n_mels))
+        _dev_tables[key] = t
+    return t
+
+
 def frames_for(n_samples, hop):
     """Frames librosa.stft(center=False) produces for ``n_samples`` samples (0 if shorter than one n_fft frame)."""
     n_samples = np.asarray(n_samples)
@@ -78,11 +90,11 @@ def logmel_batch(wave, n_samples, sfr, window_size=0.025, window_stride=0.010, w
     if n_host.shape != (wave_d.shape[0],) or (n_host > wave_d.shape[1]).any():
         raise _lib.DasvError('n_samples must be [B] and <= wave.shape[1]')
     frames = frames_for(n_host, hop).astype(np.int32)
-    taps, melw, rng = _tables(int(sfr), win_length, window, int(n_mels))
-    feat = ops.logmel(wave_d, torch.from_numpy(n_host.astype(np.int32)).to(device), torch.from_numpy(frames).to(device),
-                      int(frames.max()) if frames.size else 0, torch.from_numpy(taps).to(device), hop,
-                      torch.from_numpy(melw).to(device), torch.from_numpy(rng).to(device), float(preemCoef), 32768.0, cmn)
-    return feat, torch.from_numpy(frames).to(device)
+    taps, melw, rng = _device_tables(torch.device(device), int(sfr), win_length, window, int(n_mels))
+    counts = torch.from_numpy(np.stack([n_host.astype(np.int32), frames])).to(device, non_blocking=True)   # one small H2D copy
+    feat = ops.logmel(wave_d, counts[0], counts[1], int(frames.max()) if frames.size else 0, taps, hop, melw, rng,
+                      float(preemCoef), 32768.0, cmn)
+    return feat, counts[1]
 
 
 def mfsc(y, sfr, window_size=0.025, window_stride=0.010, window='hamming', n_mels=80, preemCoef=0.97):

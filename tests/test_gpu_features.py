@@ -94,3 +94,20 @@ def test_waveform_to_embedding_pipeline():
             want = fo.extract(wave[i, :n].astype(np.float64), 16000).astype(np.float32)
             e1 = net.getEmbedding(torch.from_numpy(want)[None].cuda()).cpu().numpy()[0]
             assert np.abs(emb[i] - e1).max() / np.abs(e1).max() < 1e-3
+
+
+def test_extract_local_audio_buckets_and_order():
+    from doubleattentionspeakerverification_b200 import extract
+    cfg = synth.example_config(kernel_size=256, embedding_size=128, heads_number=8, num_spkrs=5)
+    cfg.precision = 'fp32'
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, seed=9)).cuda().eval()
+    ns = [9000, 30000, 16000, 31000, 9500, 700]
+    waves = [synth.make_waveform(n, 16000, seed=40 + i) for i, n in enumerate(ns)]
+    embed = lambda x, L: net.getEmbedding(x, lengths=L)
+    with torch.no_grad():
+        got = extract.extract_local_audio(embed, waves, [5, 0, 1, 2, 3, 4], 16000, 'cuda', max_samples=70000).cpu().numpy()
+        for row, i in enumerate([5, 0, 1, 2, 3, 4]):
+            one = extract.extract_local_audio(embed, waves, [i], 16000, 'cuda').cpu().numpy()[0]
+            assert np.abs(got[row] - one).max() / np.abs(one).max() < 1e-4, i       # batch composition does not matter
+    with pytest.raises(ValueError):
+        extract.extract_local_audio(embed, [waves[0][:100]], [0], 16000, 'cuda')
