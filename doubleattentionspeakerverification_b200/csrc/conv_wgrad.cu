@@ -1,0 +1,313 @@
+// Weight gradient of the VGG front-end's 3x3 convolutions on the tensor cores (sm_100a): the training-side companion of
+// conv_igemm.cu (the reference gets it from cuDNN through autograd, scripts/CNNs.py:59-66 + train.py:201).
+//
+//   dW[co][ci][ky][kx] = sum_{b,t,f} G[b,t,f,co] * X[b,t+ky-1,f+kx-1,ci]
+//
+// G = gradient at the conv output (after the ReLU / pool backward, zero for frames past an utterance), X = the layer's
+// input, both bf16 NHWC.  This is a GEMM whose contraction index is the PIXEL, so with channels contiguous in memory both
+// operands are MN-major: a 128-byte shared-memory row holds 64 channels of one pixel, rows are pixels, and tcgen05.mma
+// reads them through MN-major SWIZZLE_128B descriptors (instruction-descriptor bits 15/16) exactly as TMA wrote them.
+//
+// One CTA owns a [128 co] x [32 ci] tile of all NINE taps (9 x 32 = 288 TMEM columns) and a range of (utterance, frame
+// tile) items (split-K).  Per item TMA loads
+//   G tile  [BT frames][F+2 bins] x 128 co   (two 64-channel boxes; the bins -1 and F are out of bounds = zero filled)
+//   X patch [BT+2 frames][F+2 bins] x 64 ci  (one box, +-1 frame halo, same zero-filled border columns)
+// and the contraction runs LINEARLY over the G tile's rows r = t*(F+2) + f: the X row that pairs with G row r for tap
+// (ky,kx) is r + ky*(F+2) + kx - 1, a constant row offset, so a tap is just a different start address of the same X
+// patch.  The zero border columns of G make the wrap-around rows harmless, rows beyond the tile are zero because the
+// whole shared memory is cleared once and TMA never writes them.
+// Partial sums go to a workspace [split][tap][co][ci] (fp32) and a second kernel adds the splits in fixed order
+// (deterministic) into the reference layout [Cout][Cin][3][3].
+//
+// Roofline: tensor, but with A re-read from shared memory for every 128x32x16 MMA the operand feed (5 KB per 16 clk)
+// exceeds what an SM's shared memory delivers, so this first version is bounded at about half of the dense rate; the
+// measured number is in DESIGN.md.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <stdlib.h>
+#include <stdio.h>
+
+namespace dasv {
+
+constexpr int kWgThreads = 256;      // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int kWgM = 128;            // output channels per tile (TMEM lanes)
+constexpr int kWgN = 32;             // input channels per tile
+constexpr uint32_t kWgTmemCols = 512;
+
+struct WgradParams {
+    float* ws;                       // [splits][9][Cout][Cin]
+    int B, T, F, Cin, Cout;
+    int BT, n_tt, n_items, items_per_split, splits;
+    int n_mt, n_nt;
+    int rowsG, K16, rowsX;
+    uint32_t g_box_bytes;            // bytes one G box delivers (rowsG * 128)
+    uint32_t g_alloc;                // K16 * 128
+    uint32_t x_box_bytes, x_off;     // X patch inside a stage: x_off = 2 * g_alloc + 1024 (a guard row precedes the patch)
+    uint32_t stage_bytes;
+    int stages;
+};
+
+// MN-major operand, 128-byte swizzle: a row = 64 channels (128 B) of one K index; 8 consecutive K rows form the 1024-byte
+// swizzle atom (SBO between atoms along K); the next 64 channels live `lbo` bytes further (LBO).
+DASV_DEVICE uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* ring = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * p.stage_bytes);
+    uint64_t* empty = full + p.stages;
+    uint64_t* acc_full = empty + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pairs = p.n_mt * p.n_nt;
+    const int pair = static_cast<int>(blockIdx.x) % pairs, split = static_cast<int>(blockIdx.x) / pairs;
+    const int m = pair % p.n_mt, n = pair / p.n_mt;
+    const int item0 = split * p.items_per_split;
+    const int item1 = min(item0 + p.items_per_split, p.n_items);
+
+    // clear the ring once: rows that TMA never writes (K padding, guard rows) must read as finite zeros
+    {
+        uint4* z = reinterpret_cast<uint4*>(ring);
+        const size_t n16 = static_cast<size_t>(p.stages) * p.stage_bytes / 16;
+        for (size_t i = threadIdx.x; i < n16; i += kWgThreads) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmX); }
+    if (warp == 2) { tmem_alloc(tmem_slot, kWgTmemCols); tmem_relinquish(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                            // TMA producer
+            int st = 0;
+            uint32_t ph = 0;
+            for (int it = item0; it < item1; ++it) {
+                const int b = it / p.n_tt, t0 = (it % p.n_tt) * p.BT;
+                mbar_wait(&empty[st], ph ^ 1u);
+                unsigned char* sb = ring + static_cast<size_t>(st) * p.stage_bytes;
+                mbar_arrive_expect_tx(&full[st], 2 * p.g_box_bytes + p.x_box_bytes);
+                tma_load_4d(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
+                tma_load_4d(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
+                tma_load_4d(sb + p.x_off, &tmX, &full[st], (n >> 1) * 64, -1, t0 - 1, b);
+                if (++st == p.stages) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                            // MMA issuer
+            const uint32_t idesc = umma_idesc_bf16(kWgM, kWgN) | (1u << 15) | (1u << 16);     // A and B MN-major
+            const int frow = p.F + 2;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int it = item0; it < item1; ++it) {
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
+                const uint32_t xb = sb + p.x_off + static_cast<uint32_t>(n & 1) * 64u;
+                for (int k = 0; k < p.K16; k += 16) {
+                    const uint64_t a_desc = umma_desc_mn128(sb + static_cast<uint32_t>(k) * 128u, p.g_alloc);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int shift = (tap / 3) * frow + (tap % 3) - 1;                      // rows; -1 lands on the guard row
+                        const uint64_t b_desc = umma_desc_mn128(xb + static_cast<uint32_t>((k + shift) * 128), 16);
+                        umma_bf16(tmem_base + static_cast<uint32_t>(tap * kWgN), a_desc, b_desc, idesc, (it > item0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[st]);            // frees the stage when the MMAs above have read it
+                if (++st == p.stages) { st = 0; ph ^= 1u; }
+            }
+            umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        // epilogue: lane = output channel, 32 input channels per tap
+        const int q = warp & 3;
+        const int co = m * kWgM + q * 32 + lane;
+        if (item1 > item0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            uint32_t r[32];
+            if (item1 > item0) {
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tap * kWgN), r);
+                tc_wait_ld();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (co < p.Cout) {
+                float4* dst = reinterpret_cast<float4*>(p.ws + ((static_cast<size_t>(split) * 9 + tap) * p.Cout + co) * p.Cin + n * kWgN);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                         __uint_as_float(r[4 * j + 3]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kWgTmemCols); }
+}
+
+// dW[co][ci][tap] (+)= sum over splits, fixed order
+__global__ void conv_wgrad_reduce_kernel(const float* ws, float* dw, int splits, int Cout, int Cin, int accumulate) {
+    const size_t n = static_cast<size_t>(Cout) * Cin;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // (co, ci)
+    if (i >= n) return;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += ws[(static_cast<size_t>(sp) * 9 + tap) * n + i];
+        float* d = dw + i * 9 + tap;
+        *d = accumulate ? *d + s : s;
+    }
+}
+
+typedef CUresult (*WgEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static WgEncodeTiledFn wg_encode_tiled() {
+    static WgEncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<WgEncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+struct WgradPlan {
+    int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, rowsG, K16, rowsX, stages;
+    uint32_t g_alloc, x_off, stage_bytes;
+    size_t smem;
+};
+
+static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
+    WgradPlan pl{};
+    if (Cin % 64 != 0 || Cout % 8 != 0 || F < 1 || F + 2 > 256 || T < 1 || B < 1) return pl;
+    pl.BT = 176 / (F + 2);
+    if (pl.BT < 1) pl.BT = 1;
+    if (pl.BT > T) pl.BT = T;
+    if (pl.BT + 2 > 256) pl.BT = 254;
+    pl.rowsG = pl.BT * (F + 2);
+    pl.K16 = (pl.rowsG + 15) / 16 * 16;
+    pl.rowsX = (pl.BT + 2) * (F + 2);
+    pl.g_alloc = static_cast<uint32_t>(pl.K16) * 128u;
+    pl.g_alloc = (pl.g_alloc + 1023u) & ~1023u;
+    pl.x_off = 2 * pl.g_alloc + 1024u;
+    // X rows an MMA view may touch: -1 .. K16 - 1 + 2 (F + 2) + 1
+    const uint32_t x_rows = static_cast<uint32_t>(pl.K16 + 2 * (F + 2) + 2);
+    pl.stage_bytes = (pl.x_off + x_rows * 128u + 1023u) & ~1023u;
+    const uint32_t avail = 227u * 1024u - 1024u - 256u;
+    pl.stages = static_cast<int>(avail / pl.stage_bytes);
+    if (pl.stages > 4) pl.stages = 4;
+    if (pl.stages < 1) return pl;
+    pl.smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024 + 256;
+    pl.n_tt = (T + pl.BT - 1) / pl.BT;
+    pl.n_items = B * pl.n_tt;
+    pl.n_mt = (Cout + kWgM - 1) / kWgM;
+    pl.n_nt = Cin / kWgN;
+    const int pairs = pl.n_mt * pl.n_nt;
+    // split-K factor: fill the SMs in whole waves, keep >= 2 items per CTA, bound the workspace
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 64; ++s) {
+        if (s > 1 && (pl.n_items + s - 1) / s < 2) break;
+        const double ctas = static_cast<double>(pairs) * s;
+        const double waves = (ctas + sms - 1) / sms;
+        const double eff = ctas / (static_cast<double>(static_cast<long long>(waves)) * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    if (const char* e = getenv("DASV_WGRAD_SPLITS")) { const int v = atoi(e); if (v >= 1 && v <= 256) best = v; }
+    pl.splits = best;
+    pl.items_per_split = (pl.n_items + best - 1) / best;
+    pl.ok = 1;
+    return pl;
+}
+
+}  // namespace dasv
+
+using namespace dasv;
+
+extern "C" size_t dasv_conv3x3_wgrad_workspace_bytes(int B, int T, int F, int Cin, int Cout) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    cudaGetLastError();
+    const WgradPlan pl = wgrad_plan(B, T, F, Cin, Cout, sms);
+    if (!pl.ok) return 0;
+    return static_cast<size_t>(pl.splits) * 9 * Cout * Cin * sizeof(float);
+}
+
+extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, void* workspace, int accumulate,
+                                       int B, int T, int F, int Cin, int Cout, void* stream) {
+    if (B < 0 || T < 0) { set_error("conv3x3_wgrad_bf16: negative shape"); return 1; }
+    if (!x || !g || !dw || !workspace) { set_error("conv3x3_wgrad_bf16: null pointer"); return 1; }
+    if (Cout % kWgM != 0) { set_error("conv3x3_wgrad_bf16: Cout %d must be a multiple of 128", Cout); return 1; }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (B == 0 || T == 0) {
+        if (!accumulate) cudaMemsetAsync(dw, 0, static_cast<size_t>(Cout) * Cin * 9 * sizeof(float), s);
+        return check_launch("conv3x3_wgrad_bf16");
+    }
+    const WgradPlan pl = wgrad_plan(B, T, F, Cin, Cout, sms);
+    if (!pl.ok) { set_error("conv3x3_wgrad_bf16: unsupported shape T=%d F=%d Cin=%d Cout=%d (need Cin %% 64 == 0, F <= 254)", T, F, Cin, Cout); return 1; }
+    WgEncodeTiledFn encode = wg_encode_tiled();
+    if (!encode) { set_error("conv3x3_wgrad_bf16: cuTensorMapEncodeTiled is not available from the CUDA driver"); return 1; }
+    CUtensorMap tmG, tmX;
+    for (int which = 0; which < 2; ++which) {
+        const int C = which ? Cin : Cout;
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(F), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(F) * C * 2, static_cast<cuuint64_t>(T) * F * C * 2};
+        const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(F + 2), static_cast<cuuint32_t>(which ? pl.BT + 2 : pl.BT), 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(which ? &tmX : &tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(which ? x : g), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3x3_wgrad_bf16: tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
+    }
+    WgradParams p{};
+    p.ws = static_cast<float*>(workspace);
+    p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.Cout = Cout;
+    p.BT = pl.BT; p.n_tt = pl.n_tt; p.n_items = pl.n_items; p.items_per_split = pl.items_per_split; p.splits = pl.splits;
+    p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.rowsG = pl.rowsG; p.K16 = pl.K16; p.rowsX = pl.rowsX;
+    p.g_box_bytes = static_cast<uint32_t>(pl.rowsG) * 128u; p.g_alloc = pl.g_alloc;
+    p.x_box_bytes = static_cast<uint32_t>(pl.rowsX) * 128u; p.x_off = pl.x_off;
+    p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
+    if (getenv("DASV_CONV_DEBUG"))
+        fprintf(stderr, "wgrad plan: B=%d T=%d F=%d Cin=%d Cout=%d BT=%d rowsG=%d K16=%d rowsX=%d stages=%d stage_bytes=%u items=%d splits=%d\n",
+                B, T, F, Cin, Cout, pl.BT, pl.rowsG, pl.K16, pl.rowsX, pl.stages, pl.stage_bytes, pl.n_items, pl.splits);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
+    if (e != cudaSuccess) { set_error("conv3x3_wgrad_bf16: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return 1; }
+    const int grid = pl.n_mt * pl.n_nt * pl.splits;
+    conv_wgrad_kernel<<<grid, kWgThreads, pl.smem, s>>>(tmG, tmX, p);
+    if (check_launch("conv3x3_wgrad_bf16")) return 1;
+    const size_t n = static_cast<size_t>(Cout) * Cin;
+    conv_wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p.ws, dw, pl.splits, Cout, Cin, accumulate);
+    return check_launch("conv3x3_wgrad_reduce");
+}

@@ -301,3 +301,28 @@ def logmel(wave, n_samples, frames, Tmax, window, hop, melw, mel_range, preem, s
             rc = L.dasv_cmn_f32(_p(out), _p(frames), B, Tmax, n_mels, _stream())
             _lib.check(rc, 'dasv_cmn_f32')
     return out
+
+
+# ------------------------------------------------------------------------------------ training side of the front-end
+def conv3x3_wgrad(x, g, dw=None):
+    """Weight gradient of a 3x3 pad-1 convolution (csrc/conv_wgrad.cu).  x [B,T,F,Cin] bf16 NHWC (layer input),
+    g [B,T,F,Cout] bf16 NHWC (gradient at the conv output).  Returns dw [Cout,Cin,3,3] f32 (added to ``dw`` if given)."""
+    _dev(x, 'x'); _dev(g, 'g')
+    if x.dtype != torch.bfloat16 or g.dtype != torch.bfloat16:
+        raise _lib.DasvError('conv3x3_wgrad needs bf16 activations')
+    x, g = x.contiguous(), g.contiguous()
+    B, T, F, Cin = x.shape
+    Cout = g.shape[3]
+    if g.shape[:3] != x.shape[:3]:
+        raise _lib.DasvError('x and g disagree on [B,T,F]')
+    with torch.cuda.device(x.device):
+        L = _lib.lib()
+        acc = dw is not None
+        if dw is None:
+            dw = torch.empty((Cout, Cin, 3, 3), device=x.device, dtype=torch.float32)
+        elif dw.shape != (Cout, Cin, 3, 3) or dw.dtype != torch.float32 or not dw.is_contiguous():
+            raise _lib.DasvError('dw must be a contiguous f32 [Cout,Cin,3,3] tensor')
+        ws = torch.empty((max(int(L.dasv_conv3x3_wgrad_workspace_bytes(B, T, F, Cin, Cout)), 16),), device=x.device, dtype=torch.uint8)
+        rc = L.dasv_conv3x3_wgrad_bf16(_p(x), _p(g), _p(dw), _p(ws), 1 if acc else 0, B, T, F, Cin, Cout, _stream())
+        _lib.check(rc, 'dasv_conv3x3_wgrad_bf16')
+    return dw

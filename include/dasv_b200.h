@@ -132,6 +132,17 @@ int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, co
                             void* y, int y_dtype, int flags,
                             int B, int T, int F, int Cin, int Cout, void* stream);
 
+/* Weight gradient of a 3x3 stride-1 pad-1 convolution on the tensor cores (training side of the layer above; the
+ * reference obtains it from autograd/cuDNN, scripts/CNNs.py:59-66):
+ *   dw[co][ci][ky][kx] (+)= sum_{b,t,f} g[b,t,f,co] * x[b,t+ky-1,f+kx-1,ci]
+ * x [B,T,F,Cin] bf16 (the layer's input), g [B,T,F,Cout] bf16 (gradient at the conv output, i.e. after the ReLU / pool
+ * backward; zero for frames past an utterance), dw [Cout,Cin,3,3] f32 (reference layout; overwritten, or added to when
+ * accumulate != 0).  Deterministic: split-K partials in `workspace` are added in fixed order.
+ * Requirements: Cin % 64 == 0, Cout % 128 == 0, F <= 254. */
+size_t dasv_conv3x3_wgrad_workspace_bytes(int B, int T, int F, int Cin, int Cout);
+int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, void* workspace, int accumulate,
+                            int B, int T, int F, int Cin, int Cout, void* stream);
+
 /* ---------------------------------------------------------------- embedding tail
  * getEmbedding's FC block, eval mode: b2(relu(fc2(relu(fc1(pooled))))) (scripts/model.py:56-57).
  * Packing: w1t [Din,E] = fc1.weight^T, w2t [E,E] = fc2.weight^T (f32),
