@@ -8,8 +8,11 @@ Inference (no autograd) runs on this package's sm_100a kernels, NHWC end to end:
     epilogue.  Needs every tensor-core conv to have Cin % 64 == 0 (kernel_size >= 512 for VGG4L).
   * ``precision='fp32'``: CUDA-core fp32 implicit GEMM + separate pool kernel (the 1e-4 parity path).
   * ``precision='auto'`` (default): bf16 when the channel counts allow it, else fp32.
-Under autograd the convolutions run through torch (cuDNN): conv backward is out of scope
-(SURVEY.md §7 "Conv backward is NOT required"), only the pooling has a hand-written backward.
+Under autograd the default is torch (cuDNN) convolutions in fp32, numerically the reference's own training path.
+``train_kernels=True`` (with bf16 precision and channel counts that are multiples of 64) switches training to this
+package's kernels as well: the forward keeps every layer's ReLU output, the backward is tcgen05 implicit GEMMs for the
+input gradients (the forward kernel with rotated weights and a linear epilogue) and the weight gradients
+(``csrc/conv_wgrad.cu``) plus streaming kernels for the ReLU / max-pool backward and the bias gradients.
 """
 import numpy as np
 import torch
@@ -39,8 +42,9 @@ def getVGG4LOutputDimension(inputDimension, outputChannel=128):
 class _VGG(nn.Module):
     _divisors = ()   # kernel_size / d = channels of each block
 
-    def __init__(self, kernel_size, precision='auto'):
+    def __init__(self, kernel_size, precision='auto', train_kernels=False):
         super().__init__()
+        self.train_kernels = train_kernels
         cin = 1
         self._names = []
         for blk, d in enumerate(self._divisors, start=1):
@@ -78,10 +82,35 @@ class _VGG(nn.Module):
         x = paddedInputTensor
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
+            if self.train_kernels and self._train_kernels_ok() and not x.requires_grad:
+                params = []
+                for n in self._names:
+                    c = getattr(self, n)
+                    params += [c.weight, c.bias]
+                L = None if lengths is None else torch.as_tensor(lengths, device=x.device).to(torch.int32)
+                return _VGGTrainFn.apply(self, x, L, *params)
             if lengths is not None:
-                raise NotImplementedError('length masking is an inference-only capability')
+                raise NotImplementedError('length masking under autograd needs train_kernels=True')
             return self._forward_autograd(x)
         return self._forward_kernels(x, lengths)
+
+    def _train_kernels_ok(self):
+        return self.resolved_precision() == 'bf16' and all(
+            getattr(self, n).in_channels % 64 == 0 and getattr(self, n).out_channels % 64 == 0 for n in self._names[1:])
+
+    def _pack_dgrad(self, name):
+        """Packed weights of the input-gradient pass: dx = conv3x3(g, W') with W'[ci][co][ky][kx] = W[co][ci][2-ky][2-kx]."""
+        conv = getattr(self, name)
+        w = conv.weight
+        key = (name, 'dgrad')
+        tag = (w.data_ptr(), w._version, str(w.device))
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != tag:
+            with torch.no_grad():
+                packed = ops.pack_conv_weight_bf16(w.detach().flip(2, 3).transpose(0, 1).contiguous())
+            hit = (tag, packed)
+            self._packed[key] = hit
+        return hit[1]
 
     def _forward_autograd(self, x):
         # training path: torch/cuDNN convolutions in the reference's NCHW layout (CNNs.py:68-91)
@@ -137,6 +166,77 @@ class _VGG(nn.Module):
         for _ in range(len(self._names) // 2):
             L = (L + 1) // 2
         return L
+
+
+class _VGGTrainFn(torch.autograd.Function):
+    """The whole front-end as one autograd node on this package's kernels (bf16 activations, f32 parameter gradients).
+    Forward = CNNs.py:68-91 with every ReLU output kept; backward = the chain rule through it, layer by layer."""
+
+    @staticmethod
+    def run_forward(mod, x, lengths):
+        """(features, ReLU outputs of every conv in layer order, pooled outputs per block, lengths per block)."""
+        names = mod._names
+        nblocks = len(names) // 2
+        L = lengths
+        c11 = getattr(mod, names[0])
+        acts = [ops.conv11_direct(x, c11.weight.detach(), c11.bias.detach(), L, out_dtype=torch.bfloat16)]
+        pooled, Ls = [], []
+        h = acts[0]
+        for blk in range(nblocks):
+            Ls.append(L)
+            if blk > 0:
+                c = getattr(mod, names[2 * blk])
+                h = ops.conv3x3_igemm_bf16(h, mod._pack(names[2 * blk], 'bf16'), c.bias.detach(), c.out_channels, L)
+                acts.append(h)
+            c = getattr(mod, names[2 * blk + 1])
+            h = ops.conv3x3_igemm_bf16(h, mod._pack(names[2 * blk + 1], 'bf16'), c.bias.detach(), c.out_channels, L)
+            acts.append(h)
+            last = blk == nblocks - 1
+            h = ops.maxpool2x2(h, ref_layout=last, out_dtype=torch.float32 if last else torch.bfloat16)
+            pooled.append(h)
+            if L is not None:
+                L = (L + 1) // 2
+        return h, acts, pooled, Ls
+
+    @staticmethod
+    def forward(ctx, mod, x, lengths, *params):
+        x = x.detach().float().contiguous()
+        h, acts, pooled, Ls = _VGGTrainFn.run_forward(mod, x, lengths)
+        ctx.mod, ctx.x, ctx.acts, ctx.pooled, ctx.Ls = mod, x, acts, pooled, Ls
+        return h
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        mod, x, acts, pooled, Ls = ctx.mod, ctx.x, ctx.acts, ctx.pooled, ctx.Ls
+        names = mod._names
+        nblocks = len(names) // 2
+        grads = [None] * (2 * len(names))
+        gp = dfeat.float().contiguous()                           # gradient at the pooled output of the current block
+        for blk in range(nblocks - 1, -1, -1):
+            L = Ls[blk]
+            y2 = acts[2 * blk + 1]
+            g = ops.unpool_relu_bwd(gp, y2)                       # gradient at conv_k2's output (before ReLU)
+            x2 = acts[2 * blk]                                    # conv_k2's input = conv_k1's ReLU output
+            i2 = 2 * blk + 1
+            grads[2 * i2] = ops.conv3x3_wgrad(x2, g)
+            grads[2 * i2 + 1] = ops.bias_grad(g)
+            c2 = getattr(mod, names[i2])
+            zero_b = torch.zeros((c2.in_channels,), device=g.device, dtype=torch.float32)
+            g = ops.conv3x3_igemm_bf16(g, mod._pack_dgrad(names[i2]), zero_b, c2.in_channels, L, relu=False)
+            g = ops.relu_bwd_(g, x2)                              # gradient at conv_k1's output (before ReLU)
+            i1 = 2 * blk
+            if blk == 0:
+                dw, db = ops.conv11_bwd(x, g, L)
+                grads[0], grads[1] = dw, db
+            else:
+                x1 = pooled[blk - 1]
+                grads[2 * i1] = ops.conv3x3_wgrad(x1, g)
+                grads[2 * i1 + 1] = ops.bias_grad(g)
+                c1 = getattr(mod, names[i1])
+                zero_b = torch.zeros((c1.in_channels,), device=g.device, dtype=torch.float32)
+                gp = ops.conv3x3_igemm_bf16(g, mod._pack_dgrad(names[i1]), zero_b, c1.in_channels, L, relu=False)
+        ctx.acts = ctx.pooled = None
+        return (None, None, None) + tuple(grads)
 
 
 class VGG3L(_VGG):

@@ -31,6 +31,11 @@ SIGNATURES = {
     'dasv_conv3x3_igemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_wgrad_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
     'dasv_conv3x3_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasv_relu_bwd_bf16': (_i, [_vp, _vp, _sz, _vp]),
+    'dasv_unpool_relu_bwd_bf16': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'dasv_train_workspace_bytes': (_sz, [_i]),
+    'dasv_bias_grad_bf16': (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp]),
+    'dasv_conv11_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_fc_tail_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'dasv_cosine_pairs': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     'dasv_cosine_matrix_workspace_bytes': (_sz, [_i, _i]),
@@ -43,7 +48,7 @@ SIGNATURES = {
 _LIB = None
 
 # kernels launched per successful C call, and the running count bench.py reports as gpu_launches
-KERNELS_PER_CALL = {'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
+KERNELS_PER_CALL = {'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_bias_grad_bf16': 2, 'dasv_conv11_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
 LAUNCHES = {}
 
 

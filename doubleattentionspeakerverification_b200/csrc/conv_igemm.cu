@@ -40,6 +40,7 @@ struct ConvParams {
     int kchunks;             // Cin / 64
     int stages;
     int pool, ref_layout, y_f32;
+    int relu;                // 0: linear epilogue (input-gradient pass), only without POOL
     uint32_t b_bytes;        // bytes one B box delivers
     uint32_t stage_bytes;    // per ring-1 stage: A + B(padded) (per-tap mode) or one B patch (tap-row reuse mode)
     uint32_t tmem_cols;
@@ -374,7 +375,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
                                     if (g16 * 16 + j < cnt)
-                                        dst[(g16 * 16 + j) * kConvTileM] = __float2bfloat16_rn(fmaxf(__uint_as_float(r[j]) + bias, 0.f));
+                                        dst[(g16 * 16 + j) * kConvTileM] = __float2bfloat16_rn(p.relu ? fmaxf(__uint_as_float(r[j]) + bias, 0.f) : __uint_as_float(r[j]) + bias);
                             }
                         }
                     } else {
@@ -526,8 +527,8 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     if (Cin % kConvKC != 0 || Cin <= 0) { set_error("conv3x3_igemm_bf16: Cin=%d must be a positive multiple of 64", Cin); return 1; }
     if (Cout <= 0 || Cout % 8 != 0) { set_error("conv3x3_igemm_bf16: Cout=%d must be a positive multiple of 8", Cout); return 1; }
     if (F <= 0 || F % 2 != 0 || F > 256) { set_error("conv3x3_igemm_bf16: F=%d must be even and <= 256", F); return 1; }
-    if (!(flags & 1)) { set_error("conv3x3_igemm_bf16: the epilogue always applies ReLU (flag DASV_CONV_RELU required)"); return 1; }
     const bool pool = (flags & 2) != 0, ref = (flags & 4) != 0;
+    if (!(flags & 1) && pool) { set_error("conv3x3_igemm_bf16: the pooled epilogue always applies ReLU (drop DASV_CONV_POOL or set DASV_CONV_RELU)"); return 1; }
     if (ref && !pool) { set_error("conv3x3_igemm_bf16: REF_LAYOUT requires POOL"); return 1; }
     if (!ref && y_dtype != 1) { set_error("conv3x3_igemm_bf16: NHWC output must be bf16"); return 1; }
     if (y_dtype != 0 && y_dtype != 1) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
@@ -594,6 +595,7 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     p.n_ft = F / pl.BF; p.n_tt = (T + pl.BT - 1) / pl.BT; p.n_bt = (B + pl.BB - 1) / pl.BB; p.n_mt = cout_pad / kConvTileM;
     p.kchunks = Cin / kConvKC;
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
+    p.relu = (flags & 1) ? 1 : 0;
     p.reuse = reuse;
     p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
     p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;

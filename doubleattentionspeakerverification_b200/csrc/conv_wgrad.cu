@@ -266,7 +266,7 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
                                        int B, int T, int F, int Cin, int Cout, void* stream) {
     if (B < 0 || T < 0) { set_error("conv3x3_wgrad_bf16: negative shape"); return 1; }
     if (!x || !g || !dw || !workspace) { set_error("conv3x3_wgrad_bf16: null pointer"); return 1; }
-    if (Cout % kWgM != 0) { set_error("conv3x3_wgrad_bf16: Cout %d must be a multiple of 128", Cout); return 1; }
+    if (Cout % 64 != 0) { set_error("conv3x3_wgrad_bf16: Cout %d must be a multiple of 64", Cout); return 1; }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -212,14 +212,14 @@ def maxpool2x2(x, ref_layout=False, out_dtype=None):
     return y
 
 
-def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False):
+def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False, relu=True):
     """bf16 tcgen05 implicit-GEMM conv3x3 + bias + ReLU (+ fused 2x2 ceil max-pool) on NHWC bf16."""
     _dev(x, 'x')
     if x.dtype != torch.bfloat16:
         raise _lib.DasvError('conv3x3_igemm_bf16: x must be bfloat16')
     x = x.contiguous()
     B, T, Fq, Cin = x.shape
-    flags = CONV_RELU | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0) | (CONV_PAIR if pair else 0)
+    flags = (CONV_RELU if relu else 0) | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0) | (CONV_PAIR if pair else 0)
     with torch.cuda.device(x.device):
         lengths = _lengths(lengths, B, x.device)
         if pool:
@@ -326,3 +326,59 @@ def conv3x3_wgrad(x, g, dw=None):
         rc = L.dasv_conv3x3_wgrad_bf16(_p(x), _p(g), _p(dw), _p(ws), 1 if acc else 0, B, T, F, Cin, Cout, _stream())
         _lib.check(rc, 'dasv_conv3x3_wgrad_bf16')
     return dw
+
+
+def relu_bwd_(g, y):
+    """In place g = y > 0 ? g : 0 (bf16, same shape)."""
+    _dev(g, 'g'); _dev(y, 'y')
+    if g.dtype != torch.bfloat16 or y.dtype != torch.bfloat16 or g.shape != y.shape or not g.is_contiguous() or not y.is_contiguous():
+        raise _lib.DasvError('relu_bwd_ needs contiguous bf16 tensors of one shape')
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().dasv_relu_bwd_bf16(_p(g), _p(y), g.numel(), _stream()), 'dasv_relu_bwd_bf16')
+    return g
+
+
+def unpool_relu_bwd(gp, y):
+    """Backward of relu + 2x2 ceil-mode max-pool.  y [B,T,F,C] bf16 (pre-pool ReLU output); gp bf16 [B,T2,F2,C] or, for the
+    front-end's output, f32 [B,T2,C*F2].  Returns g [B,T,F,C] bf16."""
+    _dev(gp, 'gp'); _dev(y, 'y')
+    B, T, Fq, C = y.shape
+    ref = gp.dim() == 3
+    if y.dtype != torch.bfloat16 or gp.dtype != (torch.float32 if ref else torch.bfloat16):
+        raise _lib.DasvError('unpool_relu_bwd: y must be bf16 and gp bf16 NHWC or f32 [B,T2,C*F2]')
+    gp, y = gp.contiguous(), y.contiguous()
+    with torch.cuda.device(y.device):
+        g = torch.empty_like(y)
+        _lib.check(_lib.lib().dasv_unpool_relu_bwd_bf16(_p(gp), int(ref), _p(y), _p(g), B, T, Fq, C, _stream()), 'dasv_unpool_relu_bwd_bf16')
+    return g
+
+
+def _train_ws(dev, C):
+    return torch.empty((int(_lib.lib().dasv_train_workspace_bytes(C)),), device=dev, dtype=torch.uint8)
+
+
+def bias_grad(g):
+    """Column sums of g [..., C] bf16 -> f32 [C]."""
+    _dev(g, 'g')
+    g = g.contiguous()
+    C = g.shape[-1]
+    with torch.cuda.device(g.device):
+        db = torch.empty((C,), device=g.device, dtype=torch.float32)
+        ws = _train_ws(g.device, C)
+        _lib.check(_lib.lib().dasv_bias_grad_bf16(_p(g), _p(db), _p(ws), 0, g.numel() // C, C, _stream()), 'dasv_bias_grad_bf16')
+    return db
+
+
+def conv11_bwd(x, g, lengths=None):
+    """conv11 (Cin = 1) parameter gradients: x [B,T,F] f32, g [B,T,F,C] bf16 -> (dw [C,1,3,3], db [C]) f32."""
+    x = _f32(x, 'x')
+    _dev(g, 'g')
+    g = g.contiguous()
+    B, T, Fq, C = g.shape
+    with torch.cuda.device(g.device):
+        lengths = _lengths(lengths, B, g.device)
+        dw = torch.empty((C, 1, 3, 3), device=g.device, dtype=torch.float32)
+        db = torch.empty((C,), device=g.device, dtype=torch.float32)
+        ws = _train_ws(g.device, C)
+        _lib.check(_lib.lib().dasv_conv11_bwd(_p(x), _p(g), _p(lengths), _p(dw), _p(db), _p(ws), 0, B, T, Fq, C, _stream()), 'dasv_conv11_bwd')
+    return dw, db

@@ -29,7 +29,7 @@ extern "C" {
 #define DASV_BF16 1
 
 /* conv flags */
-#define DASV_CONV_RELU 1        /* apply ReLU after bias (always set by the VGG blocks)            */
+#define DASV_CONV_RELU 1        /* apply ReLU after bias (set by the VGG blocks; clear = linear, for the input-gradient pass, no POOL) */
 #define DASV_CONV_POOL 2        /* fuse max_pool2d(2, stride 2, ceil_mode) into the epilogue         */
 #define DASV_CONV_REF_LAYOUT 4  /* with POOL: write [B,T',C*F'] with feature = c*F'+f (CNNs.py:88-89) */
 #define DASV_CONV_PAIR 8        /* run on CTA pairs (tcgen05 cta_group::2, 256 channels x N pixels per pair); same results */
@@ -138,10 +138,27 @@ int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, co
  * x [B,T,F,Cin] bf16 (the layer's input), g [B,T,F,Cout] bf16 (gradient at the conv output, i.e. after the ReLU / pool
  * backward; zero for frames past an utterance), dw [Cout,Cin,3,3] f32 (reference layout; overwritten, or added to when
  * accumulate != 0).  Deterministic: split-K partials in `workspace` are added in fixed order.
- * Requirements: Cin % 64 == 0, Cout % 128 == 0, F <= 254. */
+ * Requirements: Cin % 64 == 0, Cout % 64 == 0, F <= 254. */
 size_t dasv_conv3x3_wgrad_workspace_bytes(int B, int T, int F, int Cin, int Cout);
 int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, void* workspace, int accumulate,
                             int B, int T, int F, int Cin, int Cout, void* stream);
+
+/* Memory-bound pieces of the front-end's backward pass (what autograd does around the conv backward in the reference,
+ * scripts/CNNs.py:72-86).  bf16 NHWC activations/gradients, f32 parameter gradients, deterministic sums.
+ *  relu_bwd:        g [n] = y [n] > 0 ? g : 0, in place (n % 8 == 0).
+ *  unpool_relu_bwd: backward of relu + max_pool2d(2,2,ceil_mode=True): y [B,T,F,C] = the conv's ReLU output before the
+ *                   pool, gp = gradient at the pooled output (bf16 [B,T2,F2,C], or with gp_ref_layout_f32 the front-end's
+ *                   f32 [B,T2,C*F2] output layout); writes all of g [B,T,F,C] (first maximum of a window gets gp if > 0).
+ *  bias_grad:       db [C] (+)= column sums of g [P,C].
+ *  conv11_bwd:      conv11 (Cin = 1): dw [C,1,3,3], db [C] from x [B,T,F] f32 and g [B,T,F,C]; input rows >= lengths[b]
+ *                   count as zero, like the forward.
+ * workspace: dasv_train_workspace_bytes(C) bytes for bias_grad / conv11_bwd. */
+int dasv_relu_bwd_bf16(void* g, const void* y, size_t n, void* stream);
+int dasv_unpool_relu_bwd_bf16(const void* gp, int gp_ref_layout_f32, const void* y, void* g, int B, int T, int F, int C, void* stream);
+size_t dasv_train_workspace_bytes(int C);
+int dasv_bias_grad_bf16(const void* g, float* db, void* workspace, int accumulate, size_t P, int C, void* stream);
+int dasv_conv11_bwd(const float* x, const void* g, const int32_t* lengths, float* dw, float* db, void* workspace, int accumulate,
+                    int B, int T, int F, int C, void* stream);
 
 /* ---------------------------------------------------------------- embedding tail
  * getEmbedding's FC block, eval mode: b2(relu(fc2(relu(fc1(pooled))))) (scripts/model.py:56-57).

@@ -9,6 +9,16 @@ from doubleattentionspeakerverification_b200 import ops
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    """The torch references in this file must be plain fp32."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def ref_wgrad(x, g):
     """torch fp32 reference: d/dW of conv2d(x, W, padding=1) contracted with g.  x [B,T,F,Cin], g [B,T,F,Cout] (NHWC)."""
     xr = x.float().permute(0, 3, 1, 2).contiguous()
@@ -37,3 +47,147 @@ def test_wgrad_vs_autograd(B, T, F, Cin, Cout):
     dw2 = ops.conv3x3_wgrad(x, g, dw.clone())                    # accumulate
     assert float((dw2 - 2 * want).abs().max() / want.abs().max()) < 4e-4
     assert torch.equal(ops.conv3x3_wgrad(x, g), dw)              # deterministic
+
+
+def test_relu_and_unpool_backward_match_autograd():
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    for (B, T, F, C) in ((2, 7, 10, 64), (1, 6, 8, 16), (3, 5, 20, 128)):
+        pre = torch.randn(B, T, F, C, device='cuda', generator=gen)
+        y = torch.relu(pre).to(torch.bfloat16)
+        T2, F2 = (T + 1) // 2, F // 2
+        gp = torch.randn(B, T2, F2, C, device='cuda', generator=gen).to(torch.bfloat16)
+        # torch reference on the bf16-rounded activation: relu -> pool
+        z = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)          # NCHW, already >= 0
+        out = torch.nn.functional.max_pool2d(torch.relu(z), 2, stride=2, ceil_mode=True)
+        out.backward(gp.float().permute(0, 3, 1, 2))
+        want = z.grad.permute(0, 2, 3, 1)
+        got = ops.unpool_relu_bwd(gp, y)
+        assert torch.equal(got.float(), want.to(torch.bfloat16).float())
+        # the front-end's output layout [B,T2,C*F2] f32
+        gref = gp.float().permute(0, 1, 3, 2).reshape(B, T2, C * F2).contiguous()
+        assert torch.equal(ops.unpool_relu_bwd(gref, y), got)
+        g = torch.randn(B, T, F, C, device='cuda', generator=gen).to(torch.bfloat16)
+        want2 = torch.where(y > 0, g, torch.zeros_like(g))
+        assert torch.equal(ops.relu_bwd_(g.clone(), y), want2)
+        db = ops.bias_grad(g)
+        assert float((db - g.float().sum((0, 1, 2))).abs().max()) < 1e-3 * max(1.0, float(db.abs().max()))
+
+
+def test_conv11_backward_matches_autograd():
+    gen = torch.Generator(device='cuda').manual_seed(4)
+    B, T, F, C = 3, 11, 80, 128
+    x = torch.randn(B, T, F, device='cuda', generator=gen)
+    g = torch.randn(B, T, F, C, device='cuda', generator=gen).to(torch.bfloat16)
+    lengths = torch.tensor([11, 7, 1], device='cuda', dtype=torch.int32)
+    t = torch.arange(T, device='cuda')[None, :, None]
+    for L in (None, lengths):
+        xm = x if L is None else torch.where(t < L[:, None, None], x, torch.zeros_like(x))   # the forward treats rows >= L as zero
+        w = torch.zeros((C, 1, 3, 3), device='cuda', requires_grad=True)
+        b = torch.zeros((C,), device='cuda', requires_grad=True)
+        y = torch.nn.functional.conv2d(xm[:, None], w, b, padding=1)
+        (y * g.float().permute(0, 3, 1, 2)).sum().backward()
+        dw, db = ops.conv11_bwd(x, g, L)
+        assert float((dw - w.grad).abs().max() / w.grad.abs().max()) < 1e-4
+        assert float((db - b.grad).abs().max() / b.grad.abs().max()) < 1e-4
+
+
+def _grad_stats(a, b):
+    a, b = a.flatten().double(), b.flatten().double()
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    rel = float((a - b).norm() / b.norm())
+    return cos, rel
+
+
+class _ReLUWithGivenOutput(torch.autograd.Function):
+    """relu whose forward VALUE and backward MASK come from a given activation (the kernels' own bf16 ReLU output)."""
+
+    @staticmethod
+    def forward(ctx, z, y):
+        ctx.save_for_backward(y)
+        return y.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return g * (y > 0).to(g.dtype), None
+
+
+def _reference_backward(net, x, acts, gout):
+    """torch fp32 autograd of the front-end, evaluated AT the kernels' activations: every conv is differentiated by torch
+    (fp32, the bf16-rounded weights the tensor-core layers use), while the ReLU masks and pooling arg-max decisions are
+    taken from the kernels' saved ReLU outputs.  (Decisions made on an independently computed forward differ wherever two
+    candidates are within a bf16 ulp, and each such flip moves a whole gradient entry: that measures the forward's
+    rounding, not the backward's arithmetic.)"""
+    F = torch.nn.functional
+    h = x.view(x.size(0), x.size(1), 1, x.size(2)).transpose(1, 2)
+    for i, name in enumerate(net._names):
+        c = getattr(net, name)
+        w = c.weight if i == 0 else c.weight + (c.weight.to(torch.bfloat16).float() - c.weight).detach()
+        z = F.conv2d(h, w, c.bias, padding=1)
+        h = _ReLUWithGivenOutput.apply(z, acts[i].float().permute(0, 3, 1, 2).contiguous())
+        if i % 2 == 1:
+            h = F.max_pool2d(h, 2, stride=2, ceil_mode=True)
+    h = h.transpose(1, 2)
+    feat = h.contiguous().view(h.size(0), h.size(1), h.size(2) * h.size(3))
+    (feat * gout).sum().backward()
+    return feat.detach()
+
+
+@pytest.mark.parametrize('cls,ks', [('VGG4L', 512), ('VGG3L', 256)])
+def test_front_end_training_on_kernels_matches_autograd(cls, ks):
+    """train_kernels=True: forward + backward of the whole front-end on this package's kernels.  Forward against the
+    module's torch/cuDNN fp32 path; backward against torch fp32 autograd evaluated at the same activations."""
+    from doubleattentionspeakerverification_b200 import CNNs
+    torch.manual_seed(0)
+    net = getattr(CNNs, cls)(ks, precision='bf16', train_kernels=True).cuda()
+    B, T = 3, 44
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn(B, T, 80, device='cuda', generator=gen) * 2
+    feat = net(x)
+    assert feat.requires_grad and feat.dtype == torch.float32
+    gout = torch.randn(feat.shape, device='cuda', generator=gen)
+    (feat * gout).sum().backward()
+    got = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad()
+    with torch.no_grad():
+        _, acts, _, _ = CNNs._VGGTrainFn.run_forward(net, x, None)
+    ref_feat = _reference_backward(net, x, acts, gout)
+    assert torch.equal(ref_feat, feat.detach())                  # same activations by construction
+    stats = {n: _grad_stats(got[n], p.grad) for n, p in net.named_parameters()}
+    for n, (cos, rel) in stats.items():
+        assert cos > 0.9999 and rel < 1.5e-2, (n, stats)         # bf16 gradients between the layers
+    # the plain fp32 path (the reference's training arithmetic): same features to bf16 accuracy, gradients as close as
+    # independently rounded ReLU / arg-max decisions allow
+    net.zero_grad()
+    net.train_kernels = False
+    plain = net(x)
+    (plain * gout).sum().backward()
+    cosf, relf = _grad_stats(feat.detach(), plain.detach())
+    assert cosf > 0.9999 and relf < 1.5e-2, (cosf, relf)
+    for n, p in net.named_parameters():
+        assert _grad_stats(got[n], p.grad)[0] > 0.95, n
+
+
+def test_front_end_training_with_lengths_equals_per_utterance_runs():
+    from doubleattentionspeakerverification_b200 import CNNs
+    torch.manual_seed(1)
+    net = CNNs.VGG4L(512, precision='bf16', train_kernels=True).cuda()
+    gen = torch.Generator(device='cuda').manual_seed(2)
+    lengths = [40, 23]
+    x = torch.randn(2, 40, 80, device='cuda', generator=gen)
+    x[1, 23:] = 5.0                                               # padding content must not matter
+    feat = net(x, lengths=torch.tensor(lengths))
+    gout = torch.randn(feat.shape, device='cuda', generator=gen)
+    Lout = [int(v) for v in net.output_lengths(torch.tensor(lengths))]
+    for b, Lo in enumerate(Lout):
+        gout[b, Lo:] = 0                                          # rows past the utterance carry no loss
+    (feat * gout).sum().backward()
+    got = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad()
+    for b, Lb in enumerate(lengths):
+        fb = net(x[b:b + 1, :Lb].contiguous())
+        assert float((fb.detach() - feat.detach()[b:b + 1, :Lout[b]]).abs().max()) == 0.0
+        (fb * gout[b:b + 1, :Lout[b]]).sum().backward()
+    for n, p in net.named_parameters():
+        cos, rel = _grad_stats(got[n], p.grad)
+        assert cos > 0.99999 and rel < 2e-3, (n, cos, rel)
