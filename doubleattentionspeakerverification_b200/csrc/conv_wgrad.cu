@@ -32,7 +32,7 @@ namespace dasv {
 
 constexpr int kWgThreads = 256;      // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
 constexpr int kWgM = 128;            // output channels per tile (TMEM lanes)
-constexpr int kWgN = 32;             // input channels per tile
+constexpr int kWgNMax = 64;          // input channels per tile: 32 (all nine taps in TMEM) or 64 (taps in two groups, 5 + 4)
 constexpr uint32_t kWgTmemCols = 512;
 
 struct WgradParams {
@@ -40,6 +40,7 @@ struct WgradParams {
     int B, T, F, Cin, Cout;
     int BT, n_tt, n_items, items_per_split, splits;
     int n_mt, n_nt;
+    int N, tg, ng;                   // input channels per tile, taps per group, tap groups
     int rowsG, K16, rowsX;
     uint32_t g_box_bytes;            // bytes one G box delivers (rowsG * 128)
     uint32_t g_alloc;                // K16 * 128
@@ -60,6 +61,7 @@ DASV_DEVICE uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
     return d;
 }
 
+template <int TG>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -73,8 +75,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pairs = p.n_mt * p.n_nt;
-    const int pair = static_cast<int>(blockIdx.x) % pairs, split = static_cast<int>(blockIdx.x) / pairs;
+    const int pair = static_cast<int>(blockIdx.x) % pairs;
+    const int grp = (static_cast<int>(blockIdx.x) / pairs) % p.ng, split = static_cast<int>(blockIdx.x) / (pairs * p.ng);
     const int m = pair % p.n_mt, n = pair / p.n_mt;
+    const int tap0 = grp * p.tg, tap1 = min(tap0 + p.tg, 9);
+    const int N = p.N;
+    const int xc0 = (N == 64) ? n * 64 : (n >> 1) * 64;              // first channel of the X box
+    const uint32_t xhalf = (N == 64) ? 0u : static_cast<uint32_t>(n & 1) * 64u;
     const int item0 = split * p.items_per_split;
     const int item1 = min(item0 + p.items_per_split, p.n_items);
 
@@ -108,29 +115,40 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 mbar_arrive_expect_tx(&full[st], 2 * p.g_box_bytes + p.x_box_bytes);
                 tma_load_4d(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
                 tma_load_4d(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
-                tma_load_4d(sb + p.x_off, &tmX, &full[st], (n >> 1) * 64, -1, t0 - 1, b);
+                tma_load_4d(sb + p.x_off, &tmX, &full[st], xc0, -1, t0 - 1, b);
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                            // MMA issuer
-            const uint32_t idesc = umma_idesc_bf16(kWgM, kWgN) | (1u << 15) | (1u << 16);     // A and B MN-major
+            const uint32_t idesc = umma_idesc_bf16(kWgM, static_cast<uint32_t>(N)) | (1u << 15) | (1u << 16);   // A and B MN-major
+            // one thread issues every MMA, so the loop must cost only a few instructions per MMA: descriptors are advanced
+            // by adding row offsets (in 16-byte units) to the 64-bit value, taps are unrolled
             const int frow = p.F + 2;
+            long long toff[TG];
+#pragma unroll
+            for (int j = 0; j < TG; ++j) {
+                const int tap = min(tap0 + j, 8);
+                toff[j] = static_cast<long long>((tap / 3) * frow + (tap % 3) - 1) * 8;          // rows * 128 B >> 4; -1 lands on the guard row
+            }
+            const int ntaps = tap1 - tap0;
             int st = 0;
             uint32_t ph = 0;
+            uint32_t acc = 0;
             for (int it = item0; it < item1; ++it) {
                 mbar_wait(&full[st], ph);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
-                const uint32_t xb = sb + p.x_off + static_cast<uint32_t>(n & 1) * 64u;
+                uint64_t a_desc = umma_desc_mn128(sb, p.g_alloc);
+                uint64_t b_desc = umma_desc_mn128(sb + p.x_off + xhalf, 16);
                 for (int k = 0; k < p.K16; k += 16) {
-                    const uint64_t a_desc = umma_desc_mn128(sb + static_cast<uint32_t>(k) * 128u, p.g_alloc);
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int shift = (tap / 3) * frow + (tap % 3) - 1;                      // rows; -1 lands on the guard row
-                        const uint64_t b_desc = umma_desc_mn128(xb + static_cast<uint32_t>((k + shift) * 128), 16);
-                        umma_bf16(tmem_base + static_cast<uint32_t>(tap * kWgN), a_desc, b_desc, idesc, (it > item0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int j = 0; j < TG; ++j)
+                        if (j < ntaps)
+                            umma_bf16(tmem_base + static_cast<uint32_t>(j * N), a_desc, b_desc + static_cast<uint64_t>(toff[j]), idesc, acc);
+                    acc = 1u;
+                    a_desc += 16 * 8;                   // 16 rows of 128 B
+                    b_desc += 16 * 8;
                 }
                 umma_commit(&empty[st]);            // frees the stage when the MMAs above have read it
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
@@ -146,21 +164,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             tc_fence_after();
         }
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-            uint32_t r[32];
-            if (item1 > item0) {
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tap * kWgN), r);
-                tc_wait_ld();
-            } else {
+        for (int tap = tap0; tap < tap1; ++tap) {
+#pragma unroll 1
+            for (int c32 = 0; c32 < N; c32 += 32) {
+                uint32_t r[32];
+                if (item1 > item0) {
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((tap - tap0) * N + c32), r);
+                    tc_wait_ld();
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            if (co < p.Cout) {
-                float4* dst = reinterpret_cast<float4*>(p.ws + ((static_cast<size_t>(split) * 9 + tap) * p.Cout + co) * p.Cin + n * kWgN);
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                if (co < p.Cout) {
+                    float4* dst = reinterpret_cast<float4*>(p.ws + ((static_cast<size_t>(split) * 9 + tap) * p.Cout + co) * p.Cin + n * N + c32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                         __uint_as_float(r[4 * j + 3]));
+                    for (int j = 0; j < 8; ++j)
+                        dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                             __uint_as_float(r[4 * j + 3]));
+                }
             }
         }
         tc_fence_before();
@@ -200,7 +221,7 @@ static WgEncodeTiledFn wg_encode_tiled() {
 }
 
 struct WgradPlan {
-    int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, rowsG, K16, rowsX, stages;
+    int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, N, tg, ng, rowsG, K16, rowsX, stages;
     uint32_t g_alloc, x_off, stage_bytes;
     size_t smem;
 };
@@ -229,8 +250,14 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     pl.n_tt = (T + pl.BT - 1) / pl.BT;
     pl.n_items = B * pl.n_tt;
     pl.n_mt = (Cout + kWgM - 1) / kWgM;
-    pl.n_nt = Cin / kWgN;
-    const int pairs = pl.n_mt * pl.n_nt;
+    // 64 input channels per tile with the taps in two groups (5 + 4, 320 TMEM columns) halves the A re-reads per FLOP
+    // at the price of loading every tile twice; 32 channels keep all nine taps in one CTA
+    pl.N = 64;
+    if (const char* e = getenv("DASV_WGRAD_N")) { const int v = atoi(e); if (v == 32 || v == 64) pl.N = v; }
+    pl.tg = pl.N == 64 ? 5 : 9;
+    pl.ng = pl.N == 64 ? 2 : 1;
+    pl.n_nt = Cin / pl.N;
+    const int pairs = pl.n_mt * pl.n_nt * pl.ng;
     // split-K factor: fill the SMs in whole waves, keep >= 2 items per CTA, bound the workspace
     int best = 1;
     double best_eff = 0.0;
@@ -295,17 +322,18 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     p.ws = static_cast<float*>(workspace);
     p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.Cout = Cout;
     p.BT = pl.BT; p.n_tt = pl.n_tt; p.n_items = pl.n_items; p.items_per_split = pl.items_per_split; p.splits = pl.splits;
-    p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.rowsG = pl.rowsG; p.K16 = pl.K16; p.rowsX = pl.rowsX;
+    p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.N = pl.N; p.tg = pl.tg; p.ng = pl.ng; p.rowsG = pl.rowsG; p.K16 = pl.K16; p.rowsX = pl.rowsX;
     p.g_box_bytes = static_cast<uint32_t>(pl.rowsG) * 128u; p.g_alloc = pl.g_alloc;
     p.x_box_bytes = static_cast<uint32_t>(pl.rowsX) * 128u; p.x_off = pl.x_off;
     p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
     if (getenv("DASV_CONV_DEBUG"))
-        fprintf(stderr, "wgrad plan: B=%d T=%d F=%d Cin=%d Cout=%d BT=%d rowsG=%d K16=%d rowsX=%d stages=%d stage_bytes=%u items=%d splits=%d\n",
-                B, T, F, Cin, Cout, pl.BT, pl.rowsG, pl.K16, pl.rowsX, pl.stages, pl.stage_bytes, pl.n_items, pl.splits);
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
+        fprintf(stderr, "wgrad plan: B=%d T=%d F=%d Cin=%d Cout=%d BT=%d rowsG=%d K16=%d rowsX=%d stages=%d stage_bytes=%u items=%d splits=%d N=%d\n",
+                B, T, F, Cin, Cout, pl.BT, pl.rowsG, pl.K16, pl.rowsX, pl.stages, pl.stage_bytes, pl.n_items, pl.splits, pl.N);
+    auto kern = pl.tg == 5 ? conv_wgrad_kernel<5> : conv_wgrad_kernel<9>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     if (e != cudaSuccess) { set_error("conv3x3_wgrad_bf16: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return 1; }
-    const int grid = pl.n_mt * pl.n_nt * pl.splits;
-    conv_wgrad_kernel<<<grid, kWgThreads, pl.smem, s>>>(tmG, tmX, p);
+    const int grid = pl.n_mt * pl.n_nt * pl.ng * pl.splits;
+    kern<<<grid, kWgThreads, pl.smem, s>>>(tmG, tmX, p);
     if (check_launch("conv3x3_wgrad_bf16")) return 1;
     const size_t n = static_cast<size_t>(Cout) * Cin;
     conv_wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p.ws, dw, pl.splits, Cout, Cin, accumulate);
