@@ -33,7 +33,8 @@ SIGNATURES = {
     'dasv_conv3x3_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_relu_bwd_bf16': (_i, [_vp, _vp, _sz, _vp]),
     'dasv_unpool_relu_bwd_bf16': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'dasv_train_workspace_bytes': (_sz, [_i]),
+    'dasv_bias_grad_workspace_bytes': (_sz, [_i]),
+    'dasv_conv11_bwd_workspace_bytes': (_sz, [_i, _i, _i]),
     'dasv_bias_grad_bf16': (_i, [_vp, _vp, _vp, _i, _sz, _i, _vp]),
     'dasv_conv11_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_fc_tail_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

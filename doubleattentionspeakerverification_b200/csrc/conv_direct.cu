@@ -237,6 +237,34 @@ __global__ void maxpool2x2_kernel(const TI* __restrict__ x, TO* __restrict__ y, 
     }
 }
 
+// bf16 NHWC -> bf16 NHWC, 8 channels (16 bytes) per thread, packed bf16x2 maxima: the training forward's pool
+__global__ void maxpool2x2_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int T, int F, int C8) {
+    const int T2 = (T + 1) / 2, F2 = (F + 1) / 2;
+    const size_t n = static_cast<size_t>(B) * T2 * F2 * C8;
+    const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C8);
+        size_t r = i / C8;
+        const int f2 = static_cast<int>(r % F2); r /= F2;
+        const int t2 = static_cast<int>(r % T2);
+        const int b = static_cast<int>(r / T2);
+        __nv_bfloat162 m[4] = {ninf, ninf, ninf, ninf};
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+            for (int df = 0; df < 2; ++df) {
+                const int t = 2 * t2 + dt, f = 2 * f2 + df;
+                if (t < T && f < F) {
+                    const uint4 v = x[((static_cast<size_t>(b) * T + t) * F + f) * C8 + c];
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], h[k]);
+                }
+            }
+        y[i] = *reinterpret_cast<const uint4*>(m);
+    }
+}
+
 }  // namespace dasv
 
 using namespace dasv;
@@ -301,6 +329,8 @@ extern "C" int dasv_maxpool2x2(const void* x, int x_dtype, void* y, int y_dtype,
 #define DASV_POOL(TI, TO, REF) \
     maxpool2x2_kernel<TI, TO, REF><<<grid, 256, 0, s>>>(static_cast<const TI*>(x), static_cast<TO*>(y), B, T, F, C)
     if (x_dtype == 0 && y_dtype == 0) { if (ref_layout) DASV_POOL(float, float, true); else DASV_POOL(float, float, false); }
+    else if (x_dtype == 1 && y_dtype == 1 && !ref_layout && C % 8 == 0)
+        maxpool2x2_bf16x8_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), B, T, F, C / 8);
     else if (x_dtype == 1 && y_dtype == 1) { if (ref_layout) DASV_POOL(__nv_bfloat16, __nv_bfloat16, true); else DASV_POOL(__nv_bfloat16, __nv_bfloat16, false); }
     else if (x_dtype == 1 && y_dtype == 0) { if (ref_layout) DASV_POOL(__nv_bfloat16, float, true); else DASV_POOL(__nv_bfloat16, float, false); }
     else { set_error("maxpool2x2: unsupported dtype pair %d -> %d", x_dtype, y_dtype); return 1; }

@@ -117,59 +117,90 @@ __global__ void slab_reduce_kernel(const float* part, float* out, int slabs, int
 }
 
 // ---------------------------------------------------------------------------------- conv11 backward (Cin = 1)
-// dw[co][ky][kx] = sum_p g[p][co] * x[p + tap],  db[co] = sum_p g[p][co];  x [B,T,F] f32, g [B,T,F,C] bf16, C <= 128 per
-// grid.y slice.  One CTA per slab of frames; thread = (channel pair, row phase); partial [slab][10][C].
+// dw[co][ky][kx] = sum_p g[p][co] * x[p + tap],  db[co] = sum_p g[p][co];  x [B,T,F] f32, g [B,T,F,C] bf16, 128 channels per
+// grid.y slice.  One CTA per slab of frames of ONE utterance: the slab's input rows (+-1 halo, rows >= L and the border
+// columns as zeros) are staged in shared memory; thread = (8 channels, one of 16 pixel phases): one 16-byte load of g per
+// pixel feeds 72 FMAs.  Partial [slab][10][C], fixed-order reduce.
+constexpr int kC11BwdRows = 8;
 __global__ void __launch_bounds__(kColThreads) conv11_bwd_partial_kernel(const float* x, const __nv_bfloat16* g, const int32_t* lengths,
-                                                                         float* part, int B, int T, int F, int C, int frames_per_slab) {
-    __shared__ float red[4][10][128];
-    const int cp = threadIdx.x & 63, ph = threadIdx.x >> 6;
-    const int c0 = blockIdx.y * 128 + cp * 2;
-    const long long fr0 = static_cast<long long>(blockIdx.x) * frames_per_slab;            // flattened (b, t)
-    const long long fr1 = min(fr0 + frames_per_slab, static_cast<long long>(B) * T);
-    float a0[10], a1[10];
+                                                                         float* part, int B, int T, int F, int C, int chunks) {
+    extern __shared__ float c11_sm[];
+    float* xs = c11_sm;                                         // [kC11BwdRows + 2][F + 2]
+    float* red = c11_sm + (kC11BwdRows + 2) * (F + 2);          // [8 warps][10][128]
+    const int b = blockIdx.x / chunks, t0 = (blockIdx.x % chunks) * kC11BwdRows;
+    const int rows = min(kC11BwdRows, T - t0);
+    const int L = lengths ? min(max(lengths[b], 0), T) : T;
+    const int W2 = F + 2;
+    for (int i = threadIdx.x; i < (kC11BwdRows + 2) * W2; i += kColThreads) {
+        const int r = i / W2, fc = i - r * W2;
+        const int tt = t0 + r - 1, ff = fc - 1;
+        xs[i] = (tt >= 0 && tt < L && ff >= 0 && ff < F) ? x[(static_cast<size_t>(b) * T + tt) * F + ff] : 0.f;   // rows >= L count as zero
+    }
+    __syncthreads();
+    const int c8 = threadIdx.x & 15, ph = threadIdx.x >> 4;
+    const int c0 = blockIdx.y * 128 + c8 * 8;
+    float acc[10][8];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
     if (c0 < C)
-        for (long long fr = fr0; fr < fr1; ++fr) {
-            const int t = static_cast<int>(fr % T);
-            const int L = lengths ? min(max(lengths[fr / T], 0), T) : T;                   // input rows >= L count as zero (forward rule)
-            const float* xb = x + (fr - t) * F;                                             // utterance base
-            for (int f = ph; f < F; f += 4) {
-                const uint32_t v = *reinterpret_cast<const uint32_t*>(g + (static_cast<size_t>(fr) * F + f) * C + c0);
-                if (v == 0u) continue;                                                      // ReLU zeros are common
-                const float g0 = bf16_lo(v), g1 = bf16_hi(v);
+        for (int p = ph; p < rows * F; p += 16) {
+            const int tl = p / F, f = p - tl * F;
+            const uint4 v = *reinterpret_cast<const uint4*>(g + ((static_cast<size_t>(b) * T + t0 + tl) * F + f) * C + c0);
+            if ((v.x | v.y | v.z | v.w) == 0u) continue;        // ReLU zeros are common
+            float gv[8];
+            gv[0] = bf16_lo(v.x); gv[1] = bf16_hi(v.x); gv[2] = bf16_lo(v.y); gv[3] = bf16_hi(v.y);
+            gv[4] = bf16_lo(v.z); gv[5] = bf16_hi(v.z); gv[6] = bf16_lo(v.w); gv[7] = bf16_hi(v.w);
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const int tt = t + dy - 1;
+            for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int ff = f + dx - 1;
-                        const float xv = (tt >= 0 && tt < L && ff >= 0 && ff < F) ? xb[static_cast<size_t>(tt) * F + ff] : 0.f;
-                        a0[dy * 3 + dx] = fmaf(g0, xv, a0[dy * 3 + dx]);
-                        a1[dy * 3 + dx] = fmaf(g1, xv, a1[dy * 3 + dx]);
-                    }
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float xv = xs[(tl + dy) * W2 + f + dx];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[dy * 3 + dx][e] = fmaf(gv[e], xv, acc[dy * 3 + dx][e]);
                 }
-                a0[9] += g0; a1[9] += g1;
-            }
-        }
 #pragma unroll
-    for (int k = 0; k < 10; ++k) { red[ph][k][cp * 2] = a0[k]; red[ph][k][cp * 2 + 1] = a1[k]; }
+            for (int e = 0; e < 8; ++e) acc[9][e] += gv[e];
+        }
+    // the two phases of a warp (lanes l and l + 16), then the 8 warps through shared memory
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float s = acc[k][e] + __shfl_xor_sync(0xffffffffu, acc[k][e], 16);
+            if (lane < 16) red[(warp * 10 + k) * 128 + c8 * 8 + e] = s;
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < 10 * 128; i += kColThreads) {
         const int k = i / 128, c = i % 128;
-        if (blockIdx.y * 128 + c < C)
-            part[(static_cast<size_t>(blockIdx.x) * 10 + k) * C + blockIdx.y * 128 + c] = (red[0][k][c] + red[1][k][c]) + (red[2][k][c] + red[3][k][c]);
+        if (blockIdx.y * 128 + c < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[(w * 10 + k) * 128 + c];
+            part[(static_cast<size_t>(blockIdx.x) * 10 + k) * C + blockIdx.y * 128 + c] = s;
+        }
     }
 }
-// partial [slab][10][C] -> dw [C][9], db [C]
-__global__ void conv11_bwd_reduce_kernel(const float* part, float* dw, float* db, int slabs, int C, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (k, c)
-    if (i >= 10 * C) return;
-    const int k = i / C, c = i % C;
+// partial [slab][10][C] -> dw [C][9], db [C]; 32 outputs x 8 slab phases per block, fixed summation order
+__global__ void __launch_bounds__(256) conv11_bwd_reduce_kernel(const float* part, float* dw, float* db, int slabs, int C, int accumulate) {
+    __shared__ float red[8][32];
+    const int o = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + o;                          // (k, c)
     float s = 0.f;
-    for (int sl = 0; sl < slabs; ++sl) s += part[static_cast<size_t>(sl) * 10 * C + i];
-    float* d = k < 9 ? dw + c * 9 + k : db + c;
-    *d = accumulate ? *d + s : s;
+    if (i < 10 * C)
+        for (int sl = ph; sl < slabs; sl += 8) s += part[static_cast<size_t>(sl) * 10 * C + i];
+    red[ph][o] = s;
+    __syncthreads();
+    if (ph == 0 && i < 10 * C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][o];
+        const int k = i / C, c = i % C;
+        float* d = k < 9 ? dw + c * 9 + k : db + c;
+        *d = accumulate ? *d + t : t;
+    }
 }
 
 static int grid_for(size_t n, int threads) {
@@ -203,8 +234,10 @@ extern "C" int dasv_unpool_relu_bwd_bf16(const void* gp, int gp_ref_layout_f32, 
     return check_launch("unpool_relu_bwd");
 }
 
-// workspace for dasv_bias_grad_bf16 / dasv_conv11_bwd: slabs * 10 * C floats is enough for both
-extern "C" size_t dasv_train_workspace_bytes(int C) { return static_cast<size_t>(148 * 4) * 10 * C * sizeof(float); }
+extern "C" size_t dasv_bias_grad_workspace_bytes(int C) { return static_cast<size_t>(148 * 4) * C * sizeof(float); }
+extern "C" size_t dasv_conv11_bwd_workspace_bytes(int B, int T, int C) {
+    return static_cast<size_t>(B > 0 ? B : 0) * ((T + kC11BwdRows - 1) / kC11BwdRows) * 10 * C * sizeof(float);
+}
 
 extern "C" int dasv_bias_grad_bf16(const void* g, float* db, void* workspace, int accumulate, size_t P, int C, void* stream) {
     if (!g || !db || !workspace) { set_error("bias_grad: null pointer"); return 1; }
@@ -225,13 +258,16 @@ extern "C" int dasv_conv11_bwd(const float* x, const void* g, const int32_t* len
     if (!x || !g || !dw || !db || !workspace) { set_error("conv11_bwd: null pointer"); return 1; }
     if (C % 2 != 0) { set_error("conv11_bwd: C must be even"); return 1; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const long long frames = static_cast<long long>(B) * T;
-    if (frames <= 0) return 0;
-    int slabs = static_cast<int>(frames < 148 * 4 ? frames : 148 * 4);
-    const int fps = static_cast<int>((frames + slabs - 1) / slabs);
-    slabs = static_cast<int>((frames + fps - 1) / fps);
-    conv11_bwd_partial_kernel<<<dim3(slabs, (C + 127) / 128), kColThreads, 0, s>>>(x, static_cast<const __nv_bfloat16*>(g), lengths, static_cast<float*>(workspace), B, T, F, C, fps);
+    if (B <= 0 || T <= 0) return 0;
+    if (C % 8 != 0) { set_error("conv11_bwd: C must be a multiple of 8"); return 1; }
+    const int chunks = (T + kC11BwdRows - 1) / kC11BwdRows;
+    const long long slabs_ll = static_cast<long long>(B) * chunks;
+    const size_t smem = (static_cast<size_t>(kC11BwdRows + 2) * (F + 2) + 8 * 10 * 128) * sizeof(float);
+    if (smem > 200 * 1024 || slabs_ll > 0x7fffffffLL) { set_error("conv11_bwd: shape too large (F=%d)", F); return 1; }
+    const int slabs = static_cast<int>(slabs_ll);
+    cudaFuncSetAttribute(conv11_bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    conv11_bwd_partial_kernel<<<dim3(slabs, (C + 127) / 128), kColThreads, smem, s>>>(x, static_cast<const __nv_bfloat16*>(g), lengths, static_cast<float*>(workspace), B, T, F, C, chunks);
     if (check_launch("conv11_bwd")) return 1;
-    conv11_bwd_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, s>>>(static_cast<const float*>(workspace), dw, db, slabs, C, accumulate);
+    conv11_bwd_reduce_kernel<<<(10 * C + 31) / 32, 256, 0, s>>>(static_cast<const float*>(workspace), dw, db, slabs, C, accumulate);
     return check_launch("conv11_bwd_reduce");
 }

@@ -353,10 +353,6 @@ def unpool_relu_bwd(gp, y):
     return g
 
 
-def _train_ws(dev, C):
-    return torch.empty((int(_lib.lib().dasv_train_workspace_bytes(C)),), device=dev, dtype=torch.uint8)
-
-
 def bias_grad(g):
     """Column sums of g [..., C] bf16 -> f32 [C]."""
     _dev(g, 'g')
@@ -364,7 +360,7 @@ def bias_grad(g):
     C = g.shape[-1]
     with torch.cuda.device(g.device):
         db = torch.empty((C,), device=g.device, dtype=torch.float32)
-        ws = _train_ws(g.device, C)
+        ws = torch.empty((int(_lib.lib().dasv_bias_grad_workspace_bytes(C)),), device=g.device, dtype=torch.uint8)
         _lib.check(_lib.lib().dasv_bias_grad_bf16(_p(g), _p(db), _p(ws), 0, g.numel() // C, C, _stream()), 'dasv_bias_grad_bf16')
     return db
 
@@ -379,6 +375,6 @@ def conv11_bwd(x, g, lengths=None):
         lengths = _lengths(lengths, B, g.device)
         dw = torch.empty((C, 1, 3, 3), device=g.device, dtype=torch.float32)
         db = torch.empty((C,), device=g.device, dtype=torch.float32)
-        ws = _train_ws(g.device, C)
+        ws = torch.empty((max(int(_lib.lib().dasv_conv11_bwd_workspace_bytes(B, T, C)), 16),), device=g.device, dtype=torch.uint8)
         _lib.check(_lib.lib().dasv_conv11_bwd(_p(x), _p(g), _p(lengths), _p(dw), _p(db), _p(ws), 0, B, T, Fq, C, _stream()), 'dasv_conv11_bwd')
     return dw, db

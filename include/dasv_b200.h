@@ -152,10 +152,11 @@ int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, void* works
  *  bias_grad:       db [C] (+)= column sums of g [P,C].
  *  conv11_bwd:      conv11 (Cin = 1): dw [C,1,3,3], db [C] from x [B,T,F] f32 and g [B,T,F,C]; input rows >= lengths[b]
  *                   count as zero, like the forward.
- * workspace: dasv_train_workspace_bytes(C) bytes for bias_grad / conv11_bwd. */
+ * workspaces: dasv_bias_grad_workspace_bytes(C), dasv_conv11_bwd_workspace_bytes(B, T, C). */
 int dasv_relu_bwd_bf16(void* g, const void* y, size_t n, void* stream);
 int dasv_unpool_relu_bwd_bf16(const void* gp, int gp_ref_layout_f32, const void* y, void* g, int B, int T, int F, int C, void* stream);
-size_t dasv_train_workspace_bytes(int C);
+size_t dasv_bias_grad_workspace_bytes(int C);
+size_t dasv_conv11_bwd_workspace_bytes(int B, int T, int C);
 int dasv_bias_grad_bf16(const void* g, float* db, void* workspace, int accumulate, size_t P, int C, void* stream);
 int dasv_conv11_bwd(const float* x, const void* g, const int32_t* lengths, float* dw, float* db, void* workspace, int accumulate,
                     int B, int T, int F, int C, void* stream);
