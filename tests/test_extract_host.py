@@ -93,3 +93,36 @@ def _free_port():
 def test_world2_gloo_allgather_restores_order():
     for n in (11, 1):      # odd count (uneven shards) and fewer utterances than ranks (an empty shard)
         mp.spawn(_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+
+
+def _train_worker(rank, world, port):
+    """Two ranks, uneven shards of one batch: all-reduced gradients == the single-process gradient of the batch-mean loss."""
+    from doubleattentionspeakerverification_b200 import train_utils
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+        if rank == 1:
+            for p in net.parameters():
+                p.data.add_(1.0)                                 # ranks start out different ...
+        train_utils.broadcast_parameters(net)                      # ... until rank 0's values are broadcast
+        x = torch.randn(7, 6, generator=torch.Generator().manual_seed(1))
+        y = torch.randn(7, 3, generator=torch.Generator().manual_seed(2))
+        sl = train_utils.shard_batch(7)
+        assert (sl.start, sl.stop) == ((0, 4) if rank == 0 else (4, 7))
+        loss = ((net(x[sl]) - y[sl]) ** 2).sum(1).mean()
+        loss.backward()
+        train_utils.allreduce_gradients(list(net.parameters()), bucket_bytes=64, local_weight=(sl.stop - sl.start) / 7.0)
+        got = [p.grad.clone() for p in net.parameters()]
+        net.zero_grad()
+        ((net(x) - y) ** 2).sum(1).mean().backward()
+        for g, p in zip(got, net.parameters()):
+            assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-6)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_gradient_allreduce_equals_global_batch():
+    mp.spawn(_train_worker, args=(2, _free_port()), nprocs=2, join=True)
