@@ -45,6 +45,7 @@ struct WgradParams {
     uint32_t g_box_bytes;            // bytes one G box delivers (rowsG * 128)
     uint32_t g_alloc;                // K16 * 128
     uint32_t x_box_bytes, x_off;     // X patch inside a stage: x_off = 2 * g_alloc + 1024 (a guard row precedes the patch)
+    uint32_t x_stride;               // N = 128: distance between the two 64-channel X boxes
     uint32_t stage_bytes;
     int stages;
 };
@@ -80,8 +81,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int m = pair % p.n_mt, n = pair / p.n_mt;
     const int tap0 = grp * p.tg, tap1 = min(tap0 + p.tg, 9);
     const int N = p.N;
-    const int xc0 = (N == 64) ? n * 64 : (n >> 1) * 64;              // first channel of the X box
-    const uint32_t xhalf = (N == 64) ? 0u : static_cast<uint32_t>(n & 1) * 64u;
+    const int xc0 = (N == 32) ? (n >> 1) * 64 : n * N;               // first channel of the X box(es)
+    const uint32_t xhalf = (N == 32) ? static_cast<uint32_t>(n & 1) * 64u : 0u;
+    const int xboxes = N == 128 ? 2 : 1;
     const int item0 = split * p.items_per_split;
     const int item1 = min(item0 + p.items_per_split, p.n_items);
 
@@ -112,10 +114,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 const int b = it / p.n_tt, t0 = (it % p.n_tt) * p.BT;
                 mbar_wait(&empty[st], ph ^ 1u);
                 unsigned char* sb = ring + static_cast<size_t>(st) * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[st], 2 * p.g_box_bytes + p.x_box_bytes);
+                mbar_arrive_expect_tx(&full[st], 2 * p.g_box_bytes + xboxes * p.x_box_bytes);
                 tma_load_4d(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
                 tma_load_4d(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
                 tma_load_4d(sb + p.x_off, &tmX, &full[st], xc0, -1, t0 - 1, b);
+                if (xboxes == 2) tma_load_4d(sb + p.x_off + p.x_stride, &tmX, &full[st], xc0 + 64, -1, t0 - 1, b);
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
         }
@@ -140,7 +143,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 tc_fence_after();
                 const uint32_t sb = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
                 uint64_t a_desc = umma_desc_mn128(sb, p.g_alloc);
-                uint64_t b_desc = umma_desc_mn128(sb + p.x_off + xhalf, 16);
+                uint64_t b_desc = umma_desc_mn128(sb + p.x_off + xhalf, N == 128 ? p.x_stride : 16u);
                 for (int k = 0; k < p.K16; k += 16) {
 #pragma unroll
                     for (int j = 0; j < TG; ++j)
@@ -222,27 +225,37 @@ static WgEncodeTiledFn wg_encode_tiled() {
 
 struct WgradPlan {
     int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, N, tg, ng, rowsG, K16, rowsX, stages;
-    uint32_t g_alloc, x_off, stage_bytes;
+    uint32_t g_alloc, x_off, x_stride, stage_bytes;
     size_t smem;
 };
 
 static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     WgradPlan pl{};
     if (Cin % 64 != 0 || Cout % 8 != 0 || F < 1 || F + 2 > 256 || T < 1 || B < 1) return pl;
+    // input channels per tile: the operand feed from shared memory (MN-major reads measured at ~64 B/clk) bounds the MMA
+    // rate, and bytes per FLOP fall with N, but 9 taps x N accumulator columns must fit the 512 TMEM columns, so the taps
+    // are split into groups handled by different CTAs (each loads the tiles again): N = 128 / 3 groups, 64 / 2, 32 / 1
+    pl.N = (Cin % 128 == 0) ? 128 : 64;
+    if (const char* e = getenv("DASV_WGRAD_N")) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && Cin % v == 0) pl.N = v; }
+    pl.tg = pl.N == 128 ? 3 : (pl.N == 64 ? 5 : 9);
+    pl.ng = pl.N == 128 ? 3 : (pl.N == 64 ? 2 : 1);
+    const int xboxes = pl.N == 128 ? 2 : 1;
+    const uint32_t avail = 227u * 1024u - 1024u - 256u;
     pl.BT = 176 / (F + 2);
     if (pl.BT < 1) pl.BT = 1;
     if (pl.BT > T) pl.BT = T;
     if (pl.BT + 2 > 256) pl.BT = 254;
-    pl.rowsG = pl.BT * (F + 2);
-    pl.K16 = (pl.rowsG + 15) / 16 * 16;
-    pl.rowsX = (pl.BT + 2) * (F + 2);
-    pl.g_alloc = static_cast<uint32_t>(pl.K16) * 128u;
-    pl.g_alloc = (pl.g_alloc + 1023u) & ~1023u;
-    pl.x_off = 2 * pl.g_alloc + 1024u;
-    // X rows an MMA view may touch: -1 .. K16 - 1 + 2 (F + 2) + 1
-    const uint32_t x_rows = static_cast<uint32_t>(pl.K16 + 2 * (F + 2) + 2);
-    pl.stage_bytes = (pl.x_off + x_rows * 128u + 1023u) & ~1023u;
-    const uint32_t avail = 227u * 1024u - 1024u - 256u;
+    for (;; --pl.BT) {                               // largest frame tile that leaves room for two stages
+        pl.rowsG = pl.BT * (F + 2);
+        pl.K16 = (pl.rowsG + 15) / 16 * 16;
+        pl.rowsX = (pl.BT + 2) * (F + 2);
+        pl.g_alloc = (static_cast<uint32_t>(pl.K16) * 128u + 1023u) & ~1023u;
+        pl.x_off = 2 * pl.g_alloc + 1024u;
+        // X rows an MMA view may touch: -1 .. K16 - 1 + 2 (F + 2) + 1
+        pl.x_stride = ((static_cast<uint32_t>(pl.K16 + 2 * (F + 2) + 2)) * 128u + 1023u) & ~1023u;
+        pl.stage_bytes = pl.x_off + xboxes * pl.x_stride;
+        if (2 * pl.stage_bytes <= avail || pl.BT == 1) break;
+    }
     pl.stages = static_cast<int>(avail / pl.stage_bytes);
     if (pl.stages > 4) pl.stages = 4;
     if (pl.stages < 1) return pl;
@@ -250,12 +263,6 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     pl.n_tt = (T + pl.BT - 1) / pl.BT;
     pl.n_items = B * pl.n_tt;
     pl.n_mt = (Cout + kWgM - 1) / kWgM;
-    // 64 input channels per tile with the taps in two groups (5 + 4, 320 TMEM columns) halves the A re-reads per FLOP
-    // at the price of loading every tile twice; 32 channels keep all nine taps in one CTA
-    pl.N = 64;
-    if (const char* e = getenv("DASV_WGRAD_N")) { const int v = atoi(e); if (v == 32 || v == 64) pl.N = v; }
-    pl.tg = pl.N == 64 ? 5 : 9;
-    pl.ng = pl.N == 64 ? 2 : 1;
     pl.n_nt = Cin / pl.N;
     const int pairs = pl.n_mt * pl.n_nt * pl.ng;
     // split-K factor: fill the SMs in whole waves, keep >= 2 items per CTA, bound the workspace
@@ -324,12 +331,12 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     p.BT = pl.BT; p.n_tt = pl.n_tt; p.n_items = pl.n_items; p.items_per_split = pl.items_per_split; p.splits = pl.splits;
     p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.N = pl.N; p.tg = pl.tg; p.ng = pl.ng; p.rowsG = pl.rowsG; p.K16 = pl.K16; p.rowsX = pl.rowsX;
     p.g_box_bytes = static_cast<uint32_t>(pl.rowsG) * 128u; p.g_alloc = pl.g_alloc;
-    p.x_box_bytes = static_cast<uint32_t>(pl.rowsX) * 128u; p.x_off = pl.x_off;
+    p.x_box_bytes = static_cast<uint32_t>(pl.rowsX) * 128u; p.x_off = pl.x_off; p.x_stride = pl.x_stride;
     p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
     if (getenv("DASV_CONV_DEBUG"))
         fprintf(stderr, "wgrad plan: B=%d T=%d F=%d Cin=%d Cout=%d BT=%d rowsG=%d K16=%d rowsX=%d stages=%d stage_bytes=%u items=%d splits=%d N=%d\n",
                 B, T, F, Cin, Cout, pl.BT, pl.rowsG, pl.K16, pl.rowsX, pl.stages, pl.stage_bytes, pl.n_items, pl.splits, pl.N);
-    auto kern = pl.tg == 5 ? conv_wgrad_kernel<5> : conv_wgrad_kernel<9>;
+    auto kern = pl.tg == 3 ? conv_wgrad_kernel<3> : (pl.tg == 5 ? conv_wgrad_kernel<5> : conv_wgrad_kernel<9>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     if (e != cudaSuccess) { set_error("conv3x3_wgrad_bf16: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return 1; }
     const int grid = pl.n_mt * pl.n_nt * pl.ng * pl.splits;
