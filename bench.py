@@ -166,6 +166,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-dmha', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary measurements (training step, feature extraction)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', '0'))
@@ -342,6 +343,51 @@ def main():
         dmha['peak_gbs'] = pk['hbm_gbs']
         dmha['shape'] = 'B=512 T=200 D=1024 H=16; 2 rotating inputs (each > L2); no alignment output'
 
+    # ---- secondary measurements (not the headline): the rows SURVEY.md §8(f) marks "next"
+    extras = None
+    if not args.no_extras and not args.no_dmha and rank == 0:
+        extras = {}
+        try:
+            from doubleattentionspeakerverification_b200 import CNNs, poolings, featureExtractor as fe
+            torch.cuda.empty_cache()
+            tb = 128
+            tnet = CNNs.VGG4L(1024, precision='bf16', train_kernels=True).to(dev)
+            tpool = poolings.DoubleMHA(5120, 32, mask_prob=0.3).to(dev).train()
+            tx = torch.randn(tb, FRAMES, 80, device=dev) * 2
+
+            def train_step():
+                tnet.zero_grad(set_to_none=True); tpool.zero_grad(set_to_none=True)
+                o, _ = tpool(tnet(tx))
+                o.square().mean().backward()
+            for _ in range(2):
+                train_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                train_step()
+            e1.record(); torch.cuda.synchronize()
+            tms = e0.elapsed_time(e1) / 5
+            extras['train_step'] = {'what': 'VGG4L(1024) + DoubleMHA forward + backward on the package kernels (train_kernels=True), synthetic',
+                                    'batch': tb, 'ms': tms, 'utterances_per_s': tb / tms * 1e3,
+                                    'conv_tflops': 3.0 * sum(conv_flops(tb, FRAMES).values()) / (tms * 1e-3) / 1e12}
+            del tnet, tpool, tx
+            torch.cuda.empty_cache()
+            n = 512 + 160 * (FRAMES - 1)
+            wave = torch.from_numpy(np.stack([synth.make_waveform(n, 16000, seed=i) for i in range(4)] * 64).astype(np.float32)).to(dev)
+            for _ in range(3):
+                fe.logmel_batch(wave, [n] * 256, 16000)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                fe.logmel_batch(wave, [n] * 256, 16000)
+            e1.record(); torch.cuda.synchronize()
+            fms = e0.elapsed_time(e1) / 10
+            extras['logmel'] = {'what': '256 waveforms of %d samples (16 kHz) -> [256,%d,80] log-mel + CMN on the GPU' % (n, FRAMES),
+                                'ms': fms, 'utterances_per_s': 256 / fms * 1e3}
+        except Exception as e:                                   # secondary numbers must never take the headline down
+            extras['error'] = repr(e)[:300]
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, n, el, threads = cpu_reference_rate(15.0)
@@ -359,7 +405,7 @@ def main():
                            'parallelism': 'dp%d' % world, 'l2': 'two rotating input batches; per-step intermediates (>3 GB) exceed the 126 MB L2'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': ms_e2e / args.steps},
-                'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'dmha_microbench': dmha, 'cpu_baseline': cpu}
+                'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'dmha_microbench': dmha, 'extras': extras, 'cpu_baseline': cpu}
         emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
