@@ -221,9 +221,8 @@ class _VGGTrainFn(torch.autograd.Function):
             grads[2 * i2] = ops.conv3x3_wgrad(x2, g)
             grads[2 * i2 + 1] = ops.bias_grad(g)
             c2 = getattr(mod, names[i2])
-            zero_b = torch.zeros((c2.in_channels,), device=g.device, dtype=torch.float32)
-            g = ops.conv3x3_igemm_bf16(g, mod._pack_dgrad(names[i2]), zero_b, c2.in_channels, L, relu=False)
-            g = ops.relu_bwd_(g, x2)                              # gradient at conv_k1's output (before ReLU)
+            # gradient at conv_k1's output (before its ReLU): the ReLU backward is fused into the input-gradient store
+            g = ops.conv3x3_dgrad(g, mod._pack_dgrad(names[i2]), c2.in_channels, L, relu_mask=x2)
             i1 = 2 * blk
             if blk == 0:
                 dw, db = ops.conv11_bwd(x, g, L)
@@ -233,8 +232,7 @@ class _VGGTrainFn(torch.autograd.Function):
                 grads[2 * i1] = ops.conv3x3_wgrad(x1, g)
                 grads[2 * i1 + 1] = ops.bias_grad(g)
                 c1 = getattr(mod, names[i1])
-                zero_b = torch.zeros((c1.in_channels,), device=g.device, dtype=torch.float32)
-                gp = ops.conv3x3_igemm_bf16(g, mod._pack_dgrad(names[i1]), zero_b, c1.in_channels, L, relu=False)
+                gp = ops.conv3x3_dgrad(g, mod._pack_dgrad(names[i1]), c1.in_channels, L)
         ctx.acts = ctx.pooled = None
         return (None, None, None) + tuple(grads)
 

@@ -41,6 +41,7 @@ struct ConvParams {
     int stages;
     int pool, ref_layout, y_f32;
     int relu;                // 0: linear epilogue (input-gradient pass), only without POOL
+    const void* mask;        // optional bf16 tensor shaped like y (NHWC): outputs are zeroed where mask <= 0 (ReLU backward)
     uint32_t b_bytes;        // bytes one B box delivers
     uint32_t stage_bytes;    // per ring-1 stage: A + B(padded) (per-tap mode) or one B patch (tap-row reuse mode)
     uint32_t tmem_cols;
@@ -95,6 +96,13 @@ DASV_DEVICE void tmem_ld_x1(uint32_t taddr, uint32_t& r0) {
 }
 DASV_DEVICE void tmem_ld_x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+
+// 0xFFFF per half where the packed bf16 value is > 0
+DASV_DEVICE uint32_t bf16x2_positive_mask(uint32_t v) {
+    const uint32_t lo = ((v & 0x8000u) == 0u && (v & 0x7FFFu) != 0u) ? 0x0000FFFFu : 0u;
+    const uint32_t hi = ((v & 0x80000000u) == 0u && (v & 0x7FFF0000u) != 0u) ? 0xFFFF0000u : 0u;
+    return lo | hi;
 }
 
 template <bool F32>
@@ -296,7 +304,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tc_fence_after();
                 tcol = tmem_base + lane_addr + as * static_cast<uint32_t>(p.Npad);
             }
-            const float bias = n_ok ? p.bias[n] : 0.f;
+            const float bias = (n_ok && p.bias != nullptr) ? p.bias[n] : 0.f;
 
             if (p.ref_layout) {
                 // pooled[b, t2, n*F2 + f2] = relu(max over the valid 2x2 window + bias)   (feature = c*F' + f, CNNs.py:88-89)
@@ -428,9 +436,13 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 uint4 val = make_uint4(0u, 0u, 0u, 0u);
                                 if (!masked && t_in < conv_len(p, b))
                                     val = *reinterpret_cast<const uint4*>(buf + po * (kConvTileM * 2) + seg * 16);
-                                __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(p.y) +
-                                                    ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c.m * kConvTileM + seg * 8;
-                                *reinterpret_cast<uint4*>(yp) = val;
+                                const size_t yoff = ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c.m * kConvTileM + seg * 8;
+                                if (p.mask != nullptr) {         // fused ReLU backward: keep the gradient where the activation was > 0
+                                    const uint4 mv = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mask) + yoff);
+                                    val.x &= bf16x2_positive_mask(mv.x); val.y &= bf16x2_positive_mask(mv.y);
+                                    val.z &= bf16x2_positive_mask(mv.z); val.w &= bf16x2_positive_mask(mv.w);
+                                }
+                                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.y) + yoff) = val;
                             }
                         }
                     }
@@ -520,10 +532,10 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo, boo
 
 using namespace dasv;
 
-extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, const int32_t* lengths,
-                                       void* y, int y_dtype, int flags,
-                                       int B, int T, int F, int Cin, int Cout, void* stream) {
-    if (!x || !wp || !bias || !y) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
+static int conv_igemm_launch(const void* x, const void* wp, const float* bias, const int32_t* lengths, const void* mask,
+                             void* y, int y_dtype, int flags,
+                             int B, int T, int F, int Cin, int Cout, void* stream) {
+    if (!x || !wp || !y) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
     if (Cin % kConvKC != 0 || Cin <= 0) { set_error("conv3x3_igemm_bf16: Cin=%d must be a positive multiple of 64", Cin); return 1; }
     if (Cout <= 0 || Cout % 8 != 0) { set_error("conv3x3_igemm_bf16: Cout=%d must be a positive multiple of 8", Cout); return 1; }
     if (F <= 0 || F % 2 != 0 || F > 256) { set_error("conv3x3_igemm_bf16: F=%d must be even and <= 256", F); return 1; }
@@ -596,6 +608,7 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
     p.kchunks = Cin / kConvKC;
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
     p.relu = (flags & 1) ? 1 : 0;
+    p.mask = mask;
     p.reuse = reuse;
     p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
     p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;
@@ -658,4 +671,16 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
         kern<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
     }
     return check_launch("conv3x3_igemm_bf16");
+}
+
+extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, const int32_t* lengths,
+                                       void* y, int y_dtype, int flags,
+                                       int B, int T, int F, int Cin, int Cout, void* stream) {
+    if (!bias) { set_error("conv3x3_igemm_bf16: null bias"); return 1; }
+    return conv_igemm_launch(x, wp, bias, lengths, nullptr, y, y_dtype, flags, B, T, F, Cin, Cout, stream);
+}
+
+extern "C" int dasv_conv3x3_dgrad_bf16(const void* g, const void* wp_rot, const void* relu_mask, const int32_t* lengths,
+                                       void* dx, int B, int T, int F, int Cg, int Cx, void* stream) {
+    return conv_igemm_launch(g, wp_rot, nullptr, lengths, relu_mask, dx, 1, 0, B, T, F, Cg, Cx, stream);
 }

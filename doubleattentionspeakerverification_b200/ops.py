@@ -304,6 +304,24 @@ def logmel(wave, n_samples, frames, Tmax, window, hop, melw, mel_range, preem, s
 
 
 # ------------------------------------------------------------------------------------ training side of the front-end
+def conv3x3_dgrad(g, wp_rot, Cx, lengths=None, relu_mask=None):
+    """Input gradient of a 3x3 pad-1 convolution: g [B,T,F,Cg] bf16, wp_rot = pack_conv_weight_bf16 of the rotated,
+    transposed weights.  relu_mask [B,T,F,Cx] bf16 (optional): zero the result where it is <= 0.  Returns dx bf16."""
+    _dev(g, 'g')
+    if g.dtype != torch.bfloat16:
+        raise _lib.DasvError('conv3x3_dgrad: g must be bfloat16')
+    g = g.contiguous()
+    B, T, Fq, Cg = g.shape
+    if relu_mask is not None and (relu_mask.dtype != torch.bfloat16 or tuple(relu_mask.shape) != (B, T, Fq, Cx) or not relu_mask.is_contiguous()):
+        raise _lib.DasvError('conv3x3_dgrad: relu_mask must be a contiguous bf16 [B,T,F,Cx] tensor')
+    with torch.cuda.device(g.device):
+        lengths = _lengths(lengths, B, g.device)
+        dx = torch.empty((B, T, Fq, Cx), device=g.device, dtype=torch.bfloat16)
+        rc = _lib.lib().dasv_conv3x3_dgrad_bf16(_p(g), _p(wp_rot), _p(relu_mask), _p(lengths), _p(dx), B, T, Fq, Cg, Cx, _stream())
+        _lib.check(rc, 'dasv_conv3x3_dgrad_bf16')
+    return dx
+
+
 def conv3x3_wgrad(x, g, dw=None):
     """Weight gradient of a 3x3 pad-1 convolution (csrc/conv_wgrad.cu).  x [B,T,F,Cin] bf16 NHWC (layer input),
     g [B,T,F,Cout] bf16 NHWC (gradient at the conv output).  Returns dw [Cout,Cin,3,3] f32 (added to ``dw`` if given)."""

@@ -132,6 +132,14 @@ int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, co
                             void* y, int y_dtype, int flags,
                             int B, int T, int F, int Cin, int Cout, void* stream);
 
+/* Input gradient of the same convolution: dx = conv3x3(g, W') with the rotated, transposed weights
+ * W'[ci][co][ky][kx] = W[co][ci][2-ky][2-kx] packed by dasv_pack_conv_weight_bf16 (wp_rot), linear epilogue, on the
+ * forward's tensor-core kernel.  g [B,T,F,Cg] bf16 (Cg = the conv's output channels), dx [B,T,F,Cx] bf16.
+ * relu_mask (nullable, bf16 [B,T,F,Cx]): the activation that fed this conv, i.e. the ReLU output of the layer below;
+ * dx is zeroed where it is <= 0 (the ReLU backward of that layer fused into the store).  Rows t >= lengths[b] are 0. */
+int dasv_conv3x3_dgrad_bf16(const void* g, const void* wp_rot, const void* relu_mask, const int32_t* lengths,
+                            void* dx, int B, int T, int F, int Cg, int Cx, void* stream);
+
 /* Weight gradient of a 3x3 stride-1 pad-1 convolution on the tensor cores (training side of the layer above; the
  * reference obtains it from autograd/cuDNN, scripts/CNNs.py:59-66):
  *   dw[co][ci][ky][kx] (+)= sum_{b,t,f} g[b,t,f,co] * x[b,t+ky-1,f+kx-1,ci]

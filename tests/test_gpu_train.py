@@ -231,3 +231,26 @@ def test_speaker_classifier_training_step_on_kernels():
         first = float(l.detach()) if first is None else first
         last = float(l.detach())
     assert last < first
+
+
+@pytest.mark.parametrize('B,T,F,Cin,Cout', [(2, 9, 10, 64, 128), (1, 12, 20, 128, 64), (3, 7, 40, 128, 128)])
+def test_dgrad_with_fused_relu_mask_vs_autograd(B, T, F, Cin, Cout):
+    """Input gradient on the forward's tensor-core kernel (rotated weights, linear epilogue) with the ReLU backward of the
+    layer below fused into the store, and the row mask for padded utterances."""
+    gen = torch.Generator(device='cuda').manual_seed(7)
+    w = (torch.randn(Cout, Cin, 3, 3, device='cuda', generator=gen) * 0.05)
+    wb = w.to(torch.bfloat16).float()
+    g = torch.randn(B, T, F, Cout, device='cuda', generator=gen).to(torch.bfloat16)
+    xin = torch.relu(torch.randn(B, T, F, Cin, device='cuda', generator=gen)).to(torch.bfloat16)     # the conv's input activation
+    lengths = torch.tensor([T] + [max(1, T - 3)] * (B - 1), device='cuda', dtype=torch.int32)
+    z = xin.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    y = torch.nn.functional.conv2d(z, wb, padding=1)
+    y.backward(g.float().permute(0, 3, 1, 2))
+    want = z.grad.permute(0, 2, 3, 1)
+    wp = ops.pack_conv_weight_bf16(w.flip(2, 3).transpose(0, 1).contiguous())
+    plain = ops.conv3x3_dgrad(g, wp, Cin)
+    assert float((plain.float() - want).abs().max() / want.abs().max()) < 6e-3          # bf16 store
+    got = ops.conv3x3_dgrad(g, wp, Cin, lengths, relu_mask=xin)
+    t = torch.arange(T, device='cuda')[None, :, None, None]
+    keep = (xin > 0) & (t < lengths[:, None, None, None])
+    assert torch.equal(got, torch.where(keep, plain, torch.zeros_like(plain)))
