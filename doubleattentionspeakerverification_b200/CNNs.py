@@ -218,8 +218,7 @@ class _VGGTrainFn(torch.autograd.Function):
             g = ops.unpool_relu_bwd(gp, y2)                       # gradient at conv_k2's output (before ReLU)
             x2 = acts[2 * blk]                                    # conv_k2's input = conv_k1's ReLU output
             i2 = 2 * blk + 1
-            grads[2 * i2] = ops.conv3x3_wgrad(x2, g)
-            grads[2 * i2 + 1] = ops.bias_grad(g)
+            grads[2 * i2], grads[2 * i2 + 1] = ops.conv3x3_wgrad(x2, g, with_bias=True)
             c2 = getattr(mod, names[i2])
             # gradient at conv_k1's output (before its ReLU): the ReLU backward is fused into the input-gradient store
             g = ops.conv3x3_dgrad(g, mod._pack_dgrad(names[i2]), c2.in_channels, L, relu_mask=x2)
@@ -229,8 +228,7 @@ class _VGGTrainFn(torch.autograd.Function):
                 grads[0], grads[1] = dw, db
             else:
                 x1 = pooled[blk - 1]
-                grads[2 * i1] = ops.conv3x3_wgrad(x1, g)
-                grads[2 * i1 + 1] = ops.bias_grad(g)
+                grads[2 * i1], grads[2 * i1 + 1] = ops.conv3x3_wgrad(x1, g, with_bias=True)
                 c1 = getattr(mod, names[i1])
                 gp = ops.conv3x3_dgrad(g, mod._pack_dgrad(names[i1]), c1.in_channels, L)
         ctx.acts = ctx.pooled = None

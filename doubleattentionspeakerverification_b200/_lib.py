@@ -31,7 +31,7 @@ SIGNATURES = {
     'dasv_conv3x3_igemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_wgrad_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
-    'dasv_conv3x3_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasv_conv3x3_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_relu_bwd_bf16': (_i, [_vp, _vp, _sz, _vp]),
     'dasv_unpool_relu_bwd_bf16': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dasv_bias_grad_workspace_bytes': (_sz, [_i]),

@@ -38,6 +38,7 @@ constexpr uint32_t kWgTmemCols = 512;
 
 struct WgradParams {
     float* ws;                       // [splits][9][Cout][Cin]
+    float* ws_bias;                  // [splits][Cout] or NULL: column sums of G (the bias gradient), from one extra MMA per K step
     int B, T, F, Cin, Cout;
     int BT, n_tt, n_items, items_per_split, splits;
     int n_mt, n_nt;
@@ -70,7 +71,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     unsigned char* ring = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(p.stages) * p.stage_bytes);
+    unsigned char* ones = ring + static_cast<size_t>(p.stages) * p.stage_bytes;        // [16 rows][64 ch] of bf16 1.0
+    uint64_t* full = reinterpret_cast<uint64_t*>(ones + 2048);
     uint64_t* empty = full + p.stages;
     uint64_t* acc_full = empty + p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -85,6 +87,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int xc0 = (N == 32) ? (n >> 1) * 64 : n * N;               // first channel of the X box(es)
     const uint32_t xhalf = (N == 32) ? static_cast<uint32_t>(n & 1) * 64u : 0u;
     const int xboxes = N == 128 ? 2 : 1;
+    const bool do_bias = p.ws_bias != nullptr && n == 0 && grp == 0;        // this CTA also sums G over its items
+    const uint32_t bias_col = static_cast<uint32_t>(p.tg * N);
     const int item0 = split * p.items_per_split;
     const int item1 = min(item0 + p.items_per_split, p.n_items);
 
@@ -93,6 +97,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         uint4* z = reinterpret_cast<uint4*>(ring);
         const size_t n16 = static_cast<size_t>(p.stages) * p.stage_bytes / 16;
         for (size_t i = threadIdx.x; i < n16; i += kWgThreads) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < 2048 / 16; i += kWgThreads)
+            reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -136,6 +142,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 toff[j] = static_cast<long long>((tap / 3) * frow + (tap % 3) - 1) * 8;          // rows * 128 B >> 4; -1 lands on the guard row
             }
             const int ntaps = tap1 - tap0;
+            const uint32_t idesc_ones = umma_idesc_bf16(kWgM, 16) | (1u << 15) | (1u << 16);
+            const uint64_t ones_desc = umma_desc_mn128(smem_u32(ones), 16);
             int st = 0;
             uint32_t ph = 0;
             uint32_t acc = 0;
@@ -153,6 +161,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     acc = 1u;
                     a_desc += 16 * 8;                   // 16 rows of 128 B
                     b_desc += 16 * 8;
+                }
+                if (do_bias) {                      // column sums of G: G^T . 1 against a tile of ones
+                    uint64_t g_desc = umma_desc_mn128(sb, p.g_alloc);
+#pragma unroll 1
+                    for (int k = 0; k < p.K16; k += 16) {
+                        umma_bf16(tmem_base + bias_col, g_desc, ones_desc, idesc_ones, (it > item0 || k > 0) ? 1u : 0u);
+                        g_desc += 16 * 8;
+                    }
                 }
                 umma_commit(&empty[st]);            // frees the stage when the MMAs above have read it
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
@@ -188,6 +204,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 }
             }
         }
+        if (do_bias) {
+            uint32_t r[32];
+            float v = 0.f;
+            if (item1 > item0) {
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + bias_col, r);
+                tc_wait_ld();
+                v = __uint_as_float(r[0]);
+            }
+            if (co < p.Cout) p.ws_bias[static_cast<size_t>(split) * p.Cout + co] = v;
+        }
         tc_fence_before();
     }
     __syncthreads();
@@ -195,9 +221,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 }
 
 // dW[co][ci][tap] (+)= sum over splits, fixed order
-__global__ void conv_wgrad_reduce_kernel(const float* ws, float* dw, int splits, int Cout, int Cin, int accumulate) {
+__global__ void conv_wgrad_reduce_kernel(const float* ws, float* dw, const float* ws_bias, float* db, int splits, int Cout, int Cin, int accumulate) {
     const size_t n = static_cast<size_t>(Cout) * Cin;
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // (co, ci)
+    if (db != nullptr && i < static_cast<size_t>(Cout)) {
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += ws_bias[static_cast<size_t>(sp) * Cout + i];
+        db[i] = accumulate ? db[i] + s : s;
+    }
     if (i >= n) return;
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
@@ -241,7 +272,7 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     pl.tg = pl.N == 128 ? 3 : (pl.N == 64 ? 5 : 9);
     pl.ng = pl.N == 128 ? 3 : (pl.N == 64 ? 2 : 1);
     const int xboxes = pl.N == 128 ? 2 : 1;
-    const uint32_t avail = 227u * 1024u - 1024u - 256u;
+    const uint32_t avail = 227u * 1024u - 2048u - 1024u - 256u;
     pl.BT = 176 / (F + 2);
     if (pl.BT < 1) pl.BT = 1;
     if (pl.BT > T) pl.BT = T;
@@ -260,7 +291,7 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     pl.stages = static_cast<int>(avail / pl.stage_bytes);
     if (pl.stages > 4) pl.stages = 4;
     if (pl.stages < 1) return pl;
-    pl.smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024 + 256;
+    pl.smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 2048 + 1024 + 256;
     pl.n_tt = (T + pl.BT - 1) / pl.BT;
     pl.n_items = B * pl.n_tt;
     pl.n_mt = (Cout + kWgM - 1) / kWgM;
@@ -294,10 +325,10 @@ extern "C" size_t dasv_conv3x3_wgrad_workspace_bytes(int B, int T, int F, int Ci
     cudaGetLastError();
     const WgradPlan pl = wgrad_plan(B, T, F, Cin, Cout, sms);
     if (!pl.ok) return 0;
-    return static_cast<size_t>(pl.splits) * 9 * Cout * Cin * sizeof(float);
+    return static_cast<size_t>(pl.splits) * (static_cast<size_t>(9) * Cout * Cin + Cout) * sizeof(float);
 }
 
-extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, void* workspace, int accumulate,
+extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, float* db, void* workspace, int accumulate,
                                        int B, int T, int F, int Cin, int Cout, void* stream) {
     if (B < 0 || T < 0) { set_error("conv3x3_wgrad_bf16: negative shape"); return 1; }
     if (!x || !g || !dw || !workspace) { set_error("conv3x3_wgrad_bf16: null pointer"); return 1; }
@@ -307,7 +338,10 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (B == 0 || T == 0) {
-        if (!accumulate) cudaMemsetAsync(dw, 0, static_cast<size_t>(Cout) * Cin * 9 * sizeof(float), s);
+        if (!accumulate) {
+            cudaMemsetAsync(dw, 0, static_cast<size_t>(Cout) * Cin * 9 * sizeof(float), s);
+            if (db) cudaMemsetAsync(db, 0, static_cast<size_t>(Cout) * sizeof(float), s);
+        }
         return check_launch("conv3x3_wgrad_bf16");
     }
     const WgradPlan pl = wgrad_plan(B, T, F, Cin, Cout, sms);
@@ -328,6 +362,7 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     }
     WgradParams p{};
     p.ws = static_cast<float*>(workspace);
+    p.ws_bias = db ? p.ws + static_cast<size_t>(pl.splits) * 9 * Cout * Cin : nullptr;
     p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.Cout = Cout;
     p.BT = pl.BT; p.n_tt = pl.n_tt; p.n_items = pl.n_items; p.items_per_split = pl.items_per_split; p.splits = pl.splits;
     p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.N = pl.N; p.tg = pl.tg; p.ng = pl.ng; p.rowsG = pl.rowsG; p.K16 = pl.K16; p.rowsX = pl.rowsX;
@@ -344,6 +379,6 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     kern<<<grid, kWgThreads, pl.smem, s>>>(tmG, tmX, p);
     if (check_launch("conv3x3_wgrad_bf16")) return 1;
     const size_t n = static_cast<size_t>(Cout) * Cin;
-    conv_wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p.ws, dw, pl.splits, Cout, Cin, accumulate);
+    conv_wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p.ws, dw, p.ws_bias, db, pl.splits, Cout, Cin, accumulate);
     return check_launch("conv3x3_wgrad_reduce");
 }

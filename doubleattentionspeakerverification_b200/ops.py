@@ -322,9 +322,10 @@ def conv3x3_dgrad(g, wp_rot, Cx, lengths=None, relu_mask=None):
     return dx
 
 
-def conv3x3_wgrad(x, g, dw=None):
+def conv3x3_wgrad(x, g, dw=None, with_bias=False):
     """Weight gradient of a 3x3 pad-1 convolution (csrc/conv_wgrad.cu).  x [B,T,F,Cin] bf16 NHWC (layer input),
-    g [B,T,F,Cout] bf16 NHWC (gradient at the conv output).  Returns dw [Cout,Cin,3,3] f32 (added to ``dw`` if given)."""
+    g [B,T,F,Cout] bf16 NHWC (gradient at the conv output).  Returns dw [Cout,Cin,3,3] f32 (added to ``dw`` if given), or
+    (dw, db [Cout]) with ``with_bias`` (the bias gradient falls out of the same kernel)."""
     _dev(x, 'x'); _dev(g, 'g')
     if x.dtype != torch.bfloat16 or g.dtype != torch.bfloat16:
         raise _lib.DasvError('conv3x3_wgrad needs bf16 activations')
@@ -336,14 +337,17 @@ def conv3x3_wgrad(x, g, dw=None):
     with torch.cuda.device(x.device):
         L = _lib.lib()
         acc = dw is not None
+        if acc and with_bias:
+            raise _lib.DasvError('conv3x3_wgrad: with_bias cannot be combined with accumulation into dw')
         if dw is None:
             dw = torch.empty((Cout, Cin, 3, 3), device=x.device, dtype=torch.float32)
         elif dw.shape != (Cout, Cin, 3, 3) or dw.dtype != torch.float32 or not dw.is_contiguous():
             raise _lib.DasvError('dw must be a contiguous f32 [Cout,Cin,3,3] tensor')
+        db = torch.empty((Cout,), device=x.device, dtype=torch.float32) if with_bias else None
         ws = torch.empty((max(int(L.dasv_conv3x3_wgrad_workspace_bytes(B, T, F, Cin, Cout)), 16),), device=x.device, dtype=torch.uint8)
-        rc = L.dasv_conv3x3_wgrad_bf16(_p(x), _p(g), _p(dw), _p(ws), 1 if acc else 0, B, T, F, Cin, Cout, _stream())
+        rc = L.dasv_conv3x3_wgrad_bf16(_p(x), _p(g), _p(dw), _p(db), _p(ws), 1 if acc else 0, B, T, F, Cin, Cout, _stream())
         _lib.check(rc, 'dasv_conv3x3_wgrad_bf16')
-    return dw
+    return (dw, db) if with_bias else dw
 
 
 def relu_bwd_(g, y):

@@ -145,10 +145,11 @@ int dasv_conv3x3_dgrad_bf16(const void* g, const void* wp_rot, const void* relu_
  *   dw[co][ci][ky][kx] (+)= sum_{b,t,f} g[b,t,f,co] * x[b,t+ky-1,f+kx-1,ci]
  * x [B,T,F,Cin] bf16 (the layer's input), g [B,T,F,Cout] bf16 (gradient at the conv output, i.e. after the ReLU / pool
  * backward; zero for frames past an utterance), dw [Cout,Cin,3,3] f32 (reference layout; overwritten, or added to when
- * accumulate != 0).  Deterministic: split-K partials in `workspace` are added in fixed order.
+ * accumulate != 0); db [Cout] f32 nullable: the bias gradient sum_{b,t,f} g[b,t,f,co], from one extra MMA per K step
+ * against a tile of ones.  Deterministic: split-K partials in `workspace` are added in fixed order.
  * Requirements: Cin % 64 == 0, Cout % 64 == 0, F <= 254. */
 size_t dasv_conv3x3_wgrad_workspace_bytes(int B, int T, int F, int Cin, int Cout);
-int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, void* workspace, int accumulate,
+int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, float* db, void* workspace, int accumulate,
                             int B, int T, int F, int Cin, int Cout, void* stream);
 
 /* Memory-bound pieces of the front-end's backward pass (what autograd does around the conv backward in the reference,

@@ -47,6 +47,10 @@ def test_wgrad_vs_autograd(B, T, F, Cin, Cout):
     dw2 = ops.conv3x3_wgrad(x, g, dw.clone())                    # accumulate
     assert float((dw2 - 2 * want).abs().max() / want.abs().max()) < 4e-4
     assert torch.equal(ops.conv3x3_wgrad(x, g), dw)              # deterministic
+    dw3, db = ops.conv3x3_wgrad(x, g, with_bias=True)            # bias gradient from the same kernel
+    assert torch.equal(dw3, dw)
+    wantb = g.float().sum((0, 1, 2))
+    assert float((db - wantb).abs().max()) < 2e-4 * max(1.0, float(wantb.abs().max()))
 
 
 def test_relu_and_unpool_backward_match_autograd():
