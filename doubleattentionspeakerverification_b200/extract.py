@@ -111,26 +111,42 @@ def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400
     return out
 
 
-def extract_local_audio(embed_fn, waves, indices, sfr, device, max_samples=256 * 64352, max_batch=None, min_ratio=0.8, **feature_kw):
+def extract_sharded_audio(embed_fn, waves, sfr, device, group=None, embedding_size=None, feature_fn=None, **kw):
+    """``extract_sharded`` for waveforms: ranks take length-balanced shards of ``waves`` (1-D float arrays), compute
+    features and embeddings on their GPU (``extract_local_audio``), then one all-gather restores ``[N, E]`` in the
+    original order on every rank."""
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if distributed else 1
+    rank = dist.get_rank(group) if distributed else 0
+    plan = shard_plan(np.array([len(w) for w in waves]), world)
+    local = extract_local_audio(embed_fn, waves, plan[rank], sfr, device, feature_fn=feature_fn, **kw)
+    return _gather_shards(local, plan, len(waves), device, group, embedding_size)
+
+
+def extract_local_audio(embed_fn, waves, indices, sfr, device, max_samples=256 * 64352, max_batch=None, min_ratio=0.8,
+                        feature_fn=None, **feature_kw):
     """Waveform -> embedding without the host in between (getEmbeddingExample.py:22-36 = extractFeatures + getEmbedding):
     ``waves[i]`` (1-D float arrays in [-1, 1)) go to the device in zero-padded batches of similar length, the log-mel
     features + CMN are computed there (``featureExtractor.logmel_batch``) and handed to ``embed_fn(x [B,T,80], frames
     [B])`` with the frame counts as lengths.  Returns ``[len(indices), E]`` in the order of ``indices``."""
-    from . import featureExtractor as fe
     indices = np.asarray(indices)
     if len(indices) == 0:
         return None
+    if feature_fn is None:                                   # (wave [B,N], n_samples, sfr) -> (features [B,T,F], frames [B])
+        from . import featureExtractor as fe
+        feature_fn = fe.logmel_batch
     dev = torch.device(device)
     n = np.array([len(waves[i]) for i in indices])
-    if (n < fe.N_FFT).any():
-        raise ValueError('a waveform is shorter than one analysis frame (%d samples)' % fe.N_FFT)
+    if (n < 512).any():
+        raise ValueError('a waveform is shorter than one analysis frame (512 samples)')
     out = None
     for b in bucket_plan(n, max_samples, min_ratio, max_batch):
         nb = n[b]
-        host = torch.zeros((len(b), int(nb.max())), dtype=torch.float32, pin_memory=True)
+        host = torch.zeros((len(b), int(nb.max())), dtype=torch.float32, pin_memory=dev.type == 'cuda')
         for j, i in enumerate(b):
             host[j, :nb[j]] = torch.from_numpy(np.asarray(waves[indices[i]], dtype=np.float32))
-        feat, frames = fe.logmel_batch(host.to(dev, non_blocking=True), nb, sfr, **feature_kw)
+        feat, frames = feature_fn(host.to(dev, non_blocking=True), nb, sfr, **feature_kw)
         emb = embed_fn(feat, frames)
         if out is None:
             out = torch.empty((len(indices), emb.shape[1]), device=emb.device, dtype=emb.dtype)
@@ -184,6 +200,13 @@ def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, m
         local = extract_local_packed(embed_fn, feats, plan[rank], device, max_frames, max_batch=max_batch)
     else:
         local = extract_local(embed_fn, feats, plan[rank], device, max_frames, max_batch)
+    return _gather_shards(local, plan, N, device, group, embedding_size)
+
+
+def _gather_shards(local, plan, N, device, group, embedding_size):
+    """All-gather the ranks' ``[len(plan[rank]), E]`` shards and restore the original utterance order."""
+    import torch.distributed as dist
+    world = len(plan)
     if world == 1:
         out = torch.empty_like(local)
         out[torch.from_numpy(plan[0]).to(local.device)] = local

@@ -126,3 +126,32 @@ def _train_worker(rank, world, port):
 
 def test_world2_gloo_gradient_allreduce_equals_global_batch():
     mp.spawn(_train_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def stub_features(wave, n_samples, sfr):
+    """Stand-in for the GPU log-mel kernels in the host-logic tests: 'frames' of 100 samples, 4 moments per frame."""
+    B = wave.shape[0]
+    frames = np.asarray(n_samples) // 100
+    T = int(frames.max())
+    x = wave[:, :T * 100].reshape(B, T, 100)
+    feat = torch.stack([x.mean(2), x.abs().mean(2), x.min(2).values, x.max(2).values], dim=2)
+    return feat, torch.from_numpy(frames.astype(np.int32))
+
+
+def _audio_worker(rank, world, port):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(3)
+        waves = [rs.standard_normal(int(rs.randint(600, 5000))).astype(np.float32) for _ in range(9)]
+        emb = extract.extract_sharded_audio(stub_embed, waves, 16000, 'cpu', embedding_size=4, feature_fn=stub_features, max_samples=9000)
+        for i, w in enumerate(waves):
+            f, fr = stub_features(torch.from_numpy(w)[None], [len(w)], 16000)
+            assert torch.allclose(emb[i], stub_embed(f, fr)[0], rtol=1e-5, atol=1e-5), 'rank %d utterance %d' % (rank, i)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_waveform_extraction_restores_order():
+    mp.spawn(_audio_worker, args=(2, _free_port()), nprocs=2, join=True)
