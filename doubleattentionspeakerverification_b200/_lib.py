@@ -44,7 +44,7 @@ SIGNATURES = {
     'dasv_threshold_counts': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     'dasv_cosine_matrix': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'dasv_logmel_f32': (_i, [_vp, _vp, _i, _c.c_longlong, _vp, _i, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _vp, _i, _vp]),
-    'dasv_cmn_f32': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'dasv_cmn_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
 
 _LIB = None

@@ -125,34 +125,61 @@ __global__ void __launch_bounds__(kFeatWarps * 32) logmel_kernel(const LogmelPar
     }
 }
 
-// Cepstral mean normalisation (featureExtractor.py:25-26, data.py:21-30 'cmn'): one CTA per utterance, thread m owns mel
-// bin m: fixed-order sum over the utterance's frames, then the subtraction; frames past the utterance are zeroed.
-__global__ void cmn_kernel(float* feat, const int32_t* frames, int Tmax, int n_mels) {
+// Cepstral mean (and variance) normalisation (featureExtractor.py:25-26, data.py:21-30 'cmn' / 'cmvn'): one CTA per
+// utterance, thread (m, slice) owns mel bin m and every 8th frame: fixed-order Kahan sums over the utterance's frames, then
+// the subtraction (and the division by the population standard deviation where it exceeds 0.01, data.py:28-29); frames
+// past the utterance are zeroed.
+__global__ void cmn_kernel(float* feat, const int32_t* frames, int Tmax, int n_mels, int variance) {
     const int b = blockIdx.x;
     const int nf = min(max(frames[b], 0), Tmax);
     float* f = feat + static_cast<size_t>(b) * Tmax * n_mels;
     __shared__ float part[8][128];
+    __shared__ float stat[2][128];
     const int m = threadIdx.x % 128, slice = threadIdx.x / 128;      // 1024 threads = 8 time slices x 128 bins
-    if (m < n_mels) {
-        float s = 0.f, c = 0.f;                      // Kahan sum
+    float s = 0.f, c = 0.f;                          // Kahan sum
+    if (m < n_mels)
         for (int t = slice; t < nf; t += 8) {
             const float y = f[static_cast<size_t>(t) * n_mels + m] - c;
             const float u = s + y;
             c = (u - s) - y;
             s = u;
         }
-        part[slice][m] = s;
+    part[slice][m] = s;
+    __syncthreads();
+    if (slice == 0) {
+        float a = 0.f;
+        for (int i = 0; i < 8; ++i) a += part[i][m];
+        stat[0][m] = nf > 0 ? a / static_cast<float>(nf) : 0.f;
     }
     __syncthreads();
-    if (m < n_mels) {
-        float s = 0.f;
-        for (int i = 0; i < 8; ++i) s += part[i][m];
-        const float mean = nf > 0 ? s / static_cast<float>(nf) : 0.f;
+    const float mean = stat[0][m];
+    float inv = 1.f;
+    if (variance) {
+        s = 0.f; c = 0.f;
+        if (m < n_mels)
+            for (int t = slice; t < nf; t += 8) {
+                const float d = f[static_cast<size_t>(t) * n_mels + m] - mean;
+                const float y = d * d - c;
+                const float u = s + y;
+                c = (u - s) - y;
+                s = u;
+            }
+        part[slice][m] = s;
+        __syncthreads();
+        if (slice == 0) {
+            float a = 0.f;
+            for (int i = 0; i < 8; ++i) a += part[i][m];
+            const float sd = nf > 0 ? sqrtf(a / static_cast<float>(nf)) : 1.f;
+            stat[1][m] = sd > 0.01f ? 1.f / sd : 1.f;
+        }
+        __syncthreads();
+        inv = stat[1][m];
+    }
+    if (m < n_mels)
         for (int t = slice; t < Tmax; t += 8) {
             const size_t i = static_cast<size_t>(t) * n_mels + m;
-            f[i] = t < nf ? f[i] - mean : 0.f;
+            f[i] = t < nf ? (f[i] - mean) * inv : 0.f;
         }
-    }
 }
 
 }  // namespace dasv
@@ -176,11 +203,11 @@ extern "C" int dasv_logmel_f32(const float* wave, const int32_t* n_samples, int 
     return check_launch("logmel");
 }
 
-extern "C" int dasv_cmn_f32(float* feat, const int32_t* frames, int B, int Tmax, int n_mels, void* stream) {
+extern "C" int dasv_cmn_f32(float* feat, const int32_t* frames, int B, int Tmax, int n_mels, int variance, void* stream) {
     if (B < 0 || Tmax < 0) { set_error("cmn: negative shape"); return 1; }
     if (B == 0 || Tmax == 0) return 0;
     if (!feat || !frames) { set_error("cmn: null pointer"); return 1; }
     if (n_mels < 1 || n_mels > 128) { set_error("cmn: n_mels %d outside [1, 128]", n_mels); return 1; }
-    cmn_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(feat, frames, Tmax, n_mels);
+    cmn_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(feat, frames, Tmax, n_mels, variance);
     return check_launch("cmn");
 }

@@ -76,6 +76,7 @@ def logmel_batch(wave, n_samples, sfr, window_size=0.025, window_stride=0.010, w
                  preemCoef=0.97, cmn=True, device=None):
     """Batched ``normalize(mfsc(y).T)``.  wave ``[B, N]`` float (numpy or torch, zero-padded), n_samples ``[B]``.
 
+    ``cmn``: True / 'cmn' = cepstral mean normalisation, 'cmvn' = mean and variance (``data.py:21-30``), False = none.
     Returns (features ``[B, Tmax, n_mels]`` float32 CUDA tensor, frames ``[B]`` int32 CUDA tensor); rows past an
     utterance's frame count are zero (the masked front-end ignores them)."""
     win_length, hop = int(sfr * window_size), int(sfr * window_stride)
@@ -111,6 +112,19 @@ def mfsc(y, sfr, window_size=0.025, window_stride=0.010, window='hamming', n_mel
 def normalize(features):
     """scripts/featureExtractor.py:25-26."""
     return features - np.mean(features, axis=0)
+
+
+def normalizeFeatures(features, normalization='cmn'):
+    """scripts/data.py:21-30 on the GPU: ``[T, n_mels]`` numpy features -> 'cmn' or 'cmvn' normalised copy."""
+    if normalization not in ('cmn', 'cmvn'):
+        raise _lib.DasvError("normalization must be 'cmn' or 'cmvn'")
+    f = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32)).cuda()[None].contiguous()
+    frames = torch.tensor([f.shape[1]], dtype=torch.int32, device=f.device)
+    with torch.cuda.device(f.device):
+        rc = _lib.lib().dasv_cmn_f32(f.data_ptr(), frames.data_ptr(), 1, f.shape[1], f.shape[2], 1 if normalization == 'cmvn' else 0,
+                                     torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 'dasv_cmn_f32')
+    return f[0].cpu().numpy()
 
 
 def read_wav(path):

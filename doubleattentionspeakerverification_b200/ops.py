@@ -282,6 +282,7 @@ def threshold_counts(scores, thresholds):
 
 # ------------------------------------------------------------------------------------ features
 def logmel(wave, n_samples, frames, Tmax, window, hop, melw, mel_range, preem, scale, cmn=True):
+    # cmn: False / None = raw log-mel, True or 'cmn' = mean normalisation, 'cmvn' = mean and variance (data.py:21-30)
     """Log mel-filterbank features (+ CMN) of a padded waveform batch (csrc/features.cu).  All tensors on the device:
     wave [B,N] f32, n_samples/frames [B] i32, window [win_length] f32, melw [n_mels,257] f32, mel_range [n_mels,2] i32.
     Returns [B,Tmax,n_mels] f32; rows t >= frames[b] are zero."""
@@ -298,7 +299,7 @@ def logmel(wave, n_samples, frames, Tmax, window, hop, melw, mel_range, preem, s
                                preem, scale, _p(out), Tmax, _stream())
         _lib.check(rc, 'dasv_logmel_f32')
         if cmn:
-            rc = L.dasv_cmn_f32(_p(out), _p(frames), B, Tmax, n_mels, _stream())
+            rc = L.dasv_cmn_f32(_p(out), _p(frames), B, Tmax, n_mels, 1 if cmn == 'cmvn' else 0, _stream())
             _lib.check(rc, 'dasv_cmn_f32')
     return out
 

@@ -207,9 +207,10 @@ int dasv_logmel_f32(const float* wave, const int32_t* n_samples, int B, long lon
                     const float* melw, const int32_t* mel_range, int n_mels,
                     float preem, float scale, float* out, int Tmax, void* stream);
 
-/* scripts/featureExtractor.py:25-26 (`normalize`) / data.py:21-30 ('cmn'), in place: per utterance and mel bin subtract
- * the mean over its frames[b] frames; rows t >= frames[b] are set to zero. */
-int dasv_cmn_f32(float* feat, const int32_t* frames, int B, int Tmax, int n_mels, void* stream);
+/* scripts/featureExtractor.py:25-26 (`normalize`) / data.py:21-30 (`normalizeFeatures` 'cmn', and 'cmvn' with
+ * variance != 0), in place: per utterance and mel bin subtract the mean over its frames[b] frames and, for 'cmvn', divide
+ * by the population standard deviation where it exceeds 0.01 (data.py:28-29); rows t >= frames[b] are set to zero. */
+int dasv_cmn_f32(float* feat, const int32_t* frames, int B, int Tmax, int n_mels, int variance, void* stream);
 
 #ifdef __cplusplus
 }

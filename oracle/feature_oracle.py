@@ -106,6 +106,20 @@ def normalize(features):
     return features - np.mean(features, axis=0)
 
 
+def normalize_features(features, normalization='cmn'):
+    """scripts/data.py:21-30 (``normalizeFeatures``; ``Dataset.__normalize`` :47-54 is the same), without mutating the input."""
+    features = np.array(features, copy=True)
+    mean = np.mean(features, axis=0)
+    features -= mean
+    if normalization == 'cmn':
+        return features
+    if normalization == 'cmvn':
+        std = np.std(features, axis=0)
+        std = np.where(std > 0.01, std, 1.0)
+        return features / std
+    raise ValueError(normalization)
+
+
 def extract(y, sfr, **kw):
     """scripts/featureExtractor.py:29-33 minus the file read: ``[T, n_mels]`` CMN'd features."""
     return normalize(np.transpose(mfsc(y, sfr, **kw)))

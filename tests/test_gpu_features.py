@@ -111,3 +111,22 @@ def test_extract_local_audio_buckets_and_order():
             assert np.abs(got[row] - one).max() / np.abs(one).max() < 1e-4, i       # batch composition does not matter
     with pytest.raises(ValueError):
         extract.extract_local_audio(embed, [waves[0][:100]], [0], 16000, 'cuda')
+
+
+def test_cmvn_matches_data_py_normalisation():
+    """data.py:21-30 'cmvn' (population std, floor 0.01) and 'cmn', batched with padding and as the drop-in function."""
+    ns = [16000, 9000]
+    wave = np.zeros((2, 16000), np.float32)
+    for i, n in enumerate(ns):
+        wave[i, :n] = synth.make_waveform(n, 16000, seed=60 + i)
+    wave[1, :9000] *= 1e-6                                        # near-silent: log(max(1, .)) = 0 everywhere -> std = 0 -> left unscaled
+    raw, frames = fe.logmel_batch(wave, ns, 16000, cmn=False)
+    got, _ = fe.logmel_batch(wave, ns, 16000, cmn='cmvn')
+    for i in range(2):
+        T = int(frames[i])
+        want = fo.normalize_features(raw[i, :T].cpu().numpy(), 'cmvn')
+        assert np.abs(got[i, :T].cpu().numpy() - want).max() < 1e-4
+        assert np.all(got[i, T:].cpu().numpy() == 0)
+    f0 = raw[0, :int(frames[0])].cpu().numpy()
+    for mode in ('cmn', 'cmvn'):
+        assert np.abs(fe.normalizeFeatures(f0, mode) - fo.normalize_features(f0, mode)).max() < 1e-4
