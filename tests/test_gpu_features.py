@@ -130,3 +130,31 @@ def test_cmvn_matches_data_py_normalisation():
     f0 = raw[0, :int(frames[0])].cpu().numpy()
     for mode in ('cmn', 'cmvn'):
         assert np.abs(fe.normalizeFeatures(f0, mode) - fo.normalize_features(f0, mode)).max() < 1e-4
+
+
+def test_get_embedding_example_from_a_wav_file(tmp_path):
+    """scripts/getEmbeddingExample.py end to end: a 16-bit PCM WAV file + a checkpoint in the reference's format ->
+    the embedding, equal to getEmbedding on the oracle's features of the same samples."""
+    import pickle
+    import wave as wavmod
+    from argparse import Namespace
+    from doubleattentionspeakerverification_b200 import getEmbeddingExample as ex
+    y = synth.make_waveform(20000, 16000, seed=77)
+    pcm = np.round(y * 32768).astype('<i2')
+    wav = str(tmp_path / 'utt.wav')
+    with wavmod.open(wav, 'wb') as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+    cfg = synth.example_config(kernel_size=256, embedding_size=64, heads_number=8, num_spkrs=3)
+    cfg.precision = 'fp32'
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, seed=3))
+    ckpt = str(tmp_path / 'model.chkpt')
+    torch.save({'settings': cfg, 'model': net.state_dict()}, ckpt)
+    cfgp = str(tmp_path / 'config.pkl')
+    with open(cfgp, 'wb') as h:
+        pickle.dump(cfg, h)
+    emb = ex.main(cfg, Namespace(audioPath=wav, modelConfig=cfgp, modelCheckpoint=ckpt, device='cuda')).cpu().numpy()
+    feats = fo.extract(pcm.astype(np.float64) / 32768, 16000).astype(np.float32)
+    with torch.no_grad():
+        want = net.cuda().eval().getEmbedding(torch.from_numpy(feats)[None].cuda()).cpu().numpy()
+    assert emb.shape == (1, 64)
+    assert np.abs(emb - want).max() / np.abs(want).max() < 1e-3
