@@ -184,7 +184,7 @@ def extract_local(embed_fn, feats, indices, device, max_frames=256 * 400, max_ba
     return out
 
 
-def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, max_batch=None, embedding_size=None):
+def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, max_batch=None, embedding_size=None, min_ratio=0.8):
     """Every rank embeds its shard, then one all-gather; returns ``[N, E]`` embeddings of ALL utterances, in
     the original order, on every rank.  Without an initialised process group it is the single-GPU path.
     ``feats``: list of ``[T_i, F]`` arrays (host-padded batches) or a ``PackedUtterances`` (device-built batches)."""
@@ -197,7 +197,7 @@ def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, m
     rank = dist.get_rank(group) if distributed else 0
     plan = shard_plan(lengths, world)
     if is_packed:
-        local = extract_local_packed(embed_fn, feats, plan[rank], device, max_frames, max_batch=max_batch)
+        local = extract_local_packed(embed_fn, feats, plan[rank], device, max_frames, min_ratio=min_ratio, max_batch=max_batch)
     else:
         local = extract_local(embed_fn, feats, plan[rank], device, max_frames, max_batch)
     return _gather_shards(local, plan, N, device, group, embedding_size)

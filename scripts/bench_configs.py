@@ -25,6 +25,8 @@ from doubleattentionspeakerverification_b200 import extract, model, synth
 ap = argparse.ArgumentParser()
 ap.add_argument('--utts-per-gpu', type=int, default=256)
 ap.add_argument('--reps', type=int, default=3)
+ap.add_argument('--min-ratio', type=float, default=0.8)
+ap.add_argument('--max-frames', type=int, default=256 * 400)
 args = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
 torch.cuda.set_device(local)
@@ -67,12 +69,12 @@ frames = (100 * rs.uniform(2.0, 20.0, size=N)).astype(np.int64)
 base = synth.make_logmel(1, 2000, seed=1)[0]
 feats = [np.ascontiguousarray(np.roll(base, int(i) * 7, axis=0)[:T]) for i, T in enumerate(frames)]   # cheap distinct utterances
 packed3 = extract.PackedUtterances(feats)            # what a feature loader hands over: frames in pinned memory
-dt3, emb3 = timed(lambda: extract.extract_sharded(embed, packed3, dev, max_frames=256 * 400, embedding_size=400))
+dt3, emb3 = timed(lambda: extract.extract_sharded(embed, packed3, dev, max_frames=args.max_frames, embedding_size=400, min_ratio=args.min_ratio))
 flops = 12.99e9 * frames.sum() / 100.0     # 12.99 GFLOP per second of audio, valid frames only
 plan = extract.shard_plan(frames, world)
 pad = 0
 for p in plan:
-    for b in extract.bucket_plan(frames[p], 256 * 400):
+    for b in extract.bucket_plan(frames[p], args.max_frames, args.min_ratio):
         pad += len(b) * frames[p][b].max()
 res3 = {'config': 'configs[3] variable-length 2-20 s, padded+masked, dp%d' % world, 'utterances': int(N), 'seconds': dt3,
         'embeddings_per_s': N / dt3, 'useful_conv_tflops': flops / dt3 / 1e12, 'padding_waste': float(pad / frames.sum() - 1.0),
