@@ -327,7 +327,8 @@ def main():
         for dt_name, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16)):
             bufs = [torch.randn(Bp, Tp, Dp, device=dev, generator=gen).to(dt) for _ in range(2)]   # 2 x 419 MB fp32 >> L2
             es = 4 if dt == torch.float32 else 2
-            for case, L in (('full', None), ('masked', lens)):
+            lens_sorted = torch.sort(lens, descending=True).values   # longest first: the order extract.bucket_plan builds batches in
+            for case, L in (('full', None), ('masked', lens), ('masked_sorted', lens_sorted)):
                 nbytes = (Bp * Tp if L is None else int(L.sum().item())) * Dp * es + Bp * (Dp // Hp) * 4
                 us, mode = time_us(lambda i: ops.dmha_fwd(bufs[i & 1], q, a, lengths=L, need_align=False), 20)
                 gbs = nbytes / (us * 1e-6) / 1e9

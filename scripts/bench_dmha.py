@@ -39,7 +39,8 @@ for name, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16)):
         continue
     xs = [torch.randn(B, T, D, device=dev, generator=gen).to(dt) for _ in range(2)]
     es = 4 if dt == torch.float32 else 2
-    for case, L in (('full', None), ('masked', lens)):
+    lens_sorted = torch.sort(lens, descending=True).values       # the order extract.bucket_plan hands batches over in
+    for case, L in (('full', None), ('masked', lens), ('masked_sorted', lens_sorted)):
         nbytes = (B * T if L is None else int(L.sum().item())) * D * es
         us = time_us(lambda i: ops.dmha_fwd(xs[i & 1], q, a, lengths=L, need_align=False))
         out['%s_%s' % (name, case)] = (round(us, 1), round(nbytes / us / 1e3 / PEAK, 3))
