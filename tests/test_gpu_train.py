@@ -258,3 +258,23 @@ def test_dgrad_with_fused_relu_mask_vs_autograd(B, T, F, Cin, Cout):
     t = torch.arange(T, device='cuda')[None, :, None, None]
     keep = (xin > 0) & (t < lengths[:, None, None, None])
     assert torch.equal(got, torch.where(keep, plain, torch.zeros_like(plain)))
+
+
+def test_wgrad_full_size_properties():
+    """exampleModel layer size (conv22: 256 -> 256 channels, 200 x 40 pixels) at batch 32: sampled entries against a float64
+    sum over all 256 k pixels, and additivity over the batch (the split-K ranges change with the batch size)."""
+    gen = torch.Generator(device='cuda').manual_seed(11)
+    B, T, F, Cin, Cout = 32, 200, 40, 256, 256
+    x = torch.randn(B, T, F, Cin, device='cuda', generator=gen).to(torch.bfloat16)
+    g = (torch.randn(B, T, F, Cout, device='cuda', generator=gen) * 0.25).to(torch.bfloat16)
+    dw, db = ops.conv3x3_wgrad(x, g, with_bias=True)
+    xp = torch.nn.functional.pad(x.double(), (0, 0, 1, 1, 1, 1))                  # zero border in f and t
+    rs = np.random.RandomState(0)
+    for _ in range(6):
+        co, ci, ky, kx = int(rs.randint(Cout)), int(rs.randint(Cin)), int(rs.randint(3)), int(rs.randint(3))
+        want = float((g[..., co].double() * xp[:, ky:ky + T, kx:kx + F, ci]).sum())
+        assert abs(float(dw[co, ci, ky, kx]) - want) < 2e-3 * max(1.0, abs(want)) + 0.05, (co, ci, ky, kx)
+    wantb = g.double().sum((0, 1, 2))
+    assert float((db.double() - wantb).abs().max()) < 1e-3 * float(wantb.abs().max()) + 0.05
+    halves = ops.conv3x3_wgrad(x[:16], g[:16]) + ops.conv3x3_wgrad(x[16:], g[16:])
+    assert float((halves - dw).abs().max()) < 2e-4 * float(dw.abs().max())
