@@ -139,30 +139,38 @@ __global__ void __launch_bounds__(kColThreads) conv11_bwd_partial_kernel(const f
     __syncthreads();
     const int c8 = threadIdx.x & 15, ph = threadIdx.x >> 4;
     const int c0 = blockIdx.y * 128 + c8 * 8;
-    float acc[10][8];
+    // packed fp32x2 accumulators over channel pairs (fma.rn.f32x2: two FMAs per instruction)
+    uint64_t acc2[10][4];
 #pragma unroll
     for (int k = 0; k < 10; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+        for (int e = 0; e < 4; ++e) acc2[k][e] = pack_f32x2(0.f, 0.f);
+    const uint64_t one2 = pack_f32x2(1.f, 1.f);
     if (c0 < C)
         for (int p = ph; p < rows * F; p += 16) {
             const int tl = p / F, f = p - tl * F;
             const uint4 v = *reinterpret_cast<const uint4*>(g + ((static_cast<size_t>(b) * T + t0 + tl) * F + f) * C + c0);
             if ((v.x | v.y | v.z | v.w) == 0u) continue;        // ReLU zeros are common
-            float gv[8];
-            gv[0] = bf16_lo(v.x); gv[1] = bf16_hi(v.x); gv[2] = bf16_lo(v.y); gv[3] = bf16_hi(v.y);
-            gv[4] = bf16_lo(v.z); gv[5] = bf16_hi(v.z); gv[6] = bf16_lo(v.w); gv[7] = bf16_hi(v.w);
+            uint64_t gv2[4];
+            gv2[0] = pack_f32x2(bf16_lo(v.x), bf16_hi(v.x)); gv2[1] = pack_f32x2(bf16_lo(v.y), bf16_hi(v.y));
+            gv2[2] = pack_f32x2(bf16_lo(v.z), bf16_hi(v.z)); gv2[3] = pack_f32x2(bf16_lo(v.w), bf16_hi(v.w));
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                     const float xv = xs[(tl + dy) * W2 + f + dx];
+                    const uint64_t xv2 = pack_f32x2(xv, xv);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[dy * 3 + dx][e] = fmaf(gv[e], xv, acc[dy * 3 + dx][e]);
+                    for (int e = 0; e < 4; ++e) acc2[dy * 3 + dx][e] = fma_f32x2(gv2[e], xv2, acc2[dy * 3 + dx][e]);
                 }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[9][e] += gv[e];
+            for (int e = 0; e < 4; ++e) acc2[9][e] = fma_f32x2(gv2[e], one2, acc2[9][e]);
         }
+    float acc[10][8];
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) unpack_f32x2(acc2[k][e], acc[k][2 * e], acc[k][2 * e + 1]);
     // the two phases of a warp (lanes l and l + 16), then the 8 warps through shared memory
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
