@@ -15,6 +15,7 @@
 //   warps 4-11 = epilogue (two warps per TMEM lane quarter).  Pipelines: SMEM ring full/empty, double-buffered TMEM accumulator
 //   full/empty, persistent static tile schedule (tile = blockIdx.x + i*gridDim.x).
 #include "common.cuh"
+#include "tmap.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <stdlib.h>
@@ -467,23 +468,6 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    });
-    return fn;
-}
-
 struct ConvPlan {
     int BF, BT, BB, N, Npad;
     double cost;

@@ -24,6 +24,7 @@
 // measured 470 TFLOP/s (N = 32), 606 (N = 64), 1040 (N = 128) over the exampleModel's seven layers at batch 256;
 // splitting the taps over CTAs costs extra tile loads (3x at N = 128) which stay below the SM's L2 ingest rate.
 #include "common.cuh"
+#include "tmap.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <stdlib.h>
@@ -239,22 +240,6 @@ __global__ void conv_wgrad_reduce_kernel(const float* ws, float* dw, const float
     }
 }
 
-typedef CUresult (*WgEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static WgEncodeTiledFn wg_encode_tiled() {
-    static WgEncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<WgEncodeTiledFn>(ptr);
-    });
-    return fn;
-}
-
 struct WgradPlan {
     int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, N, tg, ng, rowsG, K16, rowsX, stages;
     uint32_t g_alloc, x_off, x_stride, stage_bytes;
@@ -346,7 +331,7 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     }
     const WgradPlan pl = wgrad_plan(B, T, F, Cin, Cout, sms);
     if (!pl.ok) { set_error("conv3x3_wgrad_bf16: unsupported shape T=%d F=%d Cin=%d Cout=%d (need Cin %% 64 == 0, F <= 254)", T, F, Cin, Cout); return 1; }
-    WgEncodeTiledFn encode = wg_encode_tiled();
+    EncodeTiledFn encode = get_encode_tiled();
     if (!encode) { set_error("conv3x3_wgrad_bf16: cuTensorMapEncodeTiled is not available from the CUDA driver"); return 1; }
     CUtensorMap tmG, tmX;
     for (int which = 0; which < 2; ++which) {
