@@ -7,7 +7,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, 'libdasv_b200.so')
+LIB_PATH = os.environ.get('DASV_LIB_PATH') or os.path.join(PKG, 'libdasv_b200.so')    # override: A/B runs of two builds
 
 _c = ctypes
 _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t

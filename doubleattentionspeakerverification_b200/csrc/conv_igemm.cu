@@ -112,7 +112,9 @@ DASV_DEVICE void conv_store(void* y, size_t idx, float v) {
     else static_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
 }
 
-template <bool PAIR>
+// DGRAD = false: the forward layer (bias + ReLU (+ pool)).  DGRAD = true: the input-gradient pass (linear epilogue, optional
+// ReLU-backward mask); a separate instantiation so that the forward's epilogue carries none of its branches.
+template <bool PAIR, bool DGRAD = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -384,7 +386,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
                                     if (g16 * 16 + j < cnt)
-                                        dst[(g16 * 16 + j) * kConvTileM] = __float2bfloat16_rn(p.relu ? fmaxf(__uint_as_float(r[j]) + bias, 0.f) : __uint_as_float(r[j]) + bias);
+                                        dst[(g16 * 16 + j) * kConvTileM] = __float2bfloat16_rn(DGRAD ? __uint_as_float(r[j]) + bias : fmaxf(__uint_as_float(r[j]) + bias, 0.f));
                             }
                         }
                     } else {
@@ -438,7 +440,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 if (!masked && t_in < conv_len(p, b))
                                     val = *reinterpret_cast<const uint4*>(buf + po * (kConvTileM * 2) + seg * 16);
                                 const size_t yoff = ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c.m * kConvTileM + seg * 8;
-                                if (p.mask != nullptr) {         // fused ReLU backward: keep the gradient where the activation was > 0
+                                if (DGRAD && p.mask != nullptr) {    // fused ReLU backward: keep the gradient where the activation was > 0
                                     const uint4 mv = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mask) + yoff);
                                     val.x &= bf16x2_positive_mask(mv.x); val.y &= bf16x2_positive_mask(mv.y);
                                     val.z &= bf16x2_positive_mask(mv.z); val.w &= bf16x2_positive_mask(mv.w);
@@ -632,7 +634,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (pair) {
-        auto kern = conv3x3_igemm_kernel<true>;
+        auto kern = p.relu ? conv3x3_igemm_kernel<true, false> : conv3x3_igemm_kernel<true, true>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
         const int clusters = static_cast<int>(n_tiles < sms / 2 ? n_tiles : sms / 2);
@@ -648,7 +650,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
         e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
         if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: pair launch failed: %s", cudaGetErrorString(e)); return 1; }
     } else {
-        auto kern = conv3x3_igemm_kernel<false>;
+        auto kern = p.relu ? conv3x3_igemm_kernel<false, false> : conv3x3_igemm_kernel<false, true>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
         const int grid = static_cast<int>(n_tiles < sms ? n_tiles : sms);
