@@ -21,7 +21,8 @@
 // (deterministic) into the reference layout [Cout][Cin][3][3].
 //
 // Roofline: tensor.  The A tile is re-read from shared memory for every MMA, so operand bytes per FLOP fall with N:
-// measured 470 TFLOP/s (N = 32), 606 (N = 64), 1040 (N = 128) over the exampleModel's seven layers at batch 256;
+// measured 470 TFLOP/s (N = 32), 606 (N = 64), 1040 (N = 128), 1141 (N = 128 on CTA pairs) over the exampleModel's seven
+// layers at batch 256;
 // splitting the taps over CTAs costs extra tile loads (3x at N = 128) which stay below the SM's L2 ingest rate.
 #include "common.cuh"
 #include "tmap.cuh"
@@ -65,7 +66,9 @@ DASV_DEVICE uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
     return d;
 }
 
-template <int TG>
+// PAIR: a 2-CTA cluster owns 256 output channels (tcgen05 cta_group::2): each CTA loads the G tile of its own 128 channels
+// and HALF of the X patch (64 of the 128 input channels), so the operand bytes an SM feeds per MMA drop from 8 KB to 6 KB.
+template <int TG, bool PAIR>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -79,15 +82,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pairs = p.n_mt * p.n_nt;
-    const int pair = static_cast<int>(blockIdx.x) % pairs;
-    const int grp = (static_cast<int>(blockIdx.x) / pairs) % p.ng, split = static_cast<int>(blockIdx.x) / (pairs * p.ng);
-    const int m = pair % p.n_mt, n = pair / p.n_mt;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                 // 0 = the leader, which issues the MMAs
+    const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int n_mu = PAIR ? p.n_mt / 2 : p.n_mt;                          // m units (tiles, or tile pairs)
+    const int pairs = n_mu * p.n_nt;
+    const int pair = unit % pairs;
+    const int grp = (unit / pairs) % p.ng, split = unit / (pairs * p.ng);
+    const int m = PAIR ? 2 * (pair % n_mu) + static_cast<int>(rank) : pair % n_mu, n = pair / n_mu;
     const int tap0 = grp * p.tg, tap1 = min(tap0 + p.tg, 9);
     const int N = p.N;
-    const int xc0 = (N == 32) ? (n >> 1) * 64 : n * N;               // first channel of the X box(es)
-    const uint32_t xhalf = (N == 32) ? static_cast<uint32_t>(n & 1) * 64u : 0u;
-    const int xboxes = N == 128 ? 2 : 1;
+    const int xc0 = PAIR ? n * N + static_cast<int>(rank) * 64 : ((N == 32) ? (n >> 1) * 64 : n * N);   // first channel of this CTA's X box(es)
+    const uint32_t xhalf = (!PAIR && N == 32) ? static_cast<uint32_t>(n & 1) * 64u : 0u;
+    const int xboxes = (!PAIR && N == 128) ? 2 : 1;
     const bool do_bias = p.ws_bias != nullptr && n == 0 && grp == 0;        // this CTA also sums G over its items
     const uint32_t bias_col = static_cast<uint32_t>(p.tg * N);
     const int item0 = split * p.items_per_split;
@@ -107,10 +113,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmX); }
-    if (warp == 2) { tmem_alloc(tmem_slot, kWgTmemCols); tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) { tmem_alloc_2sm(tmem_slot, kWgTmemCols); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, kWgTmemCols); tmem_relinquish(); }
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();           // the peer's barriers must exist before TMA completions / commits reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -122,17 +132,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 const int b = it / p.n_tt, t0 = (it % p.n_tt) * p.BT;
                 mbar_wait(&empty[st], ph ^ 1u);
                 unsigned char* sb = ring + static_cast<size_t>(st) * p.stage_bytes;
-                mbar_arrive_expect_tx(&full[st], 2 * p.g_box_bytes + xboxes * p.x_box_bytes);
-                tma_load_4d(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
-                tma_load_4d(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
-                tma_load_4d(sb + p.x_off, &tmX, &full[st], xc0, -1, t0 - 1, b);
-                if (xboxes == 2) tma_load_4d(sb + p.x_off + p.x_stride, &tmX, &full[st], xc0 + 64, -1, t0 - 1, b);
+                if (PAIR) {
+                    // both CTAs load into their own shared memory; all bytes complete on the leader's barrier
+                    if (rank == 0) mbar_arrive_expect_tx(&full[st], 2u * (2 * p.g_box_bytes + p.x_box_bytes));
+                    tma_load_4d_2sm(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
+                    tma_load_4d_2sm(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
+                    tma_load_4d_2sm(sb + p.x_off, &tmX, &full[st], xc0, -1, t0 - 1, b);
+                } else {
+                    mbar_arrive_expect_tx(&full[st], 2 * p.g_box_bytes + xboxes * p.x_box_bytes);
+                    tma_load_4d(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
+                    tma_load_4d(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
+                    tma_load_4d(sb + p.x_off, &tmX, &full[st], xc0, -1, t0 - 1, b);
+                    if (xboxes == 2) tma_load_4d(sb + p.x_off + p.x_stride, &tmX, &full[st], xc0 + 64, -1, t0 - 1, b);
+                }
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                            // MMA issuer
-            const uint32_t idesc = umma_idesc_bf16(kWgM, static_cast<uint32_t>(N)) | (1u << 15) | (1u << 16);   // A and B MN-major
+        if (lane == 0 && rank == 0) {               // MMA issuer (the pair's leader)
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kWgM : kWgM, static_cast<uint32_t>(N)) | (1u << 15) | (1u << 16);   // A and B MN-major
             // one thread issues every MMA, so the loop must cost only a few instructions per MMA: descriptors are advanced
             // by adding row offsets (in 16-byte units) to the 64-bit value, taps are unrolled
             const int frow = p.F + 2;
@@ -143,7 +161,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 toff[j] = static_cast<long long>((tap / 3) * frow + (tap % 3) - 1) * 8;          // rows * 128 B >> 4; -1 lands on the guard row
             }
             const int ntaps = tap1 - tap0;
-            const uint32_t idesc_ones = umma_idesc_bf16(kWgM, 16) | (1u << 15) | (1u << 16);
+            const uint32_t idesc_ones = umma_idesc_bf16(PAIR ? 2 * kWgM : kWgM, PAIR ? 32 : 16) | (1u << 15) | (1u << 16);
             const uint64_t ones_desc = umma_desc_mn128(smem_u32(ones), 16);
             int st = 0;
             uint32_t ph = 0;
@@ -153,12 +171,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 tc_fence_after();
                 const uint32_t sb = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
                 uint64_t a_desc = umma_desc_mn128(sb, p.g_alloc);
-                uint64_t b_desc = umma_desc_mn128(sb + p.x_off + xhalf, N == 128 ? p.x_stride : 16u);
+                uint64_t b_desc = umma_desc_mn128(sb + p.x_off + xhalf, (!PAIR && N == 128) ? p.x_stride : 16u);
                 for (int k = 0; k < p.K16; k += 16) {
 #pragma unroll
                     for (int j = 0; j < TG; ++j)
-                        if (j < ntaps)
-                            umma_bf16(tmem_base + static_cast<uint32_t>(j * N), a_desc, b_desc + static_cast<uint64_t>(toff[j]), idesc, acc);
+                        if (j < ntaps) {
+                            if (PAIR) umma_bf16_2sm(tmem_base + static_cast<uint32_t>(j * N), a_desc, b_desc + static_cast<uint64_t>(toff[j]), idesc, acc);
+                            else umma_bf16(tmem_base + static_cast<uint32_t>(j * N), a_desc, b_desc + static_cast<uint64_t>(toff[j]), idesc, acc);
+                        }
                     acc = 1u;
                     a_desc += 16 * 8;                   // 16 rows of 128 B
                     b_desc += 16 * 8;
@@ -167,14 +187,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     uint64_t g_desc = umma_desc_mn128(sb, p.g_alloc);
 #pragma unroll 1
                     for (int k = 0; k < p.K16; k += 16) {
-                        umma_bf16(tmem_base + bias_col, g_desc, ones_desc, idesc_ones, (it > item0 || k > 0) ? 1u : 0u);
+                        if (PAIR) umma_bf16_2sm(tmem_base + bias_col, g_desc, ones_desc, idesc_ones, (it > item0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(tmem_base + bias_col, g_desc, ones_desc, idesc_ones, (it > item0 || k > 0) ? 1u : 0u);
                         g_desc += 16 * 8;
                     }
                 }
-                umma_commit(&empty[st]);            // frees the stage when the MMAs above have read it
+                if (PAIR) umma_commit_2sm(&empty[st], 3); else umma_commit(&empty[st]);   // frees the stage (in both CTAs) when the MMAs above have read it
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
-            umma_commit(acc_full);
+            if (PAIR) umma_commit_2sm(acc_full, 3); else umma_commit(acc_full);
         }
     } else if (warp >= 4) {
         // epilogue: lane = output channel, 32 input channels per tap
@@ -217,8 +238,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         }
         tc_fence_before();
     }
-    __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kWgTmemCols); }
+    if (PAIR) cluster_sync_all();           // nobody leaves (or frees TMEM) while the peer may still signal into this CTA
+    else __syncthreads();
+    if (warp == 2) { tc_fence_after(); if (PAIR) tmem_dealloc_2sm(tmem_base, kWgTmemCols); else tmem_dealloc(tmem_base, kWgTmemCols); }
 }
 
 // dW[co][ci][tap] (+)= sum over splits, fixed order
@@ -241,7 +263,7 @@ __global__ void conv_wgrad_reduce_kernel(const float* ws, float* dw, const float
 }
 
 struct WgradPlan {
-    int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, N, tg, ng, rowsG, K16, rowsX, stages;
+    int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, N, tg, ng, rowsG, K16, rowsX, stages, pair;
     uint32_t g_alloc, x_off, x_stride, stage_bytes;
     size_t smem;
 };
@@ -256,7 +278,11 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     if (const char* e = getenv("DASV_WGRAD_N")) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && Cin % v == 0) pl.N = v; }
     pl.tg = pl.N == 128 ? 3 : (pl.N == 64 ? 5 : 9);
     pl.ng = pl.N == 128 ? 3 : (pl.N == 64 ? 2 : 1);
-    const int xboxes = pl.N == 128 ? 2 : 1;
+    // CTA pairs (DASV_WGRAD_PAIR=0 disables): 256 output channels per cluster, each CTA holds half of the X patch;
+    // measured 1141 vs 1040 TFLOP/s over the exampleModel's seven layers (conv22: 1426 vs 1260)
+    pl.pair = (pl.N == 128 && ((Cout + kWgM - 1) / kWgM) % 2 == 0) ? 1 : 0;
+    if (const char* e = getenv("DASV_WGRAD_PAIR")) { if (atoi(e) == 0) pl.pair = 0; }
+    const int xboxes = (pl.N == 128 && !pl.pair) ? 2 : 1;
     const uint32_t avail = 227u * 1024u - 2048u - 1024u - 256u;
     pl.BT = 176 / (F + 2);
     if (pl.BT < 1) pl.BT = 1;
@@ -281,7 +307,7 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     pl.n_items = B * pl.n_tt;
     pl.n_mt = (Cout + kWgM - 1) / kWgM;
     pl.n_nt = Cin / pl.N;
-    const int pairs = pl.n_mt * pl.n_nt * pl.ng;
+    const int pairs = pl.n_mt * pl.n_nt * pl.ng;       // CTAs per split (a CTA pair counts as two)
     // split-K factor: fill the SMs in whole waves, keep >= 2 items per CTA, bound the workspace
     int best = 1;
     double best_eff = 0.0;
@@ -355,13 +381,28 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     p.x_box_bytes = static_cast<uint32_t>(pl.rowsX) * 128u; p.x_off = pl.x_off; p.x_stride = pl.x_stride;
     p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
     if (getenv("DASV_CONV_DEBUG"))
-        fprintf(stderr, "wgrad plan: B=%d T=%d F=%d Cin=%d Cout=%d BT=%d rowsG=%d K16=%d rowsX=%d stages=%d stage_bytes=%u items=%d splits=%d N=%d\n",
-                B, T, F, Cin, Cout, pl.BT, pl.rowsG, pl.K16, pl.rowsX, pl.stages, pl.stage_bytes, pl.n_items, pl.splits, pl.N);
-    auto kern = pl.tg == 3 ? conv_wgrad_kernel<3> : (pl.tg == 5 ? conv_wgrad_kernel<5> : conv_wgrad_kernel<9>);
+        fprintf(stderr, "wgrad plan: B=%d T=%d F=%d Cin=%d Cout=%d BT=%d rowsG=%d K16=%d rowsX=%d stages=%d stage_bytes=%u items=%d splits=%d N=%d pair=%d\n",
+                B, T, F, Cin, Cout, pl.BT, pl.rowsG, pl.K16, pl.rowsX, pl.stages, pl.stage_bytes, pl.n_items, pl.splits, pl.N, pl.pair);
+    auto kern = pl.pair ? conv_wgrad_kernel<3, true>
+                        : (pl.tg == 3 ? conv_wgrad_kernel<3, false> : (pl.tg == 5 ? conv_wgrad_kernel<5, false> : conv_wgrad_kernel<9, false>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem));
     if (e != cudaSuccess) { set_error("conv3x3_wgrad_bf16: smem attribute (%zu B): %s", pl.smem, cudaGetErrorString(e)); return 1; }
     const int grid = pl.n_mt * pl.n_nt * pl.ng * pl.splits;
-    kern<<<grid, kWgThreads, pl.smem, s>>>(tmG, tmX, p);
+    if (pl.pair) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));       // n_mt is even: consecutive CTAs form the pairs
+        cfg.blockDim = dim3(kWgThreads);
+        cfg.dynamicSmemBytes = pl.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmG, tmX, p);
+        if (e != cudaSuccess) { set_error("conv3x3_wgrad_bf16: pair launch failed: %s", cudaGetErrorString(e)); return 1; }
+    } else {
+        kern<<<grid, kWgThreads, pl.smem, s>>>(tmG, tmX, p);
+    }
     if (check_launch("conv3x3_wgrad_bf16")) return 1;
     const size_t n = static_cast<size_t>(Cout) * Cin;
     conv_wgrad_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p.ws, dw, p.ws_bias, db, pl.splits, Cout, Cin, accumulate);
