@@ -11,10 +11,11 @@
 // One CTA owns a [128 co] x [N ci] tile of a GROUP of taps and a range of (utterance, frame tile) items (split-K).
 // The taps' accumulators live side by side in TMEM (taps x N <= 512 columns): N = 128 with three groups of three taps
 // (default), 64 with 5 + 4, or 32 with all nine.  Per item TMA loads
-//   G tile  [BT frames][F+2 bins] x 128 co        (two 64-channel boxes; bins -1 and F are out of bounds = zero filled)
-//   X patch [BT+2 frames][F+2 bins] x N ci        (one or two boxes, +-1 frame halo, same zero-filled border columns)
-// and the contraction runs LINEARLY over the G tile's rows r = t*(F+2) + f: the X row that pairs with G row r for tap
-// (ky,kx) is r + ky*(F+2) + kx - 1, a constant row offset, so a tap is just a different start address of the same X
+//   G tile  [BT frames][F+1 bins] x 128 co        (two 64-channel boxes; bin -1 is out of bounds = zero filled)
+//   X patch [BT+2 frames][F+1 bins] x N ci        (one or two boxes, +-1 frame halo, the same zero-filled border column)
+// One zero column per frame serves as the right border of frame t and the left border of frame t+1 (row pitch P = F+1).
+// The contraction runs LINEARLY over the G tile's rows r = t*P + f + 1: the X row that pairs with G row r for tap
+// (ky,kx) is r + ky*P + kx - 1, a constant row offset, so a tap is just a different start address of the same X
 // patch.  The zero border columns of G make the wrap-around rows harmless, rows beyond the tile are zero because the
 // whole shared memory is cleared once and TMA never writes them.
 // Partial sums go to a workspace [split][tap][co][ci] (fp32) and a second kernel adds the splits in fixed order
@@ -153,7 +154,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kWgM : kWgM, static_cast<uint32_t>(N)) | (1u << 15) | (1u << 16);   // A and B MN-major
             // one thread issues every MMA, so the loop must cost only a few instructions per MMA: descriptors are advanced
             // by adding row offsets (in 16-byte units) to the 64-bit value, taps are unrolled
-            const int frow = p.F + 2;
+            const int frow = p.F + 1;               // row pitch: F bins + the shared zero border column
             long long toff[TG];
 #pragma unroll
             for (int j = 0; j < TG; ++j) {
@@ -270,7 +271,7 @@ struct WgradPlan {
 
 static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     WgradPlan pl{};
-    if (Cin % 64 != 0 || Cout % 8 != 0 || F < 1 || F + 2 > 256 || T < 1 || B < 1) return pl;
+    if (Cin % 64 != 0 || Cout % 8 != 0 || F < 1 || F + 1 > 256 || T < 1 || B < 1) return pl;
     // input channels per tile: the operand feed from shared memory (MN-major reads measured at ~64 B/clk) bounds the MMA
     // rate, and bytes per FLOP fall with N, but 9 taps x N accumulator columns must fit the 512 TMEM columns, so the taps
     // are split into groups handled by different CTAs (each loads the tiles again): N = 128 / 3 groups, 64 / 2, 32 / 1
@@ -284,18 +285,27 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     if (const char* e = getenv("DASV_WGRAD_PAIR")) { if (atoi(e) == 0) pl.pair = 0; }
     const int xboxes = (pl.N == 128 && !pl.pair) ? 2 : 1;
     const uint32_t avail = 227u * 1024u - 2048u - 1024u - 256u;
-    pl.BT = 176 / (F + 2);
-    if (pl.BT < 1) pl.BT = 1;
-    if (pl.BT > T) pl.BT = T;
-    if (pl.BT + 2 > 256) pl.BT = 254;
+    // frames per tile: at most 176 contraction rows per stage, and among those the height that wastes the fewest MMA rows
+    // on the 16-row padding of a tile and on the partly empty last tile of an utterance
+    {
+        const int bt_max = max(1, min(min(176 / (F + 1), T), 254));
+        double best = -1.0;
+        pl.BT = bt_max;
+        for (int bt = bt_max; bt >= max(1, bt_max / 2); --bt) {
+            const int k16 = (bt * (F + 1) + 15) / 16 * 16;
+            const int ntt = (T + bt - 1) / bt;
+            const double useful = static_cast<double>(T) * F / (static_cast<double>(ntt) * k16);
+            if (useful > best + 1e-9) { best = useful; pl.BT = bt; }
+        }
+    }
     for (;; --pl.BT) {                               // largest frame tile that leaves room for two stages
-        pl.rowsG = pl.BT * (F + 2);
+        pl.rowsG = pl.BT * (F + 1);
         pl.K16 = (pl.rowsG + 15) / 16 * 16;
-        pl.rowsX = (pl.BT + 2) * (F + 2);
+        pl.rowsX = (pl.BT + 2) * (F + 1);
         pl.g_alloc = (static_cast<uint32_t>(pl.K16) * 128u + 1023u) & ~1023u;
         pl.x_off = 2 * pl.g_alloc + 1024u;
-        // X rows an MMA view may touch: -1 .. K16 - 1 + 2 (F + 2) + 1
-        pl.x_stride = ((static_cast<uint32_t>(pl.K16 + 2 * (F + 2) + 2)) * 128u + 1023u) & ~1023u;
+        // X rows an MMA view may touch: -1 .. K16 - 1 + 2 (F + 1) + 1
+        pl.x_stride = ((static_cast<uint32_t>(pl.K16 + 2 * (F + 1) + 2)) * 128u + 1023u) & ~1023u;
         pl.stage_bytes = pl.x_off + xboxes * pl.x_stride;
         if (2 * pl.stage_bytes <= avail || pl.BT == 1) break;
     }
@@ -364,7 +374,7 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
         const int C = which ? Cin : Cout;
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(F), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(F) * C * 2, static_cast<cuuint64_t>(T) * F * C * 2};
-        const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(F + 2), static_cast<cuuint32_t>(which ? pl.BT + 2 : pl.BT), 1};
+        const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(F + 1), static_cast<cuuint32_t>(which ? pl.BT + 2 : pl.BT), 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = encode(which ? &tmX : &tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(which ? x : g), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
