@@ -22,9 +22,10 @@
 // (deterministic) into the reference layout [Cout][Cin][3][3].
 //
 // Roofline: tensor.  The A tile is re-read from shared memory for every MMA, so operand bytes per FLOP fall with N:
-// measured 470 TFLOP/s (N = 32), 606 (N = 64), 1040 (N = 128), 1141 (N = 128 on CTA pairs) over the exampleModel's seven
-// layers at batch 256;
-// splitting the taps over CTAs costs extra tile loads (3x at N = 128) which stay below the SM's L2 ingest rate.
+// measured 470 TFLOP/s (N = 32), 606 (N = 64), 1040 (N = 128), 1159 (N = 128 on CTA pairs), 1248 (+ shared border column
+// and tile-height selection) over the exampleModel's seven layers at batch 256 = 0.89 of the sustained cuBLAS bf16 rate;
+// splitting the taps over CTAs costs extra tile loads (3x at N = 128) which stay below the SM's L2 ingest rate except for
+// conv12 (F = 80: one frame per tile, 3x halo).
 #include "common.cuh"
 #include "tmap.cuh"
 #include <cuda.h>
@@ -34,9 +35,8 @@
 
 namespace dasv {
 
-constexpr int kWgThreads = 256;      // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int kWgThreads = 256;      // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int kWgM = 128;            // output channels per tile (TMEM lanes)
-constexpr int kWgNMax = 64;          // input channels per tile: 32 (all nine taps in TMEM) or 64 (taps in two groups, 5 + 4)
 constexpr uint32_t kWgTmemCols = 512;
 
 struct WgradParams {
