@@ -23,9 +23,9 @@
 //
 // Roofline: tensor.  The A tile is re-read from shared memory for every MMA, so operand bytes per FLOP fall with N:
 // measured 470 TFLOP/s (N = 32), 606 (N = 64), 1040 (N = 128), 1159 (N = 128 on CTA pairs), 1248 (+ shared border column
-// and tile-height selection) over the exampleModel's seven layers at batch 256 = 0.89 of the sustained cuBLAS bf16 rate;
-// splitting the taps over CTAs costs extra tile loads (3x at N = 128) which stay below the SM's L2 ingest rate except for
-// conv12 (F = 80: one frame per tile, 3x halo).
+// and tile-height selection), 1340 (+ no frame halo when a tap group is one kernel row, taller tiles) over the
+// exampleModel's seven layers at batch 256 = 0.95 of the sustained cuBLAS bf16 rate; splitting the taps over CTAs costs
+// extra tile loads (3x at N = 128) which stay below the SM's L2 ingest rate.
 #include "common.cuh"
 #include "tmap.cuh"
 #include <cuda.h>
@@ -46,6 +46,7 @@ struct WgradParams {
     int BT, n_tt, n_items, items_per_split, splits;
     int n_mt, n_nt;
     int N, tg, ng;                   // input channels per tile, taps per group, tap groups
+    int halo;                        // frames of +-halo in the X patch: 1, or 0 when a tap group is one kernel row (tg == 3)
     int rowsG, K16, rowsX;
     uint32_t g_box_bytes;            // bytes one G box delivers (rowsG * 128)
     uint32_t g_alloc;                // K16 * 128
@@ -131,6 +132,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             uint32_t ph = 0;
             for (int it = item0; it < item1; ++it) {
                 const int b = it / p.n_tt, t0 = (it % p.n_tt) * p.BT;
+                // with a halo the patch starts one frame early; without, the group IS kernel row ky = grp: frames t0 + ky - 1 ...
+                const int tx = p.halo ? t0 - 1 : t0 + grp - 1;
                 mbar_wait(&empty[st], ph ^ 1u);
                 unsigned char* sb = ring + static_cast<size_t>(st) * p.stage_bytes;
                 if (PAIR) {
@@ -138,13 +141,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                     if (rank == 0) mbar_arrive_expect_tx(&full[st], 2u * (2 * p.g_box_bytes + p.x_box_bytes));
                     tma_load_4d_2sm(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
                     tma_load_4d_2sm(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
-                    tma_load_4d_2sm(sb + p.x_off, &tmX, &full[st], xc0, -1, t0 - 1, b);
+                    tma_load_4d_2sm(sb + p.x_off, &tmX, &full[st], xc0, -1, tx, b);
                 } else {
                     mbar_arrive_expect_tx(&full[st], 2 * p.g_box_bytes + xboxes * p.x_box_bytes);
                     tma_load_4d(sb, &tmG, &full[st], m * kWgM, -1, t0, b);
                     tma_load_4d(sb + p.g_alloc, &tmG, &full[st], m * kWgM + 64, -1, t0, b);
-                    tma_load_4d(sb + p.x_off, &tmX, &full[st], xc0, -1, t0 - 1, b);
-                    if (xboxes == 2) tma_load_4d(sb + p.x_off + p.x_stride, &tmX, &full[st], xc0 + 64, -1, t0 - 1, b);
+                    tma_load_4d(sb + p.x_off, &tmX, &full[st], xc0, -1, tx, b);
+                    if (xboxes == 2) tma_load_4d(sb + p.x_off + p.x_stride, &tmX, &full[st], xc0 + 64, -1, tx, b);
                 }
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
@@ -159,7 +162,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 #pragma unroll
             for (int j = 0; j < TG; ++j) {
                 const int tap = min(tap0 + j, 8);
-                toff[j] = static_cast<long long>((tap / 3) * frow + (tap % 3) - 1) * 8;          // rows * 128 B >> 4; -1 lands on the guard row
+                const int ky = p.halo ? tap / 3 : 0;         // without halo the patch already starts at the group's kernel row
+                toff[j] = static_cast<long long>(ky * frow + (tap % 3) - 1) * 8;                  // rows * 128 B >> 4; -1 lands on the guard row
             }
             const int ntaps = tap1 - tap0;
             const uint32_t idesc_ones = umma_idesc_bf16(PAIR ? 2 * kWgM : kWgM, PAIR ? 32 : 16) | (1u << 15) | (1u << 16);
@@ -264,7 +268,7 @@ __global__ void conv_wgrad_reduce_kernel(const float* ws, float* dw, const float
 }
 
 struct WgradPlan {
-    int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, N, tg, ng, rowsG, K16, rowsX, stages, pair;
+    int ok, BT, n_tt, n_items, splits, items_per_split, n_mt, n_nt, N, tg, ng, rowsG, K16, rowsX, stages, pair, halo;
     uint32_t g_alloc, x_off, x_stride, stage_bytes;
     size_t smem;
 };
@@ -279,16 +283,22 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     if (const char* e = getenv("DASV_WGRAD_N")) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && Cin % v == 0) pl.N = v; }
     pl.tg = pl.N == 128 ? 3 : (pl.N == 64 ? 5 : 9);
     pl.ng = pl.N == 128 ? 3 : (pl.N == 64 ? 2 : 1);
+    // three groups of three taps = one kernel row each: the X patch of a group needs no frame halo (only its own row of
+    // frames, shifted by ky - 1), which cuts its bytes by (BT + 2) / BT and lets taller tiles fit
+    pl.halo = pl.tg == 3 ? 0 : 1;
+    if (getenv("DASV_WGRAD_HALO")) pl.halo = 1;
     // CTA pairs (DASV_WGRAD_PAIR=0 disables): 256 output channels per cluster, each CTA holds half of the X patch;
     // measured 1141 vs 1040 TFLOP/s over the exampleModel's seven layers (conv22: 1426 vs 1260)
     pl.pair = (pl.N == 128 && ((Cout + kWgM - 1) / kWgM) % 2 == 0) ? 1 : 0;
     if (const char* e = getenv("DASV_WGRAD_PAIR")) { if (atoi(e) == 0) pl.pair = 0; }
     const int xboxes = (pl.N == 128 && !pl.pair) ? 2 : 1;
     const uint32_t avail = 227u * 1024u - 2048u - 1024u - 256u;
-    // frames per tile: at most 176 contraction rows per stage, and among those the height that wastes the fewest MMA rows
+    // frames per tile: at most `row_cap` contraction rows per stage, and among those the height that wastes the fewest MMA rows
     // on the 16-row padding of a tile and on the partly empty last tile of an utterance
     {
-        const int bt_max = max(1, min(min(176 / (F + 1), T), 254));
+        int row_cap = 352;                           // measured: 176 -> 1280, 256 -> 1323, 352+ -> 1330-1350 TFLOP/s (two stages must still fit)
+        if (const char* e = getenv("DASV_WGRAD_ROWS")) { const int v = atoi(e); if (v >= 16 && v <= 1024) row_cap = v; }
+        const int bt_max = max(1, min(min(row_cap / (F + 1), T), 254));
         double best = -1.0;
         pl.BT = bt_max;
         for (int bt = bt_max; bt >= max(1, bt_max / 2); --bt) {
@@ -301,11 +311,11 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
     for (;; --pl.BT) {                               // largest frame tile that leaves room for two stages
         pl.rowsG = pl.BT * (F + 1);
         pl.K16 = (pl.rowsG + 15) / 16 * 16;
-        pl.rowsX = (pl.BT + 2) * (F + 1);
+        pl.rowsX = (pl.BT + 2 * pl.halo) * (F + 1);
         pl.g_alloc = (static_cast<uint32_t>(pl.K16) * 128u + 1023u) & ~1023u;
         pl.x_off = 2 * pl.g_alloc + 1024u;
-        // X rows an MMA view may touch: -1 .. K16 - 1 + 2 (F + 1) + 1
-        pl.x_stride = ((static_cast<uint32_t>(pl.K16 + 2 * (F + 1) + 2)) * 128u + 1023u) & ~1023u;
+        // X rows an MMA view may touch: -1 .. K16 - 1 + 2 halo (F + 1) + 1
+        pl.x_stride = ((static_cast<uint32_t>(pl.K16 + 2 * pl.halo * (F + 1) + 2)) * 128u + 1023u) & ~1023u;
         pl.stage_bytes = pl.x_off + xboxes * pl.x_stride;
         if (2 * pl.stage_bytes <= avail || pl.BT == 1) break;
     }
@@ -374,7 +384,7 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
         const int C = which ? Cin : Cout;
         const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(F), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
         const cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(F) * C * 2, static_cast<cuuint64_t>(T) * F * C * 2};
-        const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(F + 1), static_cast<cuuint32_t>(which ? pl.BT + 2 : pl.BT), 1};
+        const cuuint32_t box[4] = {64, static_cast<cuuint32_t>(F + 1), static_cast<cuuint32_t>(which ? pl.BT + 2 * pl.halo : pl.BT), 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = encode(which ? &tmX : &tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(which ? x : g), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -386,7 +396,7 @@ extern "C" int dasv_conv3x3_wgrad_bf16(const void* x, const void* g, float* dw, 
     p.ws_bias = db ? p.ws + static_cast<size_t>(pl.splits) * 9 * Cout * Cin : nullptr;
     p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.Cout = Cout;
     p.BT = pl.BT; p.n_tt = pl.n_tt; p.n_items = pl.n_items; p.items_per_split = pl.items_per_split; p.splits = pl.splits;
-    p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.N = pl.N; p.tg = pl.tg; p.ng = pl.ng; p.rowsG = pl.rowsG; p.K16 = pl.K16; p.rowsX = pl.rowsX;
+    p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.N = pl.N; p.tg = pl.tg; p.ng = pl.ng; p.halo = pl.halo; p.rowsG = pl.rowsG; p.K16 = pl.K16; p.rowsX = pl.rowsX;
     p.g_box_bytes = static_cast<uint32_t>(pl.rowsG) * 128u; p.g_alloc = pl.g_alloc;
     p.x_box_bytes = static_cast<uint32_t>(pl.rowsX) * 128u; p.x_off = pl.x_off; p.x_stride = pl.x_stride;
     p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;

@@ -17,8 +17,15 @@ def pytest_configure(config):
 
 def pytest_collection_modifyitems(config, items):
     try:
+        import time
         import torch
         has_gpu = torch.cuda.is_available()
+        # a device node without a working CUDA context is a box that is still coming up: wait for it rather than skip
+        tries = 0
+        while not has_gpu and os.path.exists('/dev/nvidiactl') and tries < 10:
+            time.sleep(3.0)
+            has_gpu = torch.cuda.is_available()
+            tries += 1
     except Exception:
         has_gpu = False
     if has_gpu:
