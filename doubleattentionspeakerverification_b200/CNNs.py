@@ -77,10 +77,27 @@ class _VGG(nn.Module):
         ok = all(getattr(self, n).in_channels % 64 == 0 and getattr(self, n).out_channels % 8 == 0 for n in self._names[1:])
         return 'bf16' if ok else 'fp32'
 
+    def _precision_for(self, feature_size):
+        """The precision one call runs in: the tensor-core kernels pool in the epilogue and need an even number of bins
+        in front of every pool, so 'auto' falls back to fp32 for other feature sizes (80 -> 40 -> 20 -> 10 is fine)."""
+        prec = self.resolved_precision()
+        f, even = int(feature_size), True
+        for _ in range(len(self._names) // 2):
+            even = even and f % 2 == 0
+            f = (f + 1) // 2
+        if prec == 'bf16' and not even:
+            if self.precision == 'bf16':
+                raise ValueError('precision=bf16 needs an even number of frequency bins in front of every pool (got %d)' % feature_size)
+            return 'fp32'
+        return prec
+
     # ---------------------------------------------------------------- forward
     def forward(self, paddedInputTensor, lengths=None):
         x = paddedInputTensor
-        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        # decided from the tensors actually used: nn.DataParallel replicas have no registered parameters
+        # (self.parameters() is empty there), but their conv sub-modules carry the broadcast weights
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(
+            getattr(self, n).weight.requires_grad or getattr(self, n).bias.requires_grad for n in self._names))
         if needs_grad:
             if self.train_kernels and self._train_kernels_ok() and not x.requires_grad:
                 params = []
@@ -126,7 +143,7 @@ class _VGG(nn.Module):
     def _forward_kernels(self, x, lengths):
         x = x.float().contiguous()
         B = x.size(0)
-        prec = self.resolved_precision()
+        prec = self._precision_for(x.size(2))
         L = None if lengths is None else torch.as_tensor(lengths, device=x.device).to(torch.int32)
         c11 = getattr(self, self._names[0])
         nblocks = len(self._names) // 2

@@ -223,6 +223,8 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
     with torch.cuda.device(x.device):
         lengths = _lengths(lengths, B, x.device)
         if pool:
+            if Fq % 2:
+                raise _lib.DasvError('conv3x3_igemm_bf16: the pooled epilogue needs an even number of bins (F=%d)' % Fq)
             T2, F2 = (T + 1) // 2, Fq // 2
             shape = (B, T2, Cout * F2) if ref_layout else (B, T2, F2, Cout)
         else:
@@ -249,9 +251,18 @@ def fc_tail(pooled, w1t, b1, w2t, b2, bn_scale, bn_shift):
 
 def cosine_pairs(emb, ia, ib):
     emb = _f32(emb, 'emb')
-    ia = _dev(ia, 'ia').to(torch.int32).contiguous()
-    ib = _dev(ib, 'ib').to(torch.int32).contiguous()
+    _dev(ia, 'ia'); _dev(ib, 'ib')
     n = ia.numel()
+    if ib.numel() != n:
+        raise _lib.DasvError('cosine_pairs: %d and %d indices' % (n, ib.numel()))
+    if n:
+        # the kernel reads emb[ia], emb[ib] unchecked: validate on the host side (one small reduction)
+        both = torch.stack([ia.reshape(-1), ib.reshape(-1)])
+        lo, hi = int(both.min()), int(both.max())
+        if lo < 0 or hi >= emb.shape[0]:
+            raise _lib.DasvError('cosine_pairs: trial index out of range [0, %d): min %d, max %d' % (emb.shape[0], lo, hi))
+    ia = ia.to(torch.int32).contiguous()
+    ib = ib.to(torch.int32).contiguous()
     with torch.cuda.device(emb.device):
         scores = torch.empty((n,), device=emb.device, dtype=torch.float32)
         _lib.check(_lib.lib().dasv_cosine_pairs(_p(emb), _p(ia), _p(ib), _p(scores), n, emb.shape[1], _stream()), 'dasv_cosine_pairs')

@@ -160,6 +160,33 @@ def make_pooling_case(batch, frames, dim, heads, seed=0, with_lengths=False):
     return dict(x=x, query=query, att=att, g=g, keep=keep, lengths=lengths)
 
 
+def ragged_spec():
+    """BASELINE configs[3] at test scale: ten 2-20 s utterances (T in [200, 2000]).  Returns (frame counts, input seed of
+    utterance 0, weight seed); utterance i is ``make_logmel(1, T_i, seed0 + i)``."""
+    rs = np.random.RandomState(3)
+    return [int(T) for T in rs.randint(200, 2001, size=10)], 100, 1234
+
+
+# training-step fixtures (tests/golden/grad_<name>.npz): model + batch of one train.py step; `stride` = sampling of the
+# flattened gradients stored in the fixture
+TRAIN_STEP_SPECS = [dict(name='small', kernel_size=64, embedding_size=32, heads_number=8, num_spkrs=6, B=4, T=48, seed=3, stride=1),
+                    dict(name='k512', kernel_size=512, embedding_size=64, heads_number=16, num_spkrs=10, B=4, T=48, seed=5, stride=61)]
+
+
+def train_step_config(spec):
+    return example_config(**{k: v for k, v in spec.items() if k not in ('name', 'stride', 'B', 'T', 'seed')})
+
+
+def train_step_inputs(spec):
+    """Inputs of a training-step fixture: log-mel batch, labels, injected head keep mask."""
+    B, T, seed = spec['B'], spec['T'], spec['seed']
+    x = make_logmel(B, T, seed)
+    rs = np.random.RandomState(seed + 1000)
+    label = rs.randint(0, spec['num_spkrs'], size=(B,)).astype(np.int64)
+    keep = make_pooling_case(B, 3, vgg_output_dim('VGG4L', spec['kernel_size']), spec['heads_number'], seed=seed)['keep']
+    return x, label, keep
+
+
 def load_state_dict(module, sd, prefix=''):
     """Load a ``make_state_dict`` dictionary (numpy) into a torch module of the reference's layout."""
     import torch

@@ -156,6 +156,50 @@ def embedding_cases():
         print('embedding', name, out['emb'].shape)
 
 
+def ragged_case():
+    """exampleModel config on 2-20 s utterances, each run through the live reference at batch 1, unpadded
+    (scripts/train.py:107-131): the oracle of the padded + masked + bucketed extractor at T' up to 125."""
+    Ts, seed0, wseed = synth.ragged_spec()
+    cfg = synth.example_config(num_spkrs=7)
+    net = build_ref(cfg, synth.make_state_dict(cfg, wseed))
+    embs = []
+    with torch.no_grad():
+        for i, T in enumerate(Ts):
+            embs.append(net.getEmbedding(t(synth.make_logmel(1, T, seed=seed0 + i))).numpy())
+            print('ragged', i, T)
+    np.savez_compressed(os.path.join(OUT, 'embed_ragged.npz'), cfg=np.array(repr(vars(cfg))), lengths=np.array(Ts, np.int32),
+                        spec=np.array([seed0, wseed]), emb=np.concatenate(embs, 0))
+
+
+def gradient_cases():
+    """One train.py step (scripts/train.py:215-220): net(input, label, step) -> CrossEntropyLoss -> backward, from the
+    live reference in train mode (batch-statistics BatchNorm1d, AM-Softmax margin, head drop-out with an injected keep
+    mask).  Stores the loss, both outputs and every parameter gradient (strided sample + L2 norm for the large model)."""
+    for spec in synth.TRAIN_STEP_SPECS:
+        spec = dict(spec)
+        name, stride = spec.pop('name'), spec.pop('stride')
+        x, label, keep = synth.train_step_inputs(spec)
+        cfg = synth.train_step_config(spec)
+        net = ref_model.SpeakerClassifier(Namespace(**vars(cfg)), 'cpu')
+        load_into(net, synth.make_state_dict(cfg, spec['seed']))
+        net.train()
+        inject_keep(net.poolingLayer.headsAttention, keep)
+        pred, am = net(t(x), label=t(label), step=0)
+        loss = torch.nn.CrossEntropyLoss()(am, t(label))
+        loss.backward()
+        out = dict(loss=np.array(float(loss.detach())), pred=pred.detach().numpy(), am=am.detach().numpy(),
+                   b2_running_mean=net.b2.running_mean.numpy().copy(), b2_running_var=net.b2.running_var.numpy().copy())
+        for n, p in net.named_parameters():
+            if p.grad is None:
+                continue                                            # b1, b3: unused by forward (model.py:61-71)
+            g = p.grad.numpy().reshape(-1)
+            out['grad.' + n] = g[::stride].copy()
+            out['norm.' + n] = np.array(np.linalg.norm(g.astype(np.float64)))
+        np.savez_compressed(os.path.join(OUT, 'grad_%s.npz' % name), cfg=np.array(repr(vars(cfg))),
+                            spec=np.array([spec['B'], spec['T'], spec['seed'], stride]), **out)
+        print('gradient', name, float(loss.detach()))
+
+
 def scoring_case():
     rs = np.random.RandomState(51)
     e1 = rs.standard_normal((64, 400)).astype(np.float32)
@@ -188,12 +232,15 @@ def eer_case():
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] == 'eer':
-        eer_case()
+    if len(sys.argv) > 1:                     # regenerate single groups: eer | ragged | grad
+        for what in sys.argv[1:]:
+            {'eer': eer_case, 'ragged': ragged_case, 'grad': gradient_cases}[what]()
         sys.exit(0)
     pooling_cases()
     frontend_cases()
     embedding_cases()
+    ragged_case()
+    gradient_cases()
     scoring_case()
     eer_case()
     print('golden fixtures written to', OUT)

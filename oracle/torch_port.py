@@ -84,5 +84,38 @@ def get_embedding(x, sd, cfg):
     return tail(pooled, sd)
 
 
+def am_softmax(x, W, label, m, s, step=0, annealing=False):
+    """scripts/loss.py:37-52 (AMSoftmax.forward): cosine logits, margin m subtracted at the label, scale s."""
+    xn = x / torch.norm(x, p=2, dim=1, keepdim=True).clamp(min=1e-12)
+    wn = W / torch.norm(W, p=2, dim=0, keepdim=True).clamp(min=1e-12)
+    costh = torch.mm(xn, wn)
+    delt = torch.zeros(costh.size()).scatter_(1, label.view(-1, 1), m)
+    costh_m = costh - delt
+    alpha = max(0, 1000. / (pow(1. + 0.0001 * float(step), 2.))) if annealing else 0.       # loss.py:28-35
+    return costh, s * ((costh_m + alpha * costh) / (1 + alpha))
+
+
+def training_step(x, label, sd, cfg, keep, step=0, eps=1e-5):
+    """One train.py step (scripts/train.py:215-220) for the DoubleMHA model: SpeakerClassifier.forward in train mode
+    (scripts/model.py:61-71: batch-statistics b2, preLayer, AM-Softmax; head drop-out with the given keep mask,
+    poolings.py:39-51) -> CrossEntropyLoss -> backward.  Returns (loss, prediction, logits, {name: gradient})."""
+    names = [k for k, v in sd.items() if torch.is_tensor(v) and v.is_floating_point() and 'running' not in k
+             and not k.startswith(('b1.', 'b3.'))]
+    p = dict(sd)
+    for k in names:
+        p[k] = sd[k].clone().requires_grad_(True)
+    with torch.enable_grad():
+        feats = front_end(x, p, cfg.front_end)
+        pooled, _ = double_mha(feats, p['poolingLayer.utteranceAttention.query'], p['poolingLayer.headsAttention.att'], keep)
+        e1 = F.relu(F.linear(pooled, p['fc1.weight'], p['fc1.bias']))
+        e2 = F.batch_norm(F.relu(F.linear(e1, p['fc2.weight'], p['fc2.bias'])), None, None, p['b2.weight'], p['b2.bias'],
+                          training=True, eps=eps)
+        e3 = F.linear(e2, p['preLayer.weight'], p['preLayer.bias'])
+        pred, logits = am_softmax(e3, p['predictionLayer.W'], label, cfg.marginFactor, cfg.scalingFactor, step, cfg.annealing)
+        loss = F.cross_entropy(logits, label)
+        loss.backward()
+    return float(loss.detach()), pred.detach(), logits.detach(), {k: p[k].grad for k in names if p[k].grad is not None}
+
+
 def cosine(e1, e2):
     return F.cosine_similarity(e1, e2, dim=-1, eps=1e-8)

@@ -58,3 +58,15 @@ def min_cosine(a, b):
     b = np.asarray(b, np.float64).reshape(b.shape[0], -1)
     c = np.sum(a * b, -1) / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))
     return float(c.min())
+
+
+def report(name, **values):
+    """Append measured parity values to gpurun_out/parity_values.txt (scratch; summarised under profiles/ by hand), so the
+    bars written in the tests can be stated next to what was actually measured."""
+    try:
+        d = os.path.join(ROOT, 'gpurun_out')
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, 'parity_values.txt'), 'a') as f:
+            f.write(name + ' ' + ' '.join('%s=%.6g' % kv for kv in sorted(values.items())) + '\n')
+    except OSError:
+        pass

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, max_rel, min_cosine
+from conftest import golden, max_rel, min_cosine, report
 from doubleattentionspeakerverification_b200 import model, ops, synth, utils
 from oracle import path_oracle as po
 
@@ -33,6 +33,7 @@ def test_embedding_fp32(name):
     net, x = build(g, 'fp32')
     with torch.no_grad():
         emb = net.getEmbedding(dev(x))
+    report('embedding_fp32[%s]' % name, max_rel=max_rel(emb.cpu().numpy(), g['emb']))
     assert max_rel(emb.cpu().numpy(), g['emb']) < 1e-4               # north_star fp32 bar
     if 'emb_varlen' in g.files:
         with torch.no_grad():
@@ -51,6 +52,7 @@ def test_embedding_bf16(name):
     bar = 0.9999 if name.startswith('example') else 0.9995
     with torch.no_grad():
         emb = net.getEmbedding(dev(x))
+    report('embedding_bf16[%s]' % name, min_cos=min_cosine(emb.cpu().numpy(), g['emb']))
     assert min_cosine(emb.cpu().numpy(), g['emb']) >= bar
     if 'emb_varlen' in g.files:
         with torch.no_grad():
@@ -161,13 +163,23 @@ def test_full_size_batch_properties():
         assert min_cosine(cut.cpu().numpy(), el[:4:2].cpu().numpy()) > 0.99999
 
 
-def test_variable_length_extraction_and_trials():
-    """configs[3]/[4] at reduced scale: 2-20 s utterances through the batched extractor == per-utterance batch-1
-    runs; trial scores from the batched scoring kernels == the oracle's cosine on the same embeddings."""
+def _ragged():
+    g = golden('embed_ragged.npz')
+    Ts, seed0, wseed = synth.ragged_spec()
+    assert list(g['lengths']) == Ts
+    feats = [synth.make_logmel(1, T, seed=seed0 + i)[0] for i, T in enumerate(Ts)]
+    return g, feats, wseed
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_variable_length_extraction_and_trials(precision):
+    """configs[3]/[4] at reduced scale: ten 2-20 s utterances (T = 456 ... 1938, T' up to 122) through the bucketed, padded +
+    masked extractor (host-padded list AND device-packed path) against the LIVE REFERENCE run per utterance at batch 1
+    (tests/golden/embed_ragged.npz, scripts/train.py:107-131): fp32 < 1e-4, bf16 cosine >= 0.9999, trial scores < 1e-3."""
     from doubleattentionspeakerverification_b200 import extract
-    net = _example_net()
-    rs = np.random.RandomState(3)
-    feats = [synth.make_logmel(1, int(T), seed=100 + i)[0] for i, T in enumerate(rs.randint(200, 2001, size=10))]
+    g, feats, wseed = _ragged()
+    net = _example_net(precision, seed=wseed)
+    want = g['emb']
 
     def embed(xb, L):
         with torch.no_grad():
@@ -175,21 +187,52 @@ def test_variable_length_extraction_and_trials():
 
     emb = extract.extract_sharded(embed, feats, 'cuda', max_frames=6000)
     emb_packed = extract.extract_sharded(embed, extract.PackedUtterances(feats), 'cuda', max_frames=6000)   # device-built batches
-    assert min_cosine(emb_packed.cpu().numpy(), emb.cpu().numpy()) > 0.99999
     with torch.no_grad():
-        single = torch.cat([net.getEmbedding(dev(f[None])) for f in feats])
-    assert min_cosine(emb.cpu().numpy(), single.cpu().numpy()) > 0.9999
+        single = torch.cat([net.getEmbedding(dev(f[None])) for f in feats])                                  # batch 1, unpadded
+    for tag, got in (('list', emb), ('packed', emb_packed), ('batch1', single)):
+        got = got.cpu().numpy()
+        report('ragged[%s,%s]' % (precision, tag), max_rel=max_rel(got, want), min_cos=min_cosine(got, want))
+        if precision == 'fp32':
+            assert max_rel(got, want) < 1e-4
+        else:
+            assert min_cosine(got, want) >= 0.9999
+    rs = np.random.RandomState(3)
     trials = np.stack([rs.randint(0, 10, 200), rs.randint(0, 10, 200)], 1)
-    s = extract.score_trial_list(emb, trials).cpu().numpy()
-    e = emb.cpu().numpy()
-    assert np.max(np.abs(s - po.cosine_scores(e[trials[:, 0]], e[trials[:, 1]]))) < 1e-5
-    s_single = po.cosine_scores(single.cpu().numpy()[trials[:, 0]], single.cpu().numpy()[trials[:, 1]])
-    assert np.max(np.abs(s - s_single)) < 1e-3                       # north_star trial-score bar
+    s_ref = po.cosine_scores(want[trials[:, 0]], want[trials[:, 1]])                                         # reference embeddings
+    for e_dev in (emb, emb_packed):
+        s = extract.score_trial_list(e_dev, trials).cpu().numpy()
+        assert np.max(np.abs(s - s_ref)) < 1e-3                      # north_star trial-score bar
+        e = e_dev.cpu().numpy()
+        assert np.max(np.abs(s - po.cosine_scores(e[trials[:, 0]], e[trials[:, 1]]))) < 1e-5
     m = extract.score_cross(emb, np.arange(5), np.arange(5, 10)).cpu().numpy()
-    assert np.max(np.abs(m - po.cosine_matrix(e[:5], e[5:]))) < 1e-5
+    assert np.max(np.abs(m - po.cosine_matrix(want[:5], want[5:]))) < 1e-3
     # whole validation pass (train.py:158-184): EER from the same embeddings == the oracle's sweep on the same scores
     eer, CL, IM = extract.validate(embed, extract.PackedUtterances(feats), trials[:120], trials[120:], 'cuda', max_frames=6000)
     assert eer == po.calculate_eer(CL.cpu().numpy(), IM.cpu().numpy())
+    with pytest.raises(Exception):
+        extract.score_trial_list(emb, np.array([[0, 10]]))            # out-of-range trial index: an error, not a wild read
+
+
+def test_full_size_batch_against_oracle():
+    """BASELINE configs[2]: the whole 256 x 400 x 80 batch in bf16 against the CPU torch port of the reference (fp32),
+    every one of the 256 rows: cosine >= 0.9999, and 1 000 trial scores within 1e-3."""
+    from oracle import torch_port as tp
+    cfg = synth.example_config()
+    sd = synth.make_state_dict(cfg, 1234)
+    x = synth.make_logmel(256, 400, seed=5)
+    torch.set_num_threads(max(1, (torch.get_num_threads() or 1)))
+    want = torch.cat([tp.get_embedding(torch.from_numpy(x[i:i + 32]), tp.as_torch(sd), cfg) for i in range(0, 256, 32)]).numpy()
+    net = _example_net('bf16', 1234)
+    with torch.no_grad():
+        got = net.getEmbedding(dev(x))
+    got_np = got.cpu().numpy()
+    report('full_batch_256x400_bf16', min_cos=min_cosine(got_np, want), max_rel=max_rel(got_np, want))
+    assert min_cosine(got_np, want) >= 0.9999
+    rs = np.random.RandomState(11)
+    ia, ib = rs.randint(0, 256, 1000), rs.randint(0, 256, 1000)
+    s = utils.score_pairs(got, dev(ia), dev(ib)).cpu().numpy()
+    report('full_batch_256x400_bf16_scores', max_abs=float(np.max(np.abs(s - po.cosine_scores(want[ia], want[ib])))))
+    assert np.max(np.abs(s - po.cosine_scores(want[ia], want[ib]))) < 1e-3
 
 
 def test_million_trial_scoring_properties():
@@ -223,6 +266,7 @@ def test_other_front_ends_and_poolings_bf16(front, K, H, pm):
     with torch.no_grad():
         got = net.getEmbedding(dev(x)).cpu().numpy()
     assert got.shape == want.shape
+    report('other_front_ends_bf16[%s,%d,%d,%s]' % (front, K, H, pm), min_cos=min_cosine(got, want))
     assert min_cosine(got, want) > 0.9995
 
 

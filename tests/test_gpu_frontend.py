@@ -59,6 +59,11 @@ CASES = [  # B, T, F, Cin, Cout, pool, ref, with_lengths
     (5, 7, 10, 128, 264, True, True, True),
     (4, 50, 10, 64, 128, True, True, False),
     (1, 3, 80, 64, 8, True, False, False),
+    # the deep layers of the exampleModel config (conv32 / conv41 / conv42: K = 9*Cin = 4608 / 9216)
+    (2, 12, 20, 512, 512, True, False, True),
+    (3, 25, 10, 512, 1024, False, False, True),
+    (3, 26, 10, 1024, 1024, True, True, True),
+    (2, 9, 10, 1024, 136, True, True, False),
 ]
 
 
@@ -69,6 +74,10 @@ PAIR_CASES = [  # Cout multiple of 256: eligible for CTA pairs (cta_group::2)
     (5, 7, 10, 128, 512, True, True, True),
     (2, 30, 40, 64, 256, True, False, True),
     (7, 9, 10, 64, 256, False, False, True),
+    (2, 12, 20, 512, 512, True, False, True),
+    (3, 25, 10, 512, 1024, False, False, True),
+    (3, 26, 10, 1024, 1024, True, True, True),
+    (4, 50, 10, 1024, 256, True, True, False),
 ]
 
 

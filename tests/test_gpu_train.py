@@ -156,7 +156,7 @@ def test_front_end_training_on_kernels_matches_autograd(cls, ks):
     with torch.no_grad():
         _, acts, _, _ = CNNs._VGGTrainFn.run_forward(net, x, None)
     ref_feat = _reference_backward(net, x, acts, gout)
-    assert torch.equal(ref_feat, feat.detach())                  # same activations by construction
+    assert torch.equal(ref_feat, feat.detach())                  # harness sanity only: the reference pass is fed the kernels' activations, so this holds by construction
     stats = {n: _grad_stats(got[n], p.grad) for n, p in net.named_parameters()}
     for n, (cos, rel) in stats.items():
         assert cos > 0.9999 and rel < 1.5e-2, (n, stats)         # bf16 gradients between the layers
@@ -278,3 +278,110 @@ def test_wgrad_full_size_properties():
     assert float((db.double() - wantb).abs().max()) < 1e-3 * float(wantb.abs().max()) + 0.05
     halves = ops.conv3x3_wgrad(x[:16], g[:16]) + ops.conv3x3_wgrad(x[16:], g[16:])
     assert float((halves - dw).abs().max()) < 2e-4 * float(dw.abs().max())
+
+
+def _train_step_net(spec, **over):
+    from doubleattentionspeakerverification_b200 import model, synth
+    cfg = synth.train_step_config(spec)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, spec['seed'])).cuda().train()
+    x, label, keep = synth.train_step_inputs(spec)
+    return net, torch.from_numpy(x).cuda(), torch.from_numpy(label).cuda(), torch.from_numpy(keep).cuda()
+
+
+def _train_step(net, x, label, keep):
+    """scripts/train.py:215-220 with the head drop-out draw injected (the reference's CUDA RNG is not reproducible)."""
+    net.zero_grad()
+    draw = net.poolingLayer.headsAttention.draw_keep_mask
+    net.poolingLayer.headsAttention.draw_keep_mask = lambda *a, **k: keep
+    try:
+        pred, logits = net(x, label=label, step=0)
+    finally:
+        net.poolingLayer.headsAttention.draw_keep_mask = draw
+    loss = torch.nn.functional.cross_entropy(logits, label)
+    loss.backward()
+    return float(loss.detach()), pred.detach(), logits.detach(), {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize('name', ['small', 'k512'])
+def test_training_step_fp32_vs_live_reference(name):
+    """One train.py step (forward with labels -> CrossEntropyLoss -> backward) against the LIVE REFERENCE's loss, outputs and
+    parameter gradients (tests/golden/grad_*.npz, generated on CPU by oracle/make_golden.py with an injected keep mask).
+    Default training path: torch/cuDNN fp32 convolutions + the hand-written pooling backward: 1e-4."""
+    from conftest import golden, max_rel, report
+    from doubleattentionspeakerverification_b200 import synth
+    spec = next(s for s in synth.TRAIN_STEP_SPECS if s['name'] == name)
+    g = golden('grad_%s.npz' % name)
+    net, x, label, keep = _train_step_net(spec, precision='fp32')
+    loss, pred, logits, grads = _train_step(net, x, label, keep)
+    assert abs(loss - float(g['loss'])) < 1e-4 * abs(float(g['loss']))
+    assert max_rel(pred.cpu().numpy(), g['pred']) < 1e-4 and max_rel(logits.cpu().numpy(), g['am']) < 1e-4
+    assert max_rel(net.b2.running_mean.cpu().numpy(), g['b2_running_mean']) < 1e-4          # batch statistics (model.py:67)
+    assert max_rel(net.b2.running_var.cpu().numpy(), g['b2_running_var']) < 1e-4
+    names = [k[5:] for k in g.files if k.startswith('grad.')]
+    assert set(names) == set(grads.keys())
+    worst = 0.0
+    for n in names:
+        got = grads[n].cpu().numpy().reshape(-1)
+        worst = max(worst, max_rel(got[::spec['stride']], g['grad.' + n]))
+        assert max_rel(got[::spec['stride']], g['grad.' + n]) < 1e-4, n
+        assert abs(np.linalg.norm(got.astype(np.float64)) - float(g['norm.' + n])) < 1e-4 * float(g['norm.' + n]), n
+    report('train_step_fp32[%s]' % name, worst_grad_max_rel=worst, loss_rel=abs(loss - float(g['loss'])) / float(g['loss']))
+
+
+def test_training_step_on_kernels_vs_live_reference():
+    """The same step with train_kernels=True (bf16 tensor-core forward, input and weight gradients) against the live
+    reference's fp32 gradients.  An independently rounded bf16 forward flips ReLU / arg-max decisions that sit within a
+    bf16 ulp, so the bars are those of bf16 training arithmetic: loss within 1 %, every parameter gradient with cosine
+    >= 0.999 and relative L2 <= 5 % against the fp32 reference (measured values go to the parity report)."""
+    from conftest import golden, report
+    from doubleattentionspeakerverification_b200 import synth
+    spec = next(s for s in synth.TRAIN_STEP_SPECS if s['name'] == 'k512')
+    g = golden('grad_k512.npz')
+    net, x, label, keep = _train_step_net(spec, precision='bf16', train_kernels=True)
+    assert net.front_end._train_kernels_ok()
+    loss, pred, logits, grads = _train_step(net, x, label, keep)
+    assert abs(loss - float(g['loss'])) < 1e-2 * abs(float(g['loss']))
+    worst_cos, worst_rel = 1.0, 0.0
+    for n in [k[5:] for k in g.files if k.startswith('grad.')]:
+        got = grads[n].cpu().numpy().reshape(-1)[::spec['stride']].astype(np.float64)
+        want = g['grad.' + n].astype(np.float64)
+        cos = float(got @ want / max(np.linalg.norm(got) * np.linalg.norm(want), 1e-30))
+        rel = float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30))
+        worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
+        assert cos >= 0.999 and rel <= 5e-2, (n, cos, rel)
+    report('train_step_kernels[k512]', worst_cos=worst_cos, worst_rel_l2=worst_rel, loss_rel=abs(loss - float(g['loss'])) / float(g['loss']))
+
+
+def test_data_parallel_replicas_train_the_front_end():
+    """nn.DataParallel is the reference's multi-GPU mode (scripts/train.py:68-70).  Its replicas have no registered
+    parameters, so the front-end must decide 'training' from the conv weights themselves: every conv weight receives a
+    gradient and it equals the single-module run.  Uses two GPUs when there are two, else two replicas on one device."""
+    from doubleattentionspeakerverification_b200 import synth
+    spec = synth.TRAIN_STEP_SPECS[0]
+    net, x, label, keep = _train_step_net(spec, precision='fp32')
+    want_loss, _, _, want = _train_step(net, x, label, keep)
+    ids = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    net.zero_grad()
+    try:
+        replicas = torch.nn.parallel.replicate(net, ids)
+    except Exception as e:                                              # some torch builds refuse duplicate device ids
+        if torch.cuda.device_count() >= 2:
+            raise
+        pytest.skip('cannot replicate onto one device twice: %r' % (e,))
+    assert len(list(replicas[0].front_end.parameters())) == 0            # the situation the advisor described
+    halves = [(x[:2], label[:2], keep[:2]), (x[2:], label[2:], keep[2:])]
+    feats = []
+    for rep, (xb, lb, kb), d in zip(replicas, halves, ids):
+        f = rep.front_end(xb.to('cuda:%d' % d))
+        assert f.requires_grad, 'a DataParallel replica ran the front-end without autograd'
+        feats.append(f.to('cuda:0'))
+    torch.cat(feats).square().sum().backward()
+    single = net.front_end(x)
+    got = {n: p.grad.clone() for n, p in net.front_end.named_parameters()}
+    assert all(v is not None for v in got.values()) and len(got) == 16
+    net.zero_grad()
+    single.square().sum().backward()
+    for n, p in net.front_end.named_parameters():
+        assert float((got[n] - p.grad).abs().max()) <= 1e-4 * float(p.grad.abs().max()) + 1e-7, n

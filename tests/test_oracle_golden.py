@@ -152,3 +152,33 @@ def test_feature_host_tables_match_the_oracle():
         assert np.abs(melw - fo.mel_filterbank(sfr, 512, n_mels)).max() < 1e-6
         assert np.array_equal(rng, fo.mel_ranges(melw))
     assert fe.frames_for(np.array([511, 512, 671, 672, 16000]), 160).tolist() == [0, 1, 1, 2, 97]
+
+
+def test_ragged_fixture_short_utterances():
+    """embed_ragged.npz (2-20 s utterances through the live reference at batch 1): the torch port on the shortest ones."""
+    g = golden('embed_ragged.npz')
+    Ts, seed0, wseed = synth.ragged_spec()
+    assert list(g['lengths']) == Ts and [int(v) for v in g['spec']] == [seed0, wseed]
+    cfg = _cfg_of(g)
+    sd = tp.as_torch(synth.make_state_dict(cfg, wseed))
+    for i in np.argsort(Ts)[:2]:
+        e = tp.get_embedding(torch.from_numpy(synth.make_logmel(1, Ts[i], seed=seed0 + int(i))), sd, cfg).numpy()
+        assert max_rel(e, g['emb'][i:i + 1]) < TOL
+
+
+@pytest.mark.parametrize('spec', synth.TRAIN_STEP_SPECS, ids=lambda s: s['name'])
+def test_training_step_oracle(spec):
+    """oracle/torch_port.training_step == one train.py step of the live reference (loss, outputs, every gradient)."""
+    g = golden('grad_%s.npz' % spec['name'])
+    cfg = synth.train_step_config(spec)
+    x, label, keep = synth.train_step_inputs(spec)
+    sd = tp.as_torch(synth.make_state_dict(cfg, spec['seed']))
+    loss, pred, logits, grads = tp.training_step(torch.from_numpy(x), torch.from_numpy(label), sd, cfg, torch.from_numpy(keep))
+    assert abs(loss - float(g['loss'])) < 1e-5 * abs(float(g['loss']))
+    assert max_rel(pred.numpy(), g['pred']) < TOL and max_rel(logits.numpy(), g['am']) < TOL
+    names = [k[5:] for k in g.files if k.startswith('grad.')]
+    assert set(names) == set(grads.keys())
+    for n in names:
+        got = grads[n].numpy().reshape(-1)
+        assert max_rel(got[::spec['stride']], g['grad.' + n]) < 1e-4, n
+        assert abs(np.linalg.norm(got.astype(np.float64)) - float(g['norm.' + n])) < 1e-4 * float(g['norm.' + n]), n
