@@ -25,6 +25,18 @@ int check_launch(const char* what) {
     return 0;
 }
 
+int sm_count() {
+    static int cached[64] = {0};                 // per device ordinal; the attribute never changes
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+    int n = cached[dev];
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        cached[dev] = n;                         // benign race: every thread writes the same value
+    }
+    return n;
+}
+
 }  // namespace dasv
 
 extern "C" int dasv_abi_version(void) { return 1; }

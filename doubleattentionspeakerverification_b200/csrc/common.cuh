@@ -12,6 +12,7 @@ namespace dasv {
 // ------------------------------------------------------------------ error plumbing (host)
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);
+int  sm_count();   // multiprocessors of the current device (cached per device; 148 on B200), for grid sizing
 
 // ------------------------------------------------------------------ address helpers
 DASV_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

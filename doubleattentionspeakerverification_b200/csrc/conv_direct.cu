@@ -324,7 +324,7 @@ extern "C" int dasv_maxpool2x2(const void* x, int x_dtype, void* y, int y_dtype,
     if (!x || !y) { set_error("maxpool2x2: null argument"); return 1; }
     if (B <= 0 || T <= 0) return 0;
     const size_t n = static_cast<size_t>(B) * ((T + 1) / 2) * ((F + 1) / 2) * C;
-    const unsigned grid = static_cast<unsigned>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+    const unsigned grid = static_cast<unsigned>(n / 256 + 1 < static_cast<size_t>(sm_count()) * 16 ? n / 256 + 1 : static_cast<size_t>(sm_count()) * 16);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define DASV_POOL(TI, TO, REF) \
     maxpool2x2_kernel<TI, TO, REF><<<grid, 256, 0, s>>>(static_cast<const TI*>(x), static_cast<TO*>(y), B, T, F, C)

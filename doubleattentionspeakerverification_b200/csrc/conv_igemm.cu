@@ -20,6 +20,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace dasv {
 
@@ -518,38 +519,68 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo, boo
 
 using namespace dasv;
 
-static int conv_igemm_launch(const void* x, const void* wp, const float* bias, const int32_t* lengths, const void* mask,
-                             void* y, int y_dtype, int flags,
-                             int B, int T, int F, int Cin, int Cout, void* stream) {
-    if (!x || !wp || !y) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
-    if (Cin % kConvKC != 0 || Cin <= 0) { set_error("conv3x3_igemm_bf16: Cin=%d must be a positive multiple of 64", Cin); return 1; }
-    if (Cout <= 0 || Cout % 8 != 0) { set_error("conv3x3_igemm_bf16: Cout=%d must be a positive multiple of 8", Cout); return 1; }
-    if (F <= 0 || F % 2 != 0 || F > 256) { set_error("conv3x3_igemm_bf16: F=%d must be even and <= 256", F); return 1; }
-    const bool pool = (flags & 2) != 0, ref = (flags & 4) != 0;
-    if (!(flags & 1) && pool) { set_error("conv3x3_igemm_bf16: the pooled epilogue always applies ReLU (drop DASV_CONV_POOL or set DASV_CONV_RELU)"); return 1; }
-    if (ref && !pool) { set_error("conv3x3_igemm_bf16: REF_LAYOUT requires POOL"); return 1; }
-    if (!ref && y_dtype != 1) { set_error("conv3x3_igemm_bf16: NHWC output must be bf16"); return 1; }
-    if (y_dtype != 0 && y_dtype != 1) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
-    if (B <= 0 || T <= 0) return 0;
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15)) {
-        set_error("conv3x3_igemm_bf16: x and wp must be 16-byte aligned"); return 1;
+// ---- launch cache: the patch plan, both tensor maps (they embed the x / packed-weight addresses) and the launch shape of
+// every (addresses, shape, flags, tuning knobs) seen, so that a steady-state call is a lookup + one launch.  PyTorch's
+// caching allocator hands the same activation buffers back step after step, so a model's steps hit after the first one.
+struct ConvKey {
+    const void* x; const void* wp;
+    int B, T, F, Cin, Cout, flags, y_dtype, dgrad, dev;
+    int env_reuse, env_pair, env_sb;
+    char env_plan[24];
+};
+struct ConvEntry {
+    ConvKey key;
+    CUtensorMap tmA, tmB;
+    ConvParams p;
+    size_t smem;
+    int grid, pair;
+    unsigned long long stamp;
+};
+static std::mutex g_conv_mu;
+static ConvEntry g_conv_cache[64];
+static int g_conv_n = 0;
+static unsigned long long g_conv_clock = 0;
+
+static bool conv_key_eq(const ConvKey& a, const ConvKey& b) { return memcmp(&a, &b, sizeof(ConvKey)) == 0; }
+
+// The dynamic shared memory limit of a kernel variant is raised once per device (to the architectural 227 KB).
+static int conv_raise_smem(int variant, int dev) {
+    static bool done[4][64] = {};
+    if (dev >= 0 && dev < 64 && done[variant][dev]) return 0;
+    const int kMax = 227 * 1024;
+    cudaError_t e = cudaSuccess;
+    switch (variant) {
+        case 0: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
+        case 1: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
+        case 2: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
+        default: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
     }
+    if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute: %s", cudaGetErrorString(e)); return 1; }
+    if (dev >= 0 && dev < 64) done[variant][dev] = true;
+    return 0;
+}
+
+// Plan + tensor maps of one (x, wp, shape, flags) combination.  Returns 0 and fills `en` (everything except the per-call
+// pointers bias / lengths / mask / y), or 1 with the error set.
+static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
+    const void* x = k.x; const void* wp = k.wp;
+    const int B = k.B, T = k.T, F = k.F, Cin = k.Cin, Cout = k.Cout, flags = k.flags;
+    const bool pool = (flags & 2) != 0, ref = (flags & 4) != 0;
     EncodeTiledFn encode = get_encode_tiled();
     if (!encode) { set_error("conv3x3_igemm_bf16: cuTensorMapEncodeTiled is not available from the CUDA driver"); return 1; }
 
     // tap-row reuse is the default; DASV_CONV_REUSE=0 selects one TMA box per tap (A/B comparisons, debugging)
-    int reuse = 1;
-    if (const char* e = getenv("DASV_CONV_REUSE")) reuse = atoi(e) != 0;
+    const int reuse = k.env_reuse;
     const int cout_pad = (Cout + kConvTileM - 1) / kConvTileM * kConvTileM;
     // CTA pairs (cta_group::2, 256 channels per pair) need an even number of 128-channel tiles; DASV_CONV_PAIR=0/1 overrides
     int pair = (flags & 8) != 0;                                 // DASV_CONV_PAIR
-    if (const char* e = getenv("DASV_CONV_PAIR")) pair = atoi(e) != 0;
+    if (k.env_pair >= 0) pair = k.env_pair;
     if (!reuse || cout_pad % (2 * kConvTileM) != 0) pair = 0;
     ConvPlan pl = conv_plan(B, T, F, Cin, pool, reuse ? 2 : 0, pair != 0);
     if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Cin, pool, 2, false); }
-    if (const char* e = getenv("DASV_CONV_PLAN")) {             // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
+    if (k.env_plan[0]) {                                         // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
         int bf = 0, bt = 0, bb = 0;
-        if (sscanf(e, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
+        if (sscanf(k.env_plan, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
             int n = (bb - 1) * (bt + (reuse ? 2 : 0)) * bf + bt * bf;
             bool ok = true;
             if (pair) { ok = (bb == 1 && bt % 2 == 0 && (bt * bf) % 16 == 0) || bb == 2; n = bb == 1 ? bt * bf : 2 * ((bt * bf + 7) / 8 * 8); }
@@ -561,13 +592,12 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     const int box_t = pair ? pair_rt + 2 : pl.BT + (reuse ? 2 : 0);
     const int box_b = pair ? 1 : pl.BB;
 
-    CUtensorMap tmA, tmB;
     {
         const cuuint64_t dims[2] = {static_cast<cuuint64_t>(9) * Cin, static_cast<cuuint64_t>(cout_pad)};
         const cuuint64_t strides[1] = {static_cast<cuuint64_t>(9) * Cin * 2};
         const cuuint32_t box[2] = {kConvKC, kConvTileM};
         const cuuint32_t es[2] = {1, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
+        CUresult r = encode(&en.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: weight tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
@@ -580,21 +610,19 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
         const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(box_t),
                                    static_cast<cuuint32_t>(box_b)};
         const cuuint32_t es[4] = {1, 1, 1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+        CUresult r = encode(&en.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: activation tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
     }
 
     ConvParams p{};
-    p.bias = bias; p.lengths = lengths; p.y = y;
     p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.Cout = Cout;
     p.BF = pl.BF; p.BT = pl.BT; p.BB = pl.BB; p.N = pl.N; p.Npad = pl.Npad;
     p.n_ft = F / pl.BF; p.n_tt = (T + pl.BT - 1) / pl.BT; p.n_bt = (B + pl.BB - 1) / pl.BB; p.n_mt = cout_pad / kConvTileM;
     p.kchunks = Cin / kConvKC;
-    p.pool = pool; p.ref_layout = ref; p.y_f32 = (y_dtype == 0);
+    p.pool = pool; p.ref_layout = ref; p.y_f32 = (k.y_dtype == 0);
     p.relu = (flags & 1) ? 1 : 0;
-    p.mask = mask;
     p.reuse = reuse;
     p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
     p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;
@@ -611,7 +639,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
         if (sa < 5) { sb = 2; sa = (static_cast<int>(kAvail) - sb * static_cast<int>(p.stage_bytes)) / static_cast<int>(kConvABytes); }
         if (sa > 12) sa = 12;
         if (sa < 3) { set_error("conv3x3_igemm_bf16: rings do not fit shared memory"); return 1; }
-        if (const char* e = getenv("DASV_CONV_SB")) { const int v = atoi(e); if (v >= 2 && v <= 4) { sb = v; sa = (static_cast<int>(kAvail) - sb * static_cast<int>(p.stage_bytes)) / static_cast<int>(kConvABytes); if (sa > 12) sa = 12; } }
+        if (k.env_sb >= 2 && k.env_sb <= 4) { sb = k.env_sb; sa = (static_cast<int>(kAvail) - sb * static_cast<int>(p.stage_bytes)) / static_cast<int>(kConvABytes); if (sa > 12) sa = 12; }
         p.stages = sb; p.sa = sa;
     } else {
         p.stage_bytes = kConvABytes + ((static_cast<uint32_t>(pl.Npad) * 128u + 1023u) & ~1023u);
@@ -628,34 +656,85 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
                 B, T, F, Cin, Cout, (int)pool, reuse, pair, pl.BF, pl.BT, pl.BB, pl.N, pl.Npad, p.stages, p.sa, p.stage_bytes, p.b_bytes);
     const long long n_tiles = static_cast<long long>(pair ? p.n_mt / 2 : p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
     if (n_tiles > 0x7fffffffLL) { set_error("conv3x3_igemm_bf16: too many tiles"); return 1; }
+    en.smem = static_cast<size_t>(p.stages) * p.stage_bytes + static_cast<size_t>(p.sa) * kConvABytes + kFixed;
+    const int sms = sm_count();
+    en.grid = pair ? 2 * static_cast<int>(n_tiles < sms / 2 ? n_tiles : sms / 2) : static_cast<int>(n_tiles < sms ? n_tiles : sms);
+    en.pair = pair;
+    en.p = p;
+    en.key = k;
+    return 0;
+}
 
-    const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + static_cast<size_t>(p.sa) * kConvABytes + kFixed;
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (pair) {
-        auto kern = p.relu ? conv3x3_igemm_kernel<true, false> : conv3x3_igemm_kernel<true, true>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
-        const int clusters = static_cast<int>(n_tiles < sms / 2 ? n_tiles : sms / 2);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(static_cast<unsigned>(2 * clusters));
-        cfg.blockDim = dim3(kConvThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = static_cast<cudaStream_t>(stream);
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
-        if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: pair launch failed: %s", cudaGetErrorString(e)); return 1; }
-    } else {
-        auto kern = p.relu ? conv3x3_igemm_kernel<false, false> : conv3x3_igemm_kernel<false, true>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return 1; }
-        const int grid = static_cast<int>(n_tiles < sms ? n_tiles : sms);
-        kern<<<grid, kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+static int conv_igemm_launch(const void* x, const void* wp, const float* bias, const int32_t* lengths, const void* mask,
+                             void* y, int y_dtype, int flags,
+                             int B, int T, int F, int Cin, int Cout, void* stream) {
+    if (!x || !wp || !y) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
+    if (Cin % kConvKC != 0 || Cin <= 0) { set_error("conv3x3_igemm_bf16: Cin=%d must be a positive multiple of 64", Cin); return 1; }
+    if (Cout <= 0 || Cout % 8 != 0) { set_error("conv3x3_igemm_bf16: Cout=%d must be a positive multiple of 8", Cout); return 1; }
+    if (F <= 0 || F % 2 != 0 || F > 256) { set_error("conv3x3_igemm_bf16: F=%d must be even and <= 256", F); return 1; }
+    const bool pool = (flags & 2) != 0, ref = (flags & 4) != 0;
+    if (!(flags & 1) && pool) { set_error("conv3x3_igemm_bf16: the pooled epilogue always applies ReLU (drop DASV_CONV_POOL or set DASV_CONV_RELU)"); return 1; }
+    if (ref && !pool) { set_error("conv3x3_igemm_bf16: REF_LAYOUT requires POOL"); return 1; }
+    if (!ref && y_dtype != 1) { set_error("conv3x3_igemm_bf16: NHWC output must be bf16"); return 1; }
+    if (y_dtype != 0 && y_dtype != 1) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
+    if (B <= 0 || T <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15)) {
+        set_error("conv3x3_igemm_bf16: x and wp must be 16-byte aligned"); return 1;
     }
+    ConvKey k;
+    memset(&k, 0, sizeof(k));
+    k.x = x; k.wp = wp; k.B = B; k.T = T; k.F = F; k.Cin = Cin; k.Cout = Cout; k.flags = flags; k.y_dtype = y_dtype;
+    if (cudaGetDevice(&k.dev) != cudaSuccess) { set_error("conv3x3_igemm_bf16: no current device"); cudaGetLastError(); return 1; }
+    k.env_reuse = 1; k.env_pair = -1; k.env_sb = 0;
+    if (const char* e = getenv("DASV_CONV_REUSE")) k.env_reuse = atoi(e) != 0;
+    if (const char* e = getenv("DASV_CONV_PAIR")) k.env_pair = atoi(e) != 0;
+    if (const char* e = getenv("DASV_CONV_SB")) k.env_sb = atoi(e);
+    if (const char* e = getenv("DASV_CONV_PLAN")) strncpy(k.env_plan, e, sizeof(k.env_plan) - 1);
+
+    CUtensorMap tmA, tmB;
+    ConvParams p;
+    size_t smem; int grid, pair;
+    {
+        std::lock_guard<std::mutex> lock(g_conv_mu);
+        ConvEntry* hit = nullptr;
+        for (int i = 0; i < g_conv_n; ++i)
+            if (conv_key_eq(g_conv_cache[i].key, k)) { hit = &g_conv_cache[i]; break; }
+        if (!hit) {
+            ConvEntry en;
+            if (conv_build_entry(en, k)) return 1;
+            int slot = g_conv_n;
+            if (g_conv_n < 64) ++g_conv_n;
+            else {                                              // evict the least recently used entry
+                slot = 0;
+                for (int i = 1; i < 64; ++i) if (g_conv_cache[i].stamp < g_conv_cache[slot].stamp) slot = i;
+            }
+            g_conv_cache[slot] = en;
+            hit = &g_conv_cache[slot];
+        }
+        hit->stamp = ++g_conv_clock;
+        tmA = hit->tmA; tmB = hit->tmB; p = hit->p; smem = hit->smem; grid = hit->grid; pair = hit->pair;
+    }
+    p.bias = bias; p.lengths = lengths; p.y = y; p.mask = mask;
+
+    const int variant = (pair ? 2 : 0) + (p.relu ? 0 : 1);
+    if (conv_raise_smem(variant, k.dev)) return 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e;
+    switch (variant) {
+        case 0: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<false, false>, tmA, tmB, p); break;
+        case 1: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<false, true>, tmA, tmB, p); break;
+        case 2: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<true, false>, tmA, tmB, p); break;
+        default: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<true, true>, tmA, tmB, p); break;
+    }
+    if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("conv3x3_igemm_bf16");
 }
 

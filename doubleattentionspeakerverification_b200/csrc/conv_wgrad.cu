@@ -350,10 +350,7 @@ static WgradPlan wgrad_plan(int B, int T, int F, int Cin, int Cout, int sms) {
 using namespace dasv;
 
 extern "C" size_t dasv_conv3x3_wgrad_workspace_bytes(int B, int T, int F, int Cin, int Cout) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    cudaGetLastError();
+    const int sms = sm_count();
     const WgradPlan pl = wgrad_plan(B, T, F, Cin, Cout, sms);
     if (!pl.ok) return 0;
     return static_cast<size_t>(pl.splits) * (static_cast<size_t>(9) * Cout * Cin + Cout) * sizeof(float);

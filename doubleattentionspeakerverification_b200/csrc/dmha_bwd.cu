@@ -9,7 +9,7 @@
 
 namespace dasv {
 
-constexpr int kDmhaBwdMaxGrid = 1184;   // 148 SMs x 8: bounds the per-CTA partial workspace
+constexpr int kDmhaBwdMaxGrid = 1184;   // a workspace bound (per-CTA partials), not a machine size: grids are min(this, what the device holds)
 
 struct DmhaBwdSmem {
     uint32_t ring, q, a, dc, dq, da, dw, du, dcc, lse2, bars, total;

@@ -304,7 +304,7 @@ extern "C" int dasv_threshold_counts(const float* scores, int n, const double* t
     if (e != cudaSuccess) { set_error("threshold_counts: memset: %s", cudaGetErrorString(e)); return 1; }
     if (n <= 0) return 0;
     int grid = (n + 255) / 256;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
     const size_t smem = static_cast<size_t>(n_th) * (sizeof(double) + sizeof(unsigned int));
     threshold_counts_kernel<<<grid, 256, smem, s>>>(scores, n, thresholds, n_th, ge_counts);
     return check_launch("threshold_counts");

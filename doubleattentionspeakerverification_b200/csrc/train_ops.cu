@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) conv11_bwd_reduce_kernel(const float* par
 
 static int grid_for(size_t n, int threads) {
     size_t b = (n + threads - 1) / threads;
-    const size_t cap = 148 * 16;
+    const size_t cap = static_cast<size_t>(sm_count()) * 16;
     return static_cast<int>(b < cap ? (b ? b : 1) : cap);
 }
 
@@ -242,7 +242,7 @@ extern "C" int dasv_unpool_relu_bwd_bf16(const void* gp, int gp_ref_layout_f32, 
     return check_launch("unpool_relu_bwd");
 }
 
-extern "C" size_t dasv_bias_grad_workspace_bytes(int C) { return static_cast<size_t>(148 * 4) * C * sizeof(float); }
+extern "C" size_t dasv_bias_grad_workspace_bytes(int C) { return static_cast<size_t>(sm_count() * 4) * C * sizeof(float); }
 extern "C" size_t dasv_conv11_bwd_workspace_bytes(int B, int T, int C) {
     return static_cast<size_t>(B > 0 ? B : 0) * ((T + kC11BwdRows - 1) / kC11BwdRows) * 10 * C * sizeof(float);
 }
@@ -251,7 +251,8 @@ extern "C" int dasv_bias_grad_bf16(const void* g, float* db, void* workspace, in
     if (!g || !db || !workspace) { set_error("bias_grad: null pointer"); return 1; }
     if (C % 2 != 0) { set_error("bias_grad: C must be even"); return 1; }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int slabs = static_cast<int>(P < 148 * 4 ? (P ? P : 1) : 148 * 4);
+    const size_t slab_cap = static_cast<size_t>(sm_count()) * 4;
+    int slabs = static_cast<int>(P < slab_cap ? (P ? P : 1) : slab_cap);
     const size_t rows = (P + slabs - 1) / slabs;
     slabs = static_cast<int>((P + rows - 1) / (rows ? rows : 1));
     if (slabs < 1) slabs = 1;

@@ -80,12 +80,17 @@ class SpeakerClassifier(nn.Module):
 
     def getEmbedding(self, x, lengths=None):
         """scripts/model.py:52-59.  ``lengths`` (valid input frames per utterance) enables padded batches."""
+        out_len = None
         if lengths is None:
             encoder_output = self.front_end(x)
-            embedding0, alignment = self.poolingLayer(encoder_output)
         else:
             encoder_output = self.front_end(x, lengths=lengths)
             out_len = self.front_end.output_lengths(torch.as_tensor(lengths))
+        if isinstance(self.poolingLayer, DoubleMHA):
+            embedding0 = self.poolingLayer.pooled(encoder_output, lengths=out_len)     # the alignment is discarded here (model.py:55)
+        elif out_len is None:
+            embedding0, alignment = self.poolingLayer(encoder_output)
+        else:
             embedding0, alignment = self.poolingLayer(encoder_output, lengths=out_len)
         return self._tail(embedding0)
 

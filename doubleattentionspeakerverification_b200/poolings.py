@@ -153,6 +153,16 @@ class DoubleMHA(nn.Module):
         _, align, headw = self._run(x, lengths)
         return align, headw.view(x.size(0), self.heads_number, 1)
 
+    def pooled(self, x, lengths=None, keep=None):
+        """The pooled vector alone, for callers that discard the alignment (SpeakerClassifier.getEmbedding,
+        scripts/model.py:55): without autograd the kernel then skips the [B,T,H] alignment store altogether."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.utteranceAttention.query.requires_grad):
+            return self._run(x, lengths, keep)[0]
+        if self.training and keep is None:
+            keep = self.headsAttention.draw_keep_mask(x.size(0), self.heads_number, x.device)
+        return ops.dmha_fwd(x, self.utteranceAttention.query, self.headsAttention.att, lengths=lengths, keep=keep,
+                            need_align=False)['out']
+
     def forward(self, x, lengths=None, keep=None):
         """``keep`` ([B,H] bool) injects the training-mode head drop-out draw (for reproducible tests)."""
         out, align, _ = self._run(x, lengths, keep)
