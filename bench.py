@@ -270,9 +270,11 @@ def main():
 
         ops.conv3x3_igemm_bf16 = wrapped
         nsteps = max(3, min(args.steps, 10))
+        graphs, net.use_graphs = net.use_graphs, False      # per-launch events need the eager launches (same kernels as the graph replays)
         for i in range(nsteps):
             step_resident(i)
         torch.cuda.synchronize()
+        net.use_graphs = graphs
         ops.conv3x3_igemm_bf16 = orig
         per_layer = {n: 0.0 for n in names}
         for j, (e0, e1) in enumerate(rec):

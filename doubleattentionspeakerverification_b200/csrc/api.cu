@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace dasv {
 
@@ -23,6 +24,11 @@ int check_launch(const char* what) {
         return 1;
     }
     return 0;
+}
+
+bool pdl_enabled() {
+    const char* e = getenv("DASV_PDL");
+    return !(e && e[0] == '0');
 }
 
 int sm_count() {

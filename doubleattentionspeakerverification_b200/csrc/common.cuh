@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace dasv {
@@ -12,7 +13,21 @@ namespace dasv {
 // ------------------------------------------------------------------ error plumbing (host)
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);
+bool pdl_enabled();   // programmatic dependent launch on this library's launches (DASV_PDL=0 disables)
 int  sm_count();   // multiprocessors of the current device (cached per device; 148 on B200), for grid sizing
+
+// Launch `kern` as a programmatic dependent of the stream's previous kernel (only for kernels that call
+// griddep_wait() before touching anything an earlier kernel of the stream produced or still reads).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ------------------------------------------------------------------ address helpers
 DASV_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -190,6 +205,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);    // [24,29) M >> 4
 }
 
+// Same, with the operand formats chosen independently: fp16 (1 sign, 5 exponent, 10 mantissa bits) or bf16 (8, 7).
+__host__ __device__ constexpr uint32_t umma_idesc_f16kind(uint32_t M, uint32_t N, bool a_f16, bool b_f16) {
+    return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: everything up to griddep_wait() (barrier init, TMEM allocation, descriptor prefetch)
+// overlaps the predecessor's tail; griddep_wait() returns once the predecessor has completed and its writes are
+// visible.  griddep_launch() lets the NEXT kernel of the stream begin its own prologue early.  Both are no-ops for a
+// kernel launched without the attribute.
+DASV_DEVICE void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DASV_DEVICE void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ misc math
 DASV_DEVICE float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 DASV_DEVICE float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
@@ -197,6 +226,16 @@ DASV_DEVICE uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// fp16 storage saturates at the largest finite value instead of overflowing to infinity
+DASV_DEVICE uint32_t pack_f16(float lo, float hi) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+DASV_DEVICE uint16_t cvt_f16_bits(float v) { return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f))); }
+DASV_DEVICE uint16_t cvt_bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+// 16-bit activation formats of the tensor-core path: 1 = bf16, 2 = fp16 (the C ABI's dtype codes)
+template <int FMT> DASV_DEVICE uint16_t cvt16_bits(float v) { return FMT == 2 ? cvt_f16_bits(v) : cvt_bf16_bits(v); }
+template <int FMT> DASV_DEVICE uint32_t pack16(float lo, float hi) { return FMT == 2 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
 // packed fp32x2 arithmetic (sm_100+): one instruction, two independent fp32 FMAs on a 64-bit register pair
 DASV_DEVICE uint64_t pack_f32x2(float lo, float hi) {
     uint64_t r;

@@ -15,11 +15,13 @@ namespace dasv {
 // (channel group fastest), so the 16-byte stores of neighbouring threads form one contiguous run.
 constexpr int kC11Rows = 8;
 
-template <bool OUT_BF16>
+template <int OUT>      // 0 = f32, 1 = bf16, 2 = f16 output (the C ABI's dtype codes)
 __global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const int32_t* __restrict__ lengths,
                                                            void* __restrict__ y, int B, int T, int F, int Cout) {
     extern __shared__ float x_sm[];       // [kC11Rows + 2][F + 2], zero halo
+    griddep_launch();                     // the next kernel of the stream may start its prologue
+    griddep_wait();                       // x and the buffer behind y belong to earlier work of the stream
     const int chunks = (T + kC11Rows - 1) / kC11Rows;
     const int b = blockIdx.x / chunks, t0 = (blockIdx.x - b * chunks) * kC11Rows;
     const int L = lengths ? min(max(lengths[b], 0), T) : T;
@@ -89,14 +91,14 @@ __global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restr
             a1[e] = valid ? fmaxf(a1[e], 0.f) : 0.f;
         }
         const size_t o = (static_cast<size_t>(b) * T + t) * row_elems + static_cast<size_t>(f) * Cout + cg * 8;
-        if (OUT_BF16) {
+        if (OUT != 0) {
             uint4 v;
-            v.x = pack_bf16(a0[0], a0[1]); v.y = pack_bf16(a0[2], a0[3]);
-            v.z = pack_bf16(a0[4], a0[5]); v.w = pack_bf16(a0[6], a0[7]);
-            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + o) = v;
-            v.x = pack_bf16(a1[0], a1[1]); v.y = pack_bf16(a1[2], a1[3]);
-            v.z = pack_bf16(a1[4], a1[5]); v.w = pack_bf16(a1[6], a1[7]);
-            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + o + Cout) = v;
+            v.x = pack16<OUT>(a0[0], a0[1]); v.y = pack16<OUT>(a0[2], a0[3]);
+            v.z = pack16<OUT>(a0[4], a0[5]); v.w = pack16<OUT>(a0[6], a0[7]);
+            *reinterpret_cast<uint4*>(static_cast<uint16_t*>(y) + o) = v;
+            v.x = pack16<OUT>(a1[0], a1[1]); v.y = pack16<OUT>(a1[2], a1[3]);
+            v.z = pack16<OUT>(a1[4], a1[5]); v.w = pack16<OUT>(a1[6], a1[7]);
+            *reinterpret_cast<uint4*>(static_cast<uint16_t*>(y) + o + Cout) = v;
         } else {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(y) + o);
             op[0] = make_float4(a0[0], a0[1], a0[2], a0[3]);
@@ -115,13 +117,14 @@ __global__ void pack_w_f32_kernel(const float* __restrict__ w, float* __restrict
     const int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
     p[i] = w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap];
 }
-// [Cout_pad][9][Cin] bf16, rows co >= Cout are zero (Cout_pad = Cout rounded up to 128).
-__global__ void pack_w_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int Cout, int Cin, int Cout_pad) {
+// [Cout_pad][9][Cin] bf16 (FMT 1) or fp16 (FMT 2), rows co >= Cout are zero (Cout_pad = Cout rounded up to 128).
+template <int FMT>
+__global__ void pack_w_bf16_kernel(const float* __restrict__ w, uint16_t* __restrict__ p, int Cout, int Cin, int Cout_pad) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // [co][tap][ci]
     if (i >= static_cast<size_t>(Cout_pad) * 9 * Cin) return;
     const int ci = i % Cin, tap = (i / Cin) % 9, co = i / (static_cast<size_t>(Cin) * 9);
     const float v = co < Cout ? w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] : 0.f;
-    p[i] = __float2bfloat16_rn(v);
+    p[i] = cvt16_bits<FMT>(v);
 }
 
 // ------------------------------------------------------------------------------ fp32 implicit GEMM
@@ -273,7 +276,7 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
                                   void* y, int y_dtype, int B, int T, int F, int Cout, void* stream) {
     if (!x || !w || !bias || !y) { set_error("conv11_direct: null argument"); return 1; }
     if (Cout % 8 != 0 || Cout <= 0) { set_error("conv11_direct: Cout=%d must be a positive multiple of 8", Cout); return 1; }
-    if (y_dtype != 0 && y_dtype != 1) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
+    if (y_dtype < 0 || y_dtype > 2) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
     if (Cout > 2048) { set_error("conv11_direct: Cout=%d > 2048", Cout); return 1; }
     if (F % 2 != 0) { set_error("conv11_direct: F=%d must be even", F); return 1; }
     if (B <= 0 || T <= 0) return 0;
@@ -282,8 +285,11 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
     const int chunks = (T + kC11Rows - 1) / kC11Rows;
     const unsigned grid = static_cast<unsigned>(B) * chunks;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (y_dtype == 1) conv11_direct_kernel<true><<<grid, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
-    else conv11_direct_kernel<false><<<grid, 256, smem, s>>>(x, w, bias, lengths, y, B, T, F, Cout);
+    cudaError_t e;
+    if (y_dtype == 1) e = launch_pdl(conv11_direct_kernel<1>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout);
+    else if (y_dtype == 2) e = launch_pdl(conv11_direct_kernel<2>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout);
+    else e = launch_pdl(conv11_direct_kernel<0>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout);
+    if (e != cudaSuccess) { set_error("conv11_direct: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("conv11_direct");
 }
 
@@ -299,13 +305,19 @@ extern "C" size_t dasv_packed_conv_weight_bf16_elems(int Cout, int Cin) {
     return cp * 9 * static_cast<size_t>(Cin);
 }
 
-extern "C" int dasv_pack_conv_weight_bf16(const float* w, void* packed, int Cout, int Cin, void* stream) {
-    if (!w || !packed) { set_error("pack_conv_weight_bf16: null argument"); return 1; }
+extern "C" int dasv_pack_conv_weight_16(const float* w, void* packed, int Cout, int Cin, int dtype, void* stream) {
+    if (!w || !packed) { set_error("pack_conv_weight_16: null argument"); return 1; }
+    if (dtype != 1 && dtype != 2) { set_error("pack_conv_weight_16: dtype %d must be 1 (bf16) or 2 (f16)", dtype); return 1; }
     const int cp = (Cout + 127) / 128 * 128;
     const size_t n = static_cast<size_t>(cp) * 9 * Cin;
-    pack_w_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, cp);
-    return check_launch("pack_conv_weight_bf16");
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (dtype == 2) pack_w_bf16_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<uint16_t*>(packed), Cout, Cin, cp);
+    else pack_w_bf16_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<uint16_t*>(packed), Cout, Cin, cp);
+    return check_launch("pack_conv_weight_16");
+}
+
+extern "C" int dasv_pack_conv_weight_bf16(const float* w, void* packed, int Cout, int Cin, void* stream) {
+    return dasv_pack_conv_weight_16(w, packed, Cout, Cin, 1, stream);
 }
 
 extern "C" int dasv_conv3x3_f32(const float* x, const float* wp, const float* bias, const int32_t* lengths,

@@ -52,6 +52,7 @@ struct ConvParams {
                              // (2*BF halo rows in single-CTA reuse mode; the 8-row padding of a half in pair mode; else 0)
     int sa;                  // reuse mode: stages of the separate A (weight tile) ring
     int pair;                // 1: CTA pairs (cta_group::2): 256 channels x N pixels per pair, each CTA loads half of the patch
+    int w_f16, x_f16;        // operand formats of the MMA: weights / activations are fp16 (else bf16)
     int RT;                  // pair mode: frames of the patch half one CTA loads (without halo)
     int split_t;             // pair mode: halves split along t (BB == 1) or along the utterance (BB == 2)
 };
@@ -107,15 +108,16 @@ DASV_DEVICE uint32_t bf16x2_positive_mask(uint32_t v) {
     return lo | hi;
 }
 
-template <bool F32>
+template <bool F32, int ACT>
 DASV_DEVICE void conv_store(void* y, size_t idx, float v) {
     if (F32) static_cast<float*>(y)[idx] = v;
-    else static_cast<__nv_bfloat16*>(y)[idx] = __float2bfloat16_rn(v);
+    else static_cast<uint16_t*>(y)[idx] = cvt16_bits<ACT>(v);
 }
 
 // DGRAD = false: the forward layer (bias + ReLU (+ pool)).  DGRAD = true: the input-gradient pass (linear epilogue, optional
 // ReLU-backward mask); a separate instantiation so that the forward's epilogue carries none of its branches.
-template <bool PAIR, bool DGRAD = false>
+// ACT = format of a 16-bit output (the C ABI's dtype codes): 1 = bf16, 2 = fp16 (saturating).
+template <bool PAIR, bool DGRAD = false, int ACT = 1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ unsigned char smem_raw[];
@@ -147,6 +149,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 16 : 8); }
         fence_mbar_init();
     }
+    if (threadIdx.x == 32) griddep_launch();   // the stream's next kernel may begin its own prologue (it waits for this grid below)
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
     if (warp == 2) {
         if (PAIR) { tmem_alloc_2sm(tmem_slot, p.tmem_cols); tmem_relinquish_2sm(); }
@@ -157,6 +160,9 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the previous kernel's tail (programmatic dependent launch); x, the mask and the
+    // memory behind y belong to earlier kernels of the stream from here on
+    griddep_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -219,7 +225,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0 && rank == 0) {           // in pair mode only the leader issues (for both CTAs)
-            const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * kConvTileM : kConvTileM, static_cast<uint32_t>(p.Npad));
+            const uint32_t idesc = umma_idesc_f16kind(PAIR ? 2 * kConvTileM : kConvTileM, static_cast<uint32_t>(p.Npad), p.w_f16 != 0, p.x_f16 != 0);
             uint32_t st = 0, ph = 0, sa = 0, aph = 0, acc_it = 0;
             for (int tile = tile0; tile < n_tiles; tile += tile_step) {
                 const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
@@ -341,7 +347,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                     if (r1_ok) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
                                     m = fmaxf(m + bias, 0.f);
                                 }
-                                if (p.y_f32) conv_store<true>(p.y, row + fp0 + u, m); else conv_store<false>(p.y, row + fp0 + u, m);
+                                if (p.y_f32) conv_store<true, ACT>(p.y, row + fp0 + u, m); else conv_store<false, ACT>(p.y, row + fp0 + u, m);
                             }
                         }
                     }
@@ -363,7 +369,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 unsigned char* buf = my_stage + (chunk_it & 1u) * kConvEpiBytes;
                 if (!masked) {
                     // phase 1: this thread's channel of `cnt` output pixels -> staging[pixel][ch]
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf) + ch;
+                    uint16_t* dst = reinterpret_cast<uint16_t*>(buf) + ch;
                     if (!p.pool) {
                         // output o of utterance bb sits in accumulator column o + bb * gap_cols
 #pragma unroll
@@ -387,7 +393,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
                                     if (g16 * 16 + j < cnt)
-                                        dst[(g16 * 16 + j) * kConvTileM] = __float2bfloat16_rn(DGRAD ? __uint_as_float(r[j]) + bias : fmaxf(__uint_as_float(r[j]) + bias, 0.f));
+                                        dst[(g16 * 16 + j) * kConvTileM] = cvt16_bits<ACT>(DGRAD ? __uint_as_float(r[j]) + bias : fmaxf(__uint_as_float(r[j]) + bias, 0.f));
                             }
                         }
                     } else {
@@ -415,7 +421,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 if (j0 + u < cnt) {
                                     float m = fmaxf(__uint_as_float(v[u][0]), __uint_as_float(v[u][1]));
                                     if (r1[u]) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
-                                    dst[(j0 + u) * kConvTileM] = __float2bfloat16_rn(fmaxf(m + bias, 0.f));   // max and +bias/ReLU commute
+                                    dst[(j0 + u) * kConvTileM] = cvt16_bits<ACT>(fmaxf(m + bias, 0.f));   // max and +bias/ReLU commute
                                 }
                             }
                         }
@@ -524,7 +530,7 @@ using namespace dasv;
 // caching allocator hands the same activation buffers back step after step, so a model's steps hit after the first one.
 struct ConvKey {
     const void* x; const void* wp;
-    int B, T, F, Cin, Cout, flags, y_dtype, dgrad, dev;
+    int B, T, F, Cin, Cout, flags, y_dtype, dgrad, dev;   // flags include the operand-format bits
     int env_reuse, env_pair, env_sb;
     char env_plan[24];
 };
@@ -544,17 +550,23 @@ static unsigned long long g_conv_clock = 0;
 static bool conv_key_eq(const ConvKey& a, const ConvKey& b) { return memcmp(&a, &b, sizeof(ConvKey)) == 0; }
 
 // The dynamic shared memory limit of a kernel variant is raised once per device (to the architectural 227 KB).
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvParams);
+// variant = pair * 3 + {0: forward bf16 out, 1: input-gradient pass (bf16), 2: forward fp16 out}
+static ConvKernelFn conv_kernel_variant(int variant) {
+    switch (variant) {
+        case 0: return conv3x3_igemm_kernel<false, false, 1>;
+        case 1: return conv3x3_igemm_kernel<false, true, 1>;
+        case 2: return conv3x3_igemm_kernel<false, false, 2>;
+        case 3: return conv3x3_igemm_kernel<true, false, 1>;
+        case 4: return conv3x3_igemm_kernel<true, true, 1>;
+        default: return conv3x3_igemm_kernel<true, false, 2>;
+    }
+}
 static int conv_raise_smem(int variant, int dev) {
-    static bool done[4][64] = {};
+    static bool done[6][64] = {};
     if (dev >= 0 && dev < 64 && done[variant][dev]) return 0;
     const int kMax = 227 * 1024;
-    cudaError_t e = cudaSuccess;
-    switch (variant) {
-        case 0: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
-        case 1: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
-        case 2: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
-        default: e = cudaFuncSetAttribute(conv3x3_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax); break;
-    }
+    cudaError_t e = cudaFuncSetAttribute(conv_kernel_variant(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
     if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: smem attribute: %s", cudaGetErrorString(e)); return 1; }
     if (dev >= 0 && dev < 64) done[variant][dev] = true;
     return 0;
@@ -597,7 +609,7 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
         const cuuint64_t strides[1] = {static_cast<cuuint64_t>(9) * Cin * 2};
         const cuuint32_t box[2] = {kConvKC, kConvTileM};
         const cuuint32_t es[2] = {1, 1};
-        CUresult r = encode(&en.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
+        CUresult r = encode(&en.tmA, (flags & 16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: weight tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
@@ -610,7 +622,7 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
         const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(box_t),
                                    static_cast<cuuint32_t>(box_b)};
         const cuuint32_t es[4] = {1, 1, 1, 1};
-        CUresult r = encode(&en.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+        CUresult r = encode(&en.tmB, (flags & 32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: activation tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
@@ -623,6 +635,7 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     p.kchunks = Cin / kConvKC;
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (k.y_dtype == 0);
     p.relu = (flags & 1) ? 1 : 0;
+    p.w_f16 = (flags & 16) ? 1 : 0; p.x_f16 = (flags & 32) ? 1 : 0;
     p.reuse = reuse;
     p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
     p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;
@@ -675,8 +688,10 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     const bool pool = (flags & 2) != 0, ref = (flags & 4) != 0;
     if (!(flags & 1) && pool) { set_error("conv3x3_igemm_bf16: the pooled epilogue always applies ReLU (drop DASV_CONV_POOL or set DASV_CONV_RELU)"); return 1; }
     if (ref && !pool) { set_error("conv3x3_igemm_bf16: REF_LAYOUT requires POOL"); return 1; }
-    if (!ref && y_dtype != 1) { set_error("conv3x3_igemm_bf16: NHWC output must be bf16"); return 1; }
-    if (y_dtype != 0 && y_dtype != 1) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
+    const int act = (flags & 32) ? 2 : 1;                        // 16-bit activation format: the output's follows the input's
+    if (!ref && y_dtype != act) { set_error("conv3x3_igemm_bf16: NHWC output must have the input's 16-bit format (dtype %d)", act); return 1; }
+    if (y_dtype != 0 && y_dtype != act) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
+    if (!(flags & 1) && (flags & 48)) { set_error("conv3x3_igemm_bf16: the input-gradient pass is bf16 only"); return 1; }
     if (B <= 0 || T <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15)) {
         set_error("conv3x3_igemm_bf16: x and wp must be 16-byte aligned"); return 1;
@@ -716,24 +731,20 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     }
     p.bias = bias; p.lengths = lengths; p.y = y; p.mask = mask;
 
-    const int variant = (pair ? 2 : 0) + (p.relu ? 0 : 1);
+    const int variant = (pair ? 3 : 0) + (p.relu ? (act == 2 ? 2 : 0) : 1);
     if (conv_raise_smem(variant, k.dev)) return 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(kConvThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e;
-    switch (variant) {
-        case 0: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<false, false>, tmA, tmB, p); break;
-        case 1: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<false, true>, tmA, tmB, p); break;
-        case 2: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<true, false>, tmA, tmB, p); break;
-        default: e = cudaLaunchKernelEx(&cfg, conv3x3_igemm_kernel<true, true>, tmA, tmB, p); break;
-    }
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_variant(variant), tmA, tmB, p);
     if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("conv3x3_igemm_bf16");
 }

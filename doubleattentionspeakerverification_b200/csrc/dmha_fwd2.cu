@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
         fence_mbar_init();
     }
     __syncthreads();
+    if (tid == 0) griddep_launch();
+    griddep_wait();                 // programmatic dependent launch: x, the deal counter and the outputs' memory belong to earlier kernels
 
     if (warp == kDmhaConsumerWarps) {
         if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
@@ -346,7 +348,8 @@ static int launch_fwd2_kernel(Kern kern, DmhaFwdParams& p, size_t smem, void* wo
         // workspace once; the last CTA to leave puts it back to zero, see dmha_release_counter)
         p.ws_cnt = static_cast<int*>(workspace);
     }
-    kern<<<grid, kDmhaThreads, smem, stream>>>(p);
+    e = launch_pdl(kern, dim3(grid), dim3(kDmhaThreads), smem, stream, p);
+    if (e != cudaSuccess) { set_error("dmha_fwd: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("dmha_fwd");
 }
 

@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(512) fc_tail_kernel(const float* __restrict__ 
                                                      const float* __restrict__ bn_shift, float* __restrict__ emb,
                                                      int B, int Din, int E) {
     extern __shared__ float sm[];
+    griddep_launch();
+    griddep_wait();                          // programmatic dependent launch: `pooled` comes from the previous kernel
     float* in_sm = sm;                       // [UPB][Din]
     float* h_sm = sm + kTailUPB * Din;       // [UPB][E]
     const int b0 = blockIdx.x * kTailUPB;
@@ -262,8 +264,9 @@ extern "C" int dasv_fc_tail_f32(const float* pooled, const float* w1t, const flo
     if (smem > 200 * 1024) { set_error("fc_tail: Din=%d E=%d need %zu B of shared memory", Din, E, smem); return 1; }
     cudaError_t e = cudaFuncSetAttribute(fc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("fc_tail: smem attribute: %s", cudaGetErrorString(e)); return 1; }
-    fc_tail_kernel<<<(B + kTailUPB - 1) / kTailUPB, 512, smem, static_cast<cudaStream_t>(stream)>>>(
-        pooled, w1t, b1, w2t, b2, bn_scale, bn_shift, emb, B, Din, E);
+    e = launch_pdl(fc_tail_kernel, dim3((B + kTailUPB - 1) / kTailUPB), dim3(512), smem, static_cast<cudaStream_t>(stream),
+                   pooled, w1t, b1, w2t, b2, bn_scale, bn_shift, emb, B, Din, E);
+    if (e != cudaSuccess) { set_error("fc_tail: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("fc_tail");
 }
 

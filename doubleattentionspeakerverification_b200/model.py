@@ -7,7 +7,7 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
-from . import ops
+from . import _lib, ops
 from .CNNs import VGG3L, VGG4L, getVGG3LOutputDimension, getVGG4LOutputDimension
 from .loss import AMSoftmax
 from .poolings import Attention, DoubleMHA, MultiHeadAttention
@@ -25,16 +25,24 @@ class SpeakerClassifier(nn.Module):
         self.predictionLayer = AMSoftmax(parameters.embedding_size, parameters.num_spkrs, s=parameters.scalingFactor,
                                          m=parameters.marginFactor, annealing=parameters.annealing)
         self._tail_cache = None
+        # CUDA graphs of the inference step, one per input shape (see _graph_embedding)
+        self.use_graphs = bool(getattr(parameters, 'use_graphs', True))
+        self.graph_after = 2            # capture a shape once it has been seen this many times
+        self.max_graphs = 3
+        self._graphs = {}
+        self._shape_hits = {}
+        self._graph_clock = 0
 
     def _init_front_end(self, parameters):                            # scripts/model.py:21-29
         precision = getattr(parameters, 'precision', 'auto')
         tk = bool(getattr(parameters, 'train_kernels', False))       # training on this package's conv kernels (bf16)
+        wd = {'fp16': torch.float16, 'bf16': torch.bfloat16}[getattr(parameters, 'weight_dtype', 'fp16')]   # packed tensor-core weights
         if parameters.front_end == 'VGG3L':
             self.vector_size = getVGG3LOutputDimension(parameters.feature_size, outputChannel=parameters.kernel_size)
-            self.front_end = VGG3L(parameters.kernel_size, precision=precision, train_kernels=tk)
+            self.front_end = VGG3L(parameters.kernel_size, precision=precision, train_kernels=tk, weight_dtype=wd)
         if parameters.front_end == 'VGG4L':
             self.vector_size = getVGG4LOutputDimension(parameters.feature_size, outputChannel=parameters.kernel_size)
-            self.front_end = VGG4L(parameters.kernel_size, precision=precision, train_kernels=tk)
+            self.front_end = VGG4L(parameters.kernel_size, precision=precision, train_kernels=tk, weight_dtype=wd)
 
     def _init_pooling(self, parameters):                              # scripts/model.py:31-41
         self.pooling_method = parameters.pooling_method
@@ -79,7 +87,54 @@ class SpeakerClassifier(nn.Module):
         return self.b2(F.relu(self.fc2(embedding1)))                  # batch statistics / autograd: stock torch
 
     def getEmbedding(self, x, lengths=None):
-        """scripts/model.py:52-59.  ``lengths`` (valid input frames per utterance) enables padded batches."""
+        """scripts/model.py:52-59.  ``lengths`` (valid input frames per utterance) enables padded batches.
+
+        Repeated fixed-shape inference calls (eval mode, no autograd, no lengths) are replayed from a CUDA graph of the
+        step's ten kernel launches, captured per input shape: the launches then cost no host time and keep their
+        programmatic-dependent-launch edges (a 4 s utterance at batch 1: 0.32 ms eager)."""
+        if (self.use_graphs and lengths is None and not self.training and not torch.is_grad_enabled()
+                and isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 3 and x.dtype == torch.float32
+                and not torch.cuda.is_current_stream_capturing()):
+            out = self._graph_embedding(x)
+            if out is not None:
+                return out
+        return self._embedding(x, lengths)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the inference step
+    def _graph_tag(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + [self.b2.running_mean, self.b2.running_var])
+
+    def _graph_embedding(self, x):
+        key = (tuple(x.shape), x.device.index, self.front_end.resolved_precision())
+        ent = self._graphs.get(key)
+        tag = self._graph_tag()
+        if ent is not None and ent['tag'] != tag:                 # weights changed (optimizer step, load_state_dict): re-capture
+            del self._graphs[key]
+            ent = None
+        if ent is None:
+            hits = self._shape_hits.get(key, 0) + 1
+            self._shape_hits[key] = hits
+            if hits <= self.graph_after:
+                return None                                        # eager until the shape repeats (also warms the caches up)
+            if len(self._shape_hits) > 64:
+                self._shape_hits.clear()
+            while len(self._graphs) >= self.max_graphs:            # every graph pins its own activation memory
+                del self._graphs[min(self._graphs, key=lambda k: self._graphs[k]['used'])]
+            static_x = x.clone()
+            before = sum(_lib.LAUNCHES.values())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._embedding(static_x, None)
+            ent = dict(graph=graph, x=static_x, out=static_out, tag=tag, used=0, launches=sum(_lib.LAUNCHES.values()) - before)
+            self._graphs[key] = ent
+        self._graph_clock += 1
+        ent['used'] = self._graph_clock                             # least recently used goes first
+        ent['x'].copy_(x)
+        ent['graph'].replay()
+        _lib.LAUNCHES['graph_replay'] = _lib.LAUNCHES.get('graph_replay', 0) + ent['launches']
+        return ent['out'].clone()
+
+    def _embedding(self, x, lengths=None):
         out_len = None
         if lengths is None:
             encoder_output = self.front_end(x)

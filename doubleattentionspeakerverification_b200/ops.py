@@ -6,8 +6,8 @@ import torch
 
 from . import _lib
 
-F32, BF16 = 0, 1
-CONV_RELU, CONV_POOL, CONV_REF_LAYOUT, CONV_PAIR = 1, 2, 4, 8
+F32, BF16, F16 = 0, 1, 2
+CONV_RELU, CONV_POOL, CONV_REF_LAYOUT, CONV_PAIR, CONV_W_F16, CONV_X_F16 = 1, 2, 4, 8, 16, 32
 
 
 def _dev(t, name):
@@ -29,7 +29,9 @@ def _dtype_code(t, name):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
-    raise _lib.DasvError('%s: dtype %s not supported (float32 or bfloat16)' % (name, t.dtype))
+    if t.dtype == torch.float16:
+        return F16
+    raise _lib.DasvError('%s: dtype %s not supported (float32, bfloat16 or float16)' % (name, t.dtype))
 
 
 def _f32(t, name):
@@ -146,13 +148,15 @@ def pack_conv_weight_f32(w):
     return p
 
 
-def pack_conv_weight_bf16(w):
+def pack_conv_weight_bf16(w, dtype=torch.bfloat16):
+    """w [Cout,Cin,3,3] f32 -> the tensor-core A operand [Cout_pad][9][Cin] in ``dtype`` (bfloat16, or float16 for three
+    more mantissa bits: weights are far inside fp16's range)."""
     w = _f32(w, 'w')
     Cout, Cin = w.shape[0], w.shape[1]
     with torch.cuda.device(w.device):
         n = int(_lib.lib().dasv_packed_conv_weight_bf16_elems(Cout, Cin))
-        p = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
-        _lib.check(_lib.lib().dasv_pack_conv_weight_bf16(_p(w), _p(p), Cout, Cin, _stream()), 'dasv_pack_conv_weight_bf16')
+        p = torch.empty((n,), device=w.device, dtype=dtype)
+        _lib.check(_lib.lib().dasv_pack_conv_weight_16(_p(w), _p(p), Cout, Cin, _dtype_code(p, 'packed'), _stream()), 'dasv_pack_conv_weight_16')
     return p
 
 
@@ -213,13 +217,15 @@ def maxpool2x2(x, ref_layout=False, out_dtype=None):
 
 
 def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False, relu=True):
-    """bf16 tcgen05 implicit-GEMM conv3x3 + bias + ReLU (+ fused 2x2 ceil max-pool) on NHWC bf16."""
+    """tcgen05 implicit-GEMM conv3x3 + bias + ReLU (+ fused 2x2 ceil max-pool) on NHWC 16-bit activations (bf16 or fp16; the
+    output has the input's format) with bf16 or fp16 packed weights, fp32 accumulation."""
     _dev(x, 'x')
-    if x.dtype != torch.bfloat16:
-        raise _lib.DasvError('conv3x3_igemm_bf16: x must be bfloat16')
+    if x.dtype not in (torch.bfloat16, torch.float16) or wp.dtype not in (torch.bfloat16, torch.float16):
+        raise _lib.DasvError('conv3x3_igemm_bf16: x and wp must be bfloat16 or float16')
     x = x.contiguous()
     B, T, Fq, Cin = x.shape
     flags = (CONV_RELU if relu else 0) | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0) | (CONV_PAIR if pair else 0)
+    flags |= (CONV_W_F16 if wp.dtype == torch.float16 else 0) | (CONV_X_F16 if x.dtype == torch.float16 else 0)
     with torch.cuda.device(x.device):
         lengths = _lengths(lengths, B, x.device)
         if pool:
@@ -229,7 +235,9 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
             shape = (B, T2, Cout * F2) if ref_layout else (B, T2, F2, Cout)
         else:
             shape = (B, T, Fq, Cout)
-        y = torch.empty(shape, device=x.device, dtype=out_dtype if ref_layout else torch.bfloat16)
+        if ref_layout and out_dtype != torch.float32:
+            out_dtype = x.dtype
+        y = torch.empty(shape, device=x.device, dtype=out_dtype if ref_layout else x.dtype)
         rc = _lib.lib().dasv_conv3x3_igemm_bf16(_p(x), _p(wp), _p(_f32(bias, 'bias')), _p(lengths), _p(y), _dtype_code(y, 'y'),
                                                 flags, B, T, Fq, Cin, Cout, _stream())
         _lib.check(rc, 'dasv_conv3x3_igemm_bf16')

@@ -12,7 +12,7 @@
  *   - `stream` is a cudaStream_t passed as void*; nothing synchronises the host, allocates,
  *     or creates streams; all functions are re-entrant per device;
  *   - return 0 on success; non-zero = error, message via dasv_last_error() (thread-local);
- *   - dtype codes: DASV_F32 = 0, DASV_BF16 = 1;
+ *   - dtype codes: DASV_F32 = 0, DASV_BF16 = 1, DASV_F16 = 2 (front-end activations / packed weights only);
  *   - "nullable" arguments may be NULL to skip that input/output.
  */
 #ifndef DASV_B200_H
@@ -27,12 +27,15 @@ extern "C" {
 
 #define DASV_F32 0
 #define DASV_BF16 1
+#define DASV_F16 2
 
 /* conv flags */
 #define DASV_CONV_RELU 1        /* apply ReLU after bias (set by the VGG blocks; clear = linear, for the input-gradient pass, no POOL) */
 #define DASV_CONV_POOL 2        /* fuse max_pool2d(2, stride 2, ceil_mode) into the epilogue         */
 #define DASV_CONV_REF_LAYOUT 4  /* with POOL: write [B,T',C*F'] with feature = c*F'+f (CNNs.py:88-89) */
 #define DASV_CONV_PAIR 8        /* run on CTA pairs (tcgen05 cta_group::2, 256 channels x N pixels per pair); same results */
+#define DASV_CONV_W_F16 16      /* wp was packed as fp16 (dasv_pack_conv_weight_16 with DASV_F16) */
+#define DASV_CONV_X_F16 32      /* x (and an NHWC y) are fp16 instead of bf16; fp16 stores saturate at +-65504 */
 
 int dasv_abi_version(void);
 const char* dasv_last_error(void);
@@ -108,6 +111,9 @@ int dasv_conv11_tc_bf16(const float* x, const float* w, const float* bias, const
 int dasv_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, void* stream);
 size_t dasv_packed_conv_weight_bf16_elems(int Cout, int Cin);
 int dasv_pack_conv_weight_bf16(const float* w, void* packed, int Cout, int Cin, void* stream);
+/* The same packing with the 16-bit format chosen: dtype DASV_BF16 or DASV_F16 (three more mantissa bits; weights sit far
+ * inside fp16's range).  Pass DASV_CONV_W_F16 to the convolution for fp16-packed weights. */
+int dasv_pack_conv_weight_16(const float* w, void* packed, int Cout, int Cin, int dtype, void* stream);
 
 /* fp32 CUDA-core implicit-GEMM conv3x3 + bias + ReLU (+ row mask): the fp32-parity path
  * (1e-4 relative) for conv12..conv42 (CNNs.py:73-85).  x [B,T,F,Cin] f32, wp packed f32,
@@ -126,8 +132,12 @@ int dasv_maxpool2x2(const void* x, int x_dtype, void* y, int y_dtype, int ref_la
  * (CNNs.py:73-86, one call per conv).  x [B,T,F,Cin] bf16, wp [Cout][9][Cin] bf16, bias f32.
  * Output: without POOL y [B,T,F,Cout] bf16; with POOL y [B,T2,F2,Cout] bf16, or with
  * REF_LAYOUT y [B,T2,Cout*F2] in y_dtype (T2 = ceil(T/2), F2 = F/2).
+ * Operand formats: the MMA is tcgen05 kind::f16, whose two operands are bf16 or fp16 independently, so the packed
+ * weights may be fp16 (DASV_CONV_W_F16) and/or the activations fp16 (DASV_CONV_X_F16: x and an NHWC y are fp16,
+ * y_dtype = DASV_F16); accumulation is fp32 either way.
  * Requirements: Cin % 64 == 0, Cout % 8 == 0, F even and <= 256 (the reference's 80-bin input
- * gives F = 80, 40, 20, 10).  Needs the CUDA driver (tensor maps are encoded per call). */
+ * gives F = 80, 40, 20, 10).  Needs the CUDA driver; the plan and both tensor maps are cached per
+ * (x, wp, shape, flags), and the launch is a programmatic dependent of the stream's previous kernel. */
 int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, const int32_t* lengths,
                             void* y, int y_dtype, int flags,
                             int B, int T, int F, int Cin, int Cout, void* stream);

@@ -27,6 +27,7 @@ def main():
     cfg = synth.example_config()
     cfg.precision = 'bf16'
     net = synth.load_state_dict(model.SpeakerClassifier(cfg, dev), synth.make_state_dict(cfg, 1234)).to(dev).eval()
+    net.use_graphs = False            # this script drives the graph itself
     xs = [torch.from_numpy(synth.make_logmel(args.batch, args.frames, seed=100 + i)).to(dev) for i in range(2)]
 
     def step(i):
@@ -110,6 +111,24 @@ def main():
     print('graph == eager   :', bool(torch.equal(out, ref)))
     print('cuda graph       : %.3f ms/step' % timed(lambda i: g.replay(), args.steps))
     print('eager again      : %.3f ms/step' % timed(step, args.steps))
+    net.use_graphs = True
+    for i in range(4):
+        step(i)
+    print('module graphs    : %.3f ms/step (getEmbedding with use_graphs, incl. the input copy and output clone)' % timed(step, args.steps))
+    net.use_graphs = False
+    for b in (1, 8):
+        xb = xs[0][:b].contiguous()
+        f = lambda i: net.getEmbedding(xb)
+        with torch.no_grad():
+            for i in range(4):
+                f(i)
+            te = timed(f, 50)
+            net.use_graphs = True
+            for i in range(4):
+                f(i)
+            tg = timed(f, 50)
+            net.use_graphs = False
+        print('batch %d latency  : eager %.3f ms, graph %.3f ms' % (b, te, tg))
 
     # ---- conv layers alone, back to back
     fe = net.front_end

@@ -63,6 +63,22 @@ def test_embedding_bf16(name):
         assert abs(float(s[0]) - float(s_ref[0])) < 1e-3             # north_star trial-score bar
 
 
+@pytest.mark.parametrize('precision,weight_dtype', [('bf16', 'bf16'), ('fp16', 'fp16')])
+def test_embedding_other_16bit_formats(precision, weight_dtype):
+    """The all-bf16 operand choice (round 1's) and the all-fp16 one, on the exampleModel fixtures."""
+    for name in ('example', 'example_b2'):
+        g = golden('embed_%s.npz' % name)
+        cfg = Namespace(**ast.literal_eval(str(g['cfg'])))
+        cfg.precision, cfg.weight_dtype = precision, weight_dtype
+        B, T, seed = [int(v) for v in g['spec']]
+        net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, seed)).cuda().eval()
+        with torch.no_grad():
+            emb = net.getEmbedding(dev(synth.make_logmel(B, T, seed)))
+        c = min_cosine(emb.cpu().numpy(), g['emb'])
+        report('embedding_%s_w%s[%s]' % (precision, weight_dtype, name), min_cos=c, max_rel=max_rel(emb.cpu().numpy(), g['emb']))
+        assert c >= (0.99999 if precision == 'fp16' else 0.9999)
+
+
 def test_state_dict_contract():
     cfg = synth.example_config(kernel_size=64, embedding_size=32, heads_number=8, num_spkrs=5)
     net = model.SpeakerClassifier(cfg, 'cuda')

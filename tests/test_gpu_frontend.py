@@ -113,6 +113,45 @@ def test_igemm_vs_oracle(B, T, F, Cin, Cout, pool, ref, with_len, pair=False):
     assert max_rel(y.float().cpu().numpy(), ref_y) < tol
 
 
+def _round_to(a, dtype):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).float().numpy()
+
+
+@pytest.mark.parametrize('xdt,wdt', [(torch.bfloat16, torch.float16), (torch.float16, torch.float16), (torch.float16, torch.bfloat16)])
+@pytest.mark.parametrize('B,T,F,Cin,Cout,pool,ref,pair', [(2, 21, 40, 128, 128, True, False, False), (3, 13, 20, 128, 256, False, False, True),
+                                                         (3, 26, 10, 512, 512, True, True, True), (2, 9, 10, 64, 136, True, True, False)])
+def test_igemm_operand_formats(xdt, wdt, B, T, F, Cin, Cout, pool, ref, pair):
+    """tcgen05 kind::f16 takes bf16 or fp16 per operand: fp16-packed weights under bf16 activations (the default of the
+    inference path), and fp16 activations.  Inputs exactly representable in their formats, fp32 accumulation: only the
+    summation order and the output rounding (2^-9 bf16 / 2^-12 fp16) differ from the oracle."""
+    rs = np.random.RandomState(7 + B + Cin)
+    x = _round_to(np.maximum(rs.standard_normal((B, T, F, Cin)), 0).astype(np.float32), xdt)
+    w = _round_to((rs.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32), wdt)
+    bias = (rs.standard_normal((Cout,)) * 0.1).astype(np.float32)
+    lengths = rs.randint(1, T + 1, size=(B,)).astype(np.int32)
+    lengths[0] = T
+    x = po._zero_rows(x, lengths)
+    ref_y = po._zero_rows(po.relu(po.conv3x3_same(x, w, bias)), lengths)
+    if pool:
+        ref_y = po.maxpool2x2_ceil(ref_y)
+        if ref:
+            Bq, T2, F2, C = ref_y.shape
+            ref_y = ref_y.transpose(0, 1, 3, 2).reshape(Bq, T2, C * F2)
+    y = ops.conv3x3_igemm_bf16(dev(x, xdt), ops.pack_conv_weight_bf16(dev(w), wdt), dev(bias), Cout, lengths=dev(lengths),
+                               pool=pool, ref_layout=ref, out_dtype=torch.float32, pair=pair)
+    assert tuple(y.shape) == ref_y.shape and y.dtype == (torch.float32 if ref else xdt)
+    tol = 1e-4 if ref else (6e-3 if xdt == torch.bfloat16 else 8e-4)
+    assert max_rel(y.float().cpu().numpy(), ref_y) < tol
+
+
+def test_fp16_store_saturates():
+    """fp16 activations saturate at the largest finite value instead of overflowing to infinity."""
+    x = torch.full((1, 4, 80), 3.0e4, device='cuda')
+    w = torch.ones((8, 1, 3, 3), device='cuda')
+    y = ops.conv11_direct(x, w, torch.zeros(8, device='cuda'), None, out_dtype=torch.float16)
+    assert bool(torch.isfinite(y).all()) and float(y.max()) == 65504.0
+
+
 def test_conv11_and_pool_kernels():
     rs = np.random.RandomState(5)
     x = rs.standard_normal((2, 9, 80)).astype(np.float32)
