@@ -6,11 +6,10 @@ Inference (no autograd) runs on this package's sm_100a kernels, NHWC end to end:
   * ``precision='bf16'``: conv11 direct kernel -> bf16, then tcgen05 implicit-GEMM convs with
     bias + ReLU + 2x2 ceil max-pool (+ length mask, + the final [B,T',C*F'] re-layout) fused in the
     epilogue.  Needs every tensor-core conv to have Cin % 64 == 0 (kernel_size >= 512 for VGG4L).
-    Activations are bf16 (fp32's range); the packed weights are fp16 by default (``weight_dtype``): the MMA takes
-    either 16-bit format per operand at the same speed and weights never leave fp16's range, which removes the weight
-    rounding's half of the error (embedding cosine 0.99991 -> 0.99998 on the exampleModel config).
-  * ``precision='fp16'``: the same kernels with fp16 activations too (saturating stores): eight times finer rounding
-    than bf16 at the same speed, for models whose activations stay below 65504.
+  * ``precision='fp16'``: the same kernels with fp16 activations and weights (tcgen05 kind::f16 takes either 16-bit
+    format, but both operands must have the same one: a mixed pair is an illegal instruction on B200): three more
+    mantissa bits than bf16 at the same speed (embedding cosine 0.99991 -> 0.99999, trial-score error 1e-3 -> 2e-4 on the
+    exampleModel config), for models whose activations stay below 65504; stores saturate instead of overflowing.
   * ``precision='fp32'``: CUDA-core fp32 implicit GEMM + separate pool kernel (the 1e-4 parity path).
   * ``precision='auto'`` (default): bf16 when the channel counts allow it, else fp32.
 Under autograd the default is torch (cuDNN) convolutions in fp32, numerically the reference's own training path.
@@ -47,10 +46,9 @@ def getVGG4LOutputDimension(inputDimension, outputChannel=128):
 class _VGG(nn.Module):
     _divisors = ()   # kernel_size / d = channels of each block
 
-    def __init__(self, kernel_size, precision='auto', train_kernels=False, weight_dtype=torch.float16):
+    def __init__(self, kernel_size, precision='auto', train_kernels=False):
         super().__init__()
         self.train_kernels = train_kernels
-        self.weight_dtype = weight_dtype            # packed tensor-core weights on the inference path (training packs bf16)
         cin = 1
         self._names = []
         for blk, d in enumerate(self._divisors, start=1):
@@ -158,7 +156,7 @@ class _VGG(nn.Module):
         nblocks = len(self._names) // 2
         if prec in ('bf16', 'fp16'):
             act = torch.float16 if prec == 'fp16' else torch.bfloat16
-            wk = 'f16' if (prec == 'fp16' or self.weight_dtype == torch.float16) else 'bf16'
+            wk = 'f16' if prec == 'fp16' else 'bf16'       # both MMA operands must have the same 16-bit format
             # conv11 is bound by its NHWC 16-bit write (2.1 GB per 256 x 4 s batch at the 3.95 TB/s pure-write bandwidth)
             h = ops.conv11_direct(x, c11.weight, c11.bias, L, out_dtype=act)
             for blk in range(nblocks):

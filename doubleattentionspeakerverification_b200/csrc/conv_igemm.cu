@@ -691,6 +691,9 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     const int act = (flags & 32) ? 2 : 1;                        // 16-bit activation format: the output's follows the input's
     if (!ref && y_dtype != act) { set_error("conv3x3_igemm_bf16: NHWC output must have the input's 16-bit format (dtype %d)", act); return 1; }
     if (y_dtype != 0 && y_dtype != act) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
+    if (((flags & 16) != 0) != ((flags & 32) != 0)) {            // measured on B200: a mixed pair faults (illegal instruction)
+        set_error("conv3x3_igemm_bf16: tcgen05 kind::f16 needs both operands in the same format (set both or neither of DASV_CONV_W_F16, DASV_CONV_X_F16)"); return 1;
+    }
     if (!(flags & 1) && (flags & 48)) { set_error("conv3x3_igemm_bf16: the input-gradient pass is bf16 only"); return 1; }
     if (B <= 0 || T <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15)) {

@@ -36,13 +36,12 @@ class SpeakerClassifier(nn.Module):
     def _init_front_end(self, parameters):                            # scripts/model.py:21-29
         precision = getattr(parameters, 'precision', 'auto')
         tk = bool(getattr(parameters, 'train_kernels', False))       # training on this package's conv kernels (bf16)
-        wd = {'fp16': torch.float16, 'bf16': torch.bfloat16}[getattr(parameters, 'weight_dtype', 'fp16')]   # packed tensor-core weights
         if parameters.front_end == 'VGG3L':
             self.vector_size = getVGG3LOutputDimension(parameters.feature_size, outputChannel=parameters.kernel_size)
-            self.front_end = VGG3L(parameters.kernel_size, precision=precision, train_kernels=tk, weight_dtype=wd)
+            self.front_end = VGG3L(parameters.kernel_size, precision=precision, train_kernels=tk)
         if parameters.front_end == 'VGG4L':
             self.vector_size = getVGG4LOutputDimension(parameters.feature_size, outputChannel=parameters.kernel_size)
-            self.front_end = VGG4L(parameters.kernel_size, precision=precision, train_kernels=tk, weight_dtype=wd)
+            self.front_end = VGG4L(parameters.kernel_size, precision=precision, train_kernels=tk)
 
     def _init_pooling(self, parameters):                              # scripts/model.py:31-41
         self.pooling_method = parameters.pooling_method

@@ -173,6 +173,11 @@ TRAIN_STEP_SPECS = [dict(name='small', kernel_size=64, embedding_size=32, heads_
                     dict(name='k512', kernel_size=512, embedding_size=64, heads_number=16, num_spkrs=10, B=4, T=48, seed=5, stride=61)]
 
 
+def grad_sample_stride(numel, stride):
+    """Gradients of small tensors are stored whole in the fixtures, large ones as every `stride`-th element."""
+    return stride if numel > 4096 else 1
+
+
 def train_step_config(spec):
     return example_config(**{k: v for k, v in spec.items() if k not in ('name', 'stride', 'B', 'T', 'seed')})
 

@@ -132,9 +132,9 @@ int dasv_maxpool2x2(const void* x, int x_dtype, void* y, int y_dtype, int ref_la
  * (CNNs.py:73-86, one call per conv).  x [B,T,F,Cin] bf16, wp [Cout][9][Cin] bf16, bias f32.
  * Output: without POOL y [B,T,F,Cout] bf16; with POOL y [B,T2,F2,Cout] bf16, or with
  * REF_LAYOUT y [B,T2,Cout*F2] in y_dtype (T2 = ceil(T/2), F2 = F/2).
- * Operand formats: the MMA is tcgen05 kind::f16, whose two operands are bf16 or fp16 independently, so the packed
- * weights may be fp16 (DASV_CONV_W_F16) and/or the activations fp16 (DASV_CONV_X_F16: x and an NHWC y are fp16,
- * y_dtype = DASV_F16); accumulation is fp32 either way.
+ * Operand formats: the MMA is tcgen05 kind::f16, whose operands are both bf16 (default) or both fp16
+ * (DASV_CONV_W_F16 | DASV_CONV_X_F16: wp, x and an NHWC y are fp16, y_dtype = DASV_F16); a mixed pair is rejected
+ * (it is an illegal instruction on B200).  Accumulation is fp32 either way.
  * Requirements: Cin % 64 == 0, Cout % 8 == 0, F even and <= 256 (the reference's 80-bin input
  * gives F = 80, 40, 20, 10).  Needs the CUDA driver; the plan and both tensor maps are cached per
  * (x, wp, shape, flags), and the launch is a programmatic dependent of the stream's previous kernel. */

@@ -193,7 +193,7 @@ def gradient_cases():
             if p.grad is None:
                 continue                                            # b1, b3: unused by forward (model.py:61-71)
             g = p.grad.numpy().reshape(-1)
-            out['grad.' + n] = g[::stride].copy()
+            out['grad.' + n] = g[::synth.grad_sample_stride(g.size, stride)].copy()
             out['norm.' + n] = np.array(np.linalg.norm(g.astype(np.float64)))
         np.savez_compressed(os.path.join(OUT, 'grad_%s.npz' % name), cfg=np.array(repr(vars(cfg))),
                             spec=np.array([spec['B'], spec['T'], spec['seed'], stride]), **out)

@@ -180,5 +180,5 @@ def test_training_step_oracle(spec):
     assert set(names) == set(grads.keys())
     for n in names:
         got = grads[n].numpy().reshape(-1)
-        assert max_rel(got[::spec['stride']], g['grad.' + n]) < 1e-4, n
+        assert max_rel(got[::synth.grad_sample_stride(got.size, spec['stride'])], g['grad.' + n]) < 1e-4, n
         assert abs(np.linalg.norm(got.astype(np.float64)) - float(g['norm.' + n])) < 1e-4 * float(g['norm.' + n]), n
