@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 
 namespace dasv {
 
@@ -486,7 +487,7 @@ struct ConvPlan {
 // MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
 // ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
-static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo, bool pair) {
+static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms) {
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
     for (int BF = 2; BF <= F && BF <= 256; BF += 2) {
@@ -510,10 +511,16 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, bool pool, int halo, boo
                 }
                 const int Npad = (N + 15) / 16 * 16;
                 if (Npad > 256) continue;
-                const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB);
+                // tiles are dealt to the SMs (or SM pairs) in whole waves: with few tiles (small batches) a smaller patch
+                // that fills more SMs wins even though each of its MMAs is less efficient
+                const int n_mt = (Cout + kConvTileM - 1) / kConvTileM;
+                const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB) * (pair ? n_mt / 2 : n_mt);
+                const double units = pair ? sms / 2 : sms;
+                const double waves = ceil(tiles / units);
                 const double ingest = (128.0 + b_rows) * 32.0 / 52.0;                   // bytes per 16-deep step / ~52 B/clk effective
-                const double step = Npad / 2.0 > ingest ? Npad / 2.0 : ingest;
-                const double cost = tiles * (step * ksteps + 700.0);
+                double step = Npad / 2.0 > ingest ? Npad / 2.0 : ingest;
+                if (step < 40.0) step = 40.0;                                           // issue + operand-fetch floor of one MMA
+                const double cost = waves * (step * ksteps + 700.0);
                 if (cost < best.cost) best = ConvPlan{BF, BT, BB, N, Npad, cost};
             }
         }
@@ -588,8 +595,9 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     int pair = (flags & 8) != 0;                                 // DASV_CONV_PAIR
     if (k.env_pair >= 0) pair = k.env_pair;
     if (!reuse || cout_pad % (2 * kConvTileM) != 0) pair = 0;
-    ConvPlan pl = conv_plan(B, T, F, Cin, pool, reuse ? 2 : 0, pair != 0);
-    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Cin, pool, 2, false); }
+    const int sms = sm_count();
+    ConvPlan pl = conv_plan(B, T, F, Cin, Cout, pool, reuse ? 2 : 0, pair != 0, sms);
+    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Cin, Cout, pool, 2, false, sms); }
     if (k.env_plan[0]) {                                         // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
         int bf = 0, bt = 0, bb = 0;
         if (sscanf(k.env_plan, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
@@ -670,7 +678,6 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     const long long n_tiles = static_cast<long long>(pair ? p.n_mt / 2 : p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
     if (n_tiles > 0x7fffffffLL) { set_error("conv3x3_igemm_bf16: too many tiles"); return 1; }
     en.smem = static_cast<size_t>(p.stages) * p.stage_bytes + static_cast<size_t>(p.sa) * kConvABytes + kFixed;
-    const int sms = sm_count();
     en.grid = pair ? 2 * static_cast<int>(n_tiles < sms / 2 ? n_tiles : sms / 2) : static_cast<int>(n_tiles < sms ? n_tiles : sms);
     en.pair = pair;
     en.p = p;

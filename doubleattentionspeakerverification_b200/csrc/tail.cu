@@ -1,7 +1,7 @@
 // Embedding tail and trial scoring.
 //   * dasv_fc_tail_f32: b2(relu(fc2(relu(fc1(pooled))))) in eval mode (scripts/model.py:56-57), one
 //     fused kernel: 0.45 MFLOP per utterance, so the whole cost is weight traffic and launch latency.
-//     A CTA owns UPB utterances so each weight element read from L2 is used UPB times.
+//     An 8-CTA cluster owns up to 8 utterances; each CTA computes 1/8 of the columns of both layers.
 //   * dasv_cosine_pairs / dasv_cosine_matrix: F.cosine_similarity(dim=-1, eps=1e-8) (scripts/utils.py:18-21)
 //     batched over a trial list or a full enrol x test cross-product.
 //   * dasv_attention_fwd: the single-query Attention pooling (scripts/poolings.py:22-27).
@@ -10,72 +10,103 @@
 
 namespace dasv {
 
-constexpr int kTailUPB = 4;
+// A thread-block cluster of kTailCL CTAs owns UB utterances; CTA r computes output columns [r*CW, (r+1)*CW) of both
+// layers, so every weight element is read once per cluster and the reads of one layer are spread over kTailCL SMs
+// (the first version gave a single CTA all E columns: 78 us of dependent L2 round trips even for ONE utterance).
+// Between the layers the relu(fc1) slices are exchanged through distributed shared memory (each CTA stores its slice
+// into every CTA of the cluster) and one cluster barrier.
+constexpr int kTailCL = 8;            // CTAs per cluster (portable maximum)
+constexpr int kTailKS = 4;            // k slices per column (threads = 64 column lanes x kTailKS)
+constexpr int kTailThreads = 64 * kTailKS;
 
-__global__ void __launch_bounds__(512) fc_tail_kernel(const float* __restrict__ pooled, const float* __restrict__ w1t,
-                                                     const float* __restrict__ b1, const float* __restrict__ w2t,
-                                                     const float* __restrict__ b2, const float* __restrict__ bn_scale,
-                                                     const float* __restrict__ bn_shift, float* __restrict__ emb,
-                                                     int B, int Din, int E) {
+template <int UB>
+DASV_DEVICE void tail_layer(const float* __restrict__ in_sm, int K, const float* __restrict__ wt, int E, int c0, int cw,
+                            float* __restrict__ red_sm, float (&out)[UB]) {
+    // out[u] = sum_k in_sm[u][k] * wt[k][c0 + el] for this thread's column el, reduced over the kTailKS k slices
+    const int el = threadIdx.x & 63, ks = threadIdx.x >> 6;
+    const int kper = (K + kTailKS - 1) / kTailKS;
+    const int k0 = ks * kper, k1 = min(K, k0 + kper);
+    float acc[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) acc[u] = 0.f;
+    if (el < cw) {
+        const float* wcol = wt + c0 + el;
+        int k = k0;
+        for (; k + 10 <= k1; k += 10) {          // 10 independent weight loads in flight per thread
+            float w[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) w[j] = __ldg(wcol + static_cast<size_t>(k + j) * E);
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+#pragma unroll
+                for (int u = 0; u < UB; ++u) acc[u] = fmaf(in_sm[u * K + k + j], w[j], acc[u]);
+        }
+        for (; k < k1; ++k) {
+            const float w = __ldg(wcol + static_cast<size_t>(k) * E);
+#pragma unroll
+            for (int u = 0; u < UB; ++u) acc[u] = fmaf(in_sm[u * K + k], w, acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) red_sm[(ks * UB + u) * 64 + el] = acc[u];
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < kTailKS; ++q) v += red_sm[(q * UB + u) * 64 + el];     // fixed order: deterministic
+            out[u] = v;
+        }
+    }
+}
+
+template <int UB>
+__global__ void __launch_bounds__(kTailThreads) fc_tail_kernel(const float* __restrict__ pooled, const float* __restrict__ w1t,
+                                                             const float* __restrict__ b1, const float* __restrict__ w2t,
+                                                             const float* __restrict__ b2, const float* __restrict__ bn_scale,
+                                                             const float* __restrict__ bn_shift, float* __restrict__ emb,
+                                                             int B, int Din, int E) {
     extern __shared__ float sm[];
     griddep_launch();
     griddep_wait();                          // programmatic dependent launch: `pooled` comes from the previous kernel
-    float* in_sm = sm;                       // [UPB][Din]
-    float* h_sm = sm + kTailUPB * Din;       // [UPB][E]
-    const int b0 = blockIdx.x * kTailUPB;
-    const int nb = min(kTailUPB, B - b0);
-    for (int i = threadIdx.x; i < kTailUPB * Din; i += blockDim.x) {
+    float* in_sm = sm;                       // [UB][Din]
+    float* h_sm = sm + UB * Din;             // [UB][E]   relu(fc1), assembled from all CTAs of the cluster
+    float* red_sm = h_sm + UB * E;           // [kTailKS][UB][64]
+    const uint32_t rank = cluster_ctarank();
+    const int b0 = static_cast<int>(blockIdx.x / kTailCL) * UB;
+    const int nb = min(UB, B - b0);
+    const int CW = (E + kTailCL - 1) / kTailCL;          // columns per CTA (<= 64, checked by the host)
+    const int c0 = static_cast<int>(rank) * CW, cw = max(0, min(CW, E - c0));
+    for (int i = threadIdx.x; i < UB * Din; i += blockDim.x) {
         const int u = i / Din;
         in_sm[i] = u < nb ? pooled[static_cast<size_t>(b0) * Din + i] : 0.f;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        float acc[kTailUPB];
+    const int el = threadIdx.x & 63, ks = threadIdx.x >> 6;
+    float v[UB];
+    tail_layer<UB>(in_sm, Din, w1t, E, c0, cw, red_sm, v);
+    if (ks == 0 && el < cw) {
+        const float bb = b1[c0 + el];
+        const uint32_t mine = smem_u32(h_sm + c0 + el);
 #pragma unroll
-        for (int u = 0; u < kTailUPB; ++u) acc[u] = 0.f;
-        int d = 0;
-        for (; d + 8 <= Din; d += 8) {          // 8 independent weight loads in flight per thread
-            float w[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = w1t[static_cast<size_t>(d + k) * E + e];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(in_sm[u * Din + d + k], w[k], acc[u]);
+        for (int u = 0; u < UB; ++u) {
+            const float h = fmaxf(v[u] + bb, 0.f);                                   // relu(fc1), model.py:56
+            for (uint32_t r = 0; r < kTailCL; ++r) {                                 // into every CTA's copy of h
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine + static_cast<uint32_t>(u * E) * 4u), "r"(r));
+                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(h) : "memory");
+            }
         }
-        for (; d < Din; ++d) {
-            const float w = w1t[static_cast<size_t>(d) * E + e];
-#pragma unroll
-            for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(in_sm[u * Din + d], w, acc[u]);
-        }
-        const float bb = b1[e];
-#pragma unroll
-        for (int u = 0; u < kTailUPB; ++u) h_sm[u * E + e] = fmaxf(acc[u] + bb, 0.f);     // relu(fc1), model.py:56
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        float acc[kTailUPB];
-#pragma unroll
-        for (int u = 0; u < kTailUPB; ++u) acc[u] = 0.f;
-        int d = 0;
-        for (; d + 8 <= E; d += 8) {
-            float w[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = w2t[static_cast<size_t>(d + k) * E + e];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(h_sm[u * E + d + k], w[k], acc[u]);
-        }
-        for (; d < E; ++d) {
-            const float w = w2t[static_cast<size_t>(d) * E + e];
-#pragma unroll
-            for (int u = 0; u < kTailUPB; ++u) acc[u] = fmaf(h_sm[u * E + d], w, acc[u]);
-        }
+    cluster_sync_all();                      // release/acquire: every slice of h is visible in every CTA
+    tail_layer<UB>(h_sm, E, w2t, E, c0, cw, red_sm, v);
+    if (ks == 0 && el < cw) {
+        const int e = c0 + el;
         const float bb = b2[e], sc = bn_scale[e], sh = bn_shift[e];
 #pragma unroll
-        for (int u = 0; u < kTailUPB; ++u)
-            if (u < nb) emb[static_cast<size_t>(b0 + u) * E + e] = fmaf(fmaxf(acc[u] + bb, 0.f), sc, sh);   // b2(relu(fc2)), model.py:57
+        for (int u = 0; u < UB; ++u)
+            if (u < nb) emb[static_cast<size_t>(b0 + u) * E + e] = fmaf(fmaxf(v[u] + bb, 0.f), sc, sh);   // b2(relu(fc2)), model.py:57
     }
 }
 
@@ -260,12 +291,29 @@ extern "C" int dasv_fc_tail_f32(const float* pooled, const float* w1t, const flo
                                 int B, int Din, int E, void* stream) {
     if (!pooled || !w1t || !b1 || !w2t || !b2 || !bn_scale || !bn_shift || !emb) { set_error("fc_tail: null argument"); return 1; }
     if (B <= 0) return 0;
-    const size_t smem = static_cast<size_t>(kTailUPB) * (Din + E) * sizeof(float);
+    if ((E + kTailCL - 1) / kTailCL > 64) { set_error("fc_tail: E=%d > %d", E, 64 * kTailCL); return 1; }
+    // utterances per cluster: as many as shared memory holds (the fc1 input rows are the large part for the MHA pooling)
+    int UB = 8;
+    auto smem_of = [&](int ub) { return (static_cast<size_t>(ub) * (Din + E) + static_cast<size_t>(kTailKS) * ub * 64) * sizeof(float); };
+    while (UB > 1 && (smem_of(UB) > 160 * 1024 || UB / 2 >= B)) UB /= 2;
+    if (UB == 2) UB = 1;
+    const size_t smem = smem_of(UB);
     if (smem > 200 * 1024) { set_error("fc_tail: Din=%d E=%d need %zu B of shared memory", Din, E, smem); return 1; }
-    cudaError_t e = cudaFuncSetAttribute(fc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    auto kern = UB == 8 ? fc_tail_kernel<8> : (UB == 4 ? fc_tail_kernel<4> : fc_tail_kernel<1>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) { set_error("fc_tail: smem attribute: %s", cudaGetErrorString(e)); return 1; }
-    e = launch_pdl(fc_tail_kernel, dim3((B + kTailUPB - 1) / kTailUPB), dim3(512), smem, static_cast<cudaStream_t>(stream),
-                   pooled, w1t, b1, w2t, b2, bn_scale, bn_shift, emb, B, Din, E);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>((B + UB - 1) / UB) * kTailCL);
+    cfg.blockDim = dim3(kTailThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kTailCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    e = cudaLaunchKernelEx(&cfg, kern, pooled, w1t, b1, w2t, b2, bn_scale, bn_shift, emb, B, Din, E);
     if (e != cudaSuccess) { set_error("fc_tail: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("fc_tail");
 }
