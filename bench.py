@@ -41,6 +41,26 @@ BATCH, FRAMES, BINS = 256, 400, 80
 METRIC, UNIT = 'embeddings/sec (4 s utts)', 'embeddings/s'
 
 
+def workload_config(world, batch=BATCH):
+    """The `config` object of the JSON line: the same keys and values from both arms (--impl b200 / reference)."""
+    return {'workload': 'full embedding extraction VGG4L(K=1024)+DoubleMHA(H=32)+FC(E=400), 4 s (400x80) log-mel '
+                        'utterances, random-init (BASELINE configs[2])', 'batch_per_gpu': batch,
+            'parallelism': 'dp%d' % world,
+            'l2': 'two rotating input batches; per-step intermediates (>3 GB) exceed the 126 MB L2'}
+
+
+def profiled_traffic():
+    """DRAM bytes per conv launch from the committed ncu capture of this round (profiles/r2_conv_ncu.json, written by
+    scripts/ncu_summary.py from `ncu --set full`): dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    seven launches of a step.  None when the file is missing, so a stale literal can never be reported."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r2_conv_ncu.json')) as f:
+            d = json.load(f)
+        return float(d['dram_bytes_per_launch']), d.get('source', 'profiles/r2_conv_ncu.json')
+    except Exception:
+        return None, 'no ncu capture committed for this round'
+
+
 def peaks():
     p = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
     try:
@@ -61,6 +81,22 @@ def conv_flops(batch, frames, kernel_size=1024):
         out[name] = 2.0 * batch * T * F * cout * 9 * cin
         if i % 2 == 1:
             T, F = (T + 1) // 2, (F + 1) // 2
+    return out
+
+
+def conv_io_bytes(batch, frames, kernel_size=1024):
+    """Compulsory HBM bytes of every tensor-core conv launch: 16-bit NHWC input + output (fp32 for the last layer) + weights."""
+    from doubleattentionspeakerverification_b200 import synth
+    out, T, F = {}, frames, BINS
+    chans = synth.vgg_channels('VGG4L', kernel_size)
+    names = synth.conv_names('VGG4L')
+    for i, ((cin, cout), name) in enumerate(zip(chans, names)):
+        pooled = i % 2 == 1
+        To, Fo = ((T + 1) // 2, (F + 1) // 2) if pooled else (T, F)
+        if i > 0:
+            out[name] = batch * T * F * cin * 2.0 + batch * To * Fo * cout * (4.0 if i == len(names) - 1 else 2.0) + 9.0 * cin * cout * 2
+        if pooled:
+            T, F = To, Fo
     return out
 
 
@@ -149,8 +185,7 @@ def run_reference(args, rank):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * t_tot / len(per_step), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'full embedding extraction VGG4L(K=1024)+DoubleMHA(H=32)+FC(E=400), 4 s (400x80) log-mel '
-                                   'utterances, random-init (BASELINE configs[2])', 'batch_per_gpu': BATCH},
+            'config': workload_config(args.gpus),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(json.dumps(line))
@@ -162,11 +197,12 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-dmha', action='store_true')
-    ap.add_argument('--no-extras', action='store_true', help='skip the secondary measurements (training step, feature extraction)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary measurements (training step, feature extraction, other precisions)')
+    ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs[3] (2-20 s ragged) and configs[4] (1 M trials)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', '0'))
@@ -254,7 +290,7 @@ def main():
 
     # ---- roofline of the dominant kernel (conv3x3_igemm: tensor-bound), timed per launch inside real steps
     roof = None
-    if args.precision == 'bf16':
+    if args.precision in ('bf16', 'fp16'):
         fl = conv_flops(Bn, FRAMES)
         names = [n for n in synth.conv_names('VGG4L')][1:]
         rec = []
@@ -285,8 +321,81 @@ def main():
         roof = {'bound': 'tensor', 'kernel': 'conv3x3_igemm_kernel (7 launches per step, conv12..conv42)',
                 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / pk['bf16_tflops_sustained'], 'peak_source': pk['source'] + ' sustained cuBLAS bf16',
-                'traffic': 1.081e9, 'traffic_source': 'ncu --set full, dram__bytes_read+write averaged over the 7 launches of a step (profiles/r1_final_conv_summary.txt): 7.57 GB per step = compulsory input+output+weights', 'avg_launch_ms': conv_ms / len(names), 'share_of_step': conv_ms / (ms / args.steps),
+                'traffic': profiled_traffic()[0], 'traffic_source': profiled_traffic()[1],
+                'algorithmic_bytes_per_launch': sum(conv_io_bytes(Bn, FRAMES).values()) / len(names),
+                'avg_launch_ms': conv_ms / len(names), 'share_of_step': conv_ms / (ms / args.steps),
                 'per_layer_tflops': {n: fl[n] / (per_layer[n] * 1e-3) / 1e12 for n in names}}
+
+    # ---- BASELINE configs[3] (2-20 s utterances, packed + masked, sharded) and configs[4] (1 M trials) at this N
+    cfg3 = cfg4 = None
+    if not args.no_configs:
+        def embed_len(xb, L):
+            with torch.no_grad():
+                return net.getEmbedding(xb, lengths=L)
+
+        def timed_call(fn, reps=2):
+            fn()                                                  # warm-up
+            best = None
+            for _ in range(reps):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn()
+                e1.record()
+                torch.cuda.synchronize()
+                t = max_over_ranks(e0.elapsed_time(e1))
+                best = t if best is None else min(best, t)
+            return best * 1e-3, out
+
+        per_gpu = 256
+        N3 = per_gpu * world
+        rs3 = np.random.RandomState(0)
+        frames3 = (100 * rs3.uniform(2.0, 20.0, size=N3)).astype(np.int64)
+        base = synth.make_logmel(1, 2000, seed=1)[0]
+        gp = extract.global_plan(frames3, world)
+        mine = set(int(i) for b in gp[rank] for i in b)
+        # every rank holds the frames of ITS utterances only (the others are never touched: the plan decides the owner)
+        packed3 = extract.PackedUtterances.sparse(frames3, {i: np.roll(base, i * 7, axis=0)[:int(frames3[i])] for i in sorted(mine)})
+        dt3, _ = timed_call(lambda: extract.extract_sharded(embed_len, packed3, dev, embedding_size=cfg.embedding_size))
+        pad = sum(len(b) * int(frames3[b].max()) for bs in gp for b in bs)
+        loads = [sum(extract._batch_cost(frames3, b) for b in bs) for bs in gp]
+        useful = 12.99e9 * frames3.sum() / 100.0                  # conv FLOPs of the VALID frames (12.99 GFLOP per second of audio)
+        cfg3 = {'workload': 'BASELINE configs[3]: %d utterances/GPU, durations U[2,20] s, one global batch plan (extract.global_plan), '
+                            'padded + length-masked batches, one all-gather' % per_gpu,
+                'utterances': int(N3), 'seconds': dt3, 'embeddings_per_s': N3 / dt3,
+                'useful_conv_tflops_per_gpu': useful / dt3 / 1e12 / world, 'frac_of_sustained_peak': useful / dt3 / 1e12 / world / pk['bf16_tflops_sustained'],
+                'padding_waste': float(pad / frames3.sum() - 1.0), 'batches': int(sum(len(bs) for bs in gp)),
+                'plan_imbalance': float(max(loads) / (sum(loads) / world)),
+                'timing': 'CUDA events, max over ranks, best of 2: pinned host frames -> H2D -> device gather -> extraction -> all-gather'}
+        del packed3
+
+        M4 = 2048
+        lo4, hi4 = extract.rank_slice(M4, rank, world)
+        x4 = torch.from_numpy(np.stack([np.roll(base, int(i) * 3, axis=0)[:FRAMES] for i in range(lo4, hi4)])).pin_memory()
+        per4 = -(-M4 // world)
+        gath4 = torch.empty((world * per4, cfg.embedding_size), device=dev)
+
+        def trials():
+            embs = []
+            for j in range(0, x4.shape[0], Bn):                  # this rank's share of the 2 048 utterances, 256 at a time
+                with torch.no_grad():
+                    embs.append(net.getEmbedding(x4[j:j + Bn].to(dev, non_blocking=True)))
+            local = torch.cat(embs)
+            if world > 1:
+                send = torch.zeros((per4, cfg.embedding_size), device=dev)
+                send[:local.shape[0]] = local
+                dist.all_gather_into_tensor(gath4, send)          # NCCL over NVLink: the path's only collective
+                emb_all = torch.cat([gath4[r * per4:r * per4 + (extract.rank_slice(M4, r, world)[1] - extract.rank_slice(M4, r, world)[0])] for r in range(world)])
+            else:
+                emb_all = local
+            return extract.score_cross_sharded(emb_all, np.arange(1024), np.arange(1024, 2048), gather=True)
+
+        dt4, scores4 = timed_call(trials)
+        cfg4 = {'workload': 'BASELINE configs[4]: 1024 x 1024 = 1 048 576 trials: 2 048 4 s utterances extracted across the ranks from pinned host '
+                            'memory, all-gather of the embeddings, enrol rows of the cosine GEMM split over the ranks, all-gather of the score slices',
+                'trials': 1 << 20, 'seconds': dt4, 'trials_per_s': (1 << 20) / dt4, 'embeddings_per_s': M4 / dt4,
+                'score_checksum': float(scores4.double().sum().item()), 'timing': 'CUDA events, max over ranks, best of 2'}
+        del x4
 
     # ---- DoubleMHA pooling microbench (BASELINE configs[1]): B=512, T=200, D=1024, H=16, length-masked
     dmha = None
@@ -391,6 +500,34 @@ def main():
         except Exception as e:                                   # secondary numbers must never take the headline down
             extras['error'] = repr(e)[:300]
 
+    # ---- the other precisions of the same step (fp16 operands; fp32 parity path) as secondary numbers
+    if extras is not None and 'error' not in extras:
+        try:
+            for prec, bsz, reps in (('fp16', Bn, 5), ('fp32', 32, 2)):
+                if prec == args.precision:
+                    continue
+                c2 = synth.example_config()
+                c2.precision = prec
+                n2 = synth.load_state_dict(model.SpeakerClassifier(c2, dev), synth.make_state_dict(c2, 1234)).to(dev).eval()
+                xb = xs[0][:bsz].contiguous()
+                with torch.no_grad():
+                    for _ in range(3):
+                        n2.getEmbedding(xb)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(reps):
+                        n2.getEmbedding(xb)
+                    e1.record()
+                    torch.cuda.synchronize()
+                t2 = e0.elapsed_time(e1) / reps
+                extras['precision_' + prec] = {'batch': bsz, 'ms_per_step': t2, 'embeddings_per_s': bsz / t2 * 1e3,
+                                               'what': 'the same getEmbedding step with precision=%r' % prec}
+                del n2
+                torch.cuda.empty_cache()
+        except Exception as e:
+            extras['precision_error'] = repr(e)[:300]
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, n, el, threads = cpu_reference_rate(15.0)
@@ -402,13 +539,11 @@ def main():
         d2h = emb_host.numel() * 4
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': {'workload': 'full embedding extraction VGG4L(K=1024)+DoubleMHA(H=32)+FC(E=400), 4 s (400x80) log-mel '
-                                       'utterances, random-init (BASELINE configs[2])', 'batch_per_gpu': Bn,
-                           'parallelism': 'dp%d' % world, 'l2': 'two rotating input batches; per-step intermediates (>3 GB) exceed the 126 MB L2'},
+                'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
+                'config': workload_config(world, Bn),
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': ms_e2e / args.steps},
-                'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'dmha_microbench': dmha, 'extras': extras, 'cpu_baseline': cpu}
+                'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'dmha_microbench': dmha, 'configs3': cfg3, 'configs4': cfg4, 'extras': extras, 'cpu_baseline': cpu}
         emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -44,6 +44,75 @@ def batch_plan(lengths, max_frames, max_batch=None, multiple=1):
     return batches
 
 
+# Cost model of one batch for the global plan, in frames: its valid frames, a quarter of its padding (masked tiles are
+# skipped by the kernels, partially masked ones are not) and a fixed part per batch (ten launches + host work).
+BATCH_OVERHEAD_FRAMES = 1500
+
+
+def _batch_cost(lengths, b):
+    L = np.asarray(lengths)[b]
+    valid = float(L.sum())
+    return valid + 0.25 * (float(L.max()) * len(b) - valid) + BATCH_OVERHEAD_FRAMES
+
+
+def global_plan(lengths, world, max_frames=256 * 400, min_ratio=0.5, min_frames=32 * 400, balance=1.03):
+    """Batches over the WHOLE utterance list first, ranks second (BASELINE configs[3]).
+
+    1. Walk the list by decreasing length and close a batch when its padded size would pass ``max_frames``, or when the
+       next utterance is shorter than ``min_ratio`` x the batch's longest AND the batch already holds ``min_frames``
+       padded frames -- so short utterances, of which a length bucket holds few, still form batches large enough to
+       fill the SMs (a batch far below ~64 x 400 frames runs in partial waves).
+    2. Deal whole batches to the ranks, longest estimated time first, each to the least loaded rank (LPT).
+    3. While the busiest rank is more than ``balance`` x the mean, halve its largest batch (alternate utterances, so
+       both halves keep the length mix) and deal again.
+
+    Returns ``[[index arrays] per rank]``; deterministic, so every rank computes the same plan."""
+    lengths = np.asarray(lengths)
+    order = np.argsort(-lengths, kind='stable')
+    batches, cur = [], []
+    for i in order:
+        if cur:
+            Tmax = int(lengths[cur[0]])
+            if (len(cur) + 1) * Tmax > max_frames or (lengths[i] < min_ratio * Tmax and len(cur) * Tmax >= min_frames):
+                batches.append(np.array(cur))
+                cur = []
+        cur.append(int(i))
+    if cur:
+        batches.append(np.array(cur))
+    # a small leftover at the short end joins its neighbour when the sum stays near the budget
+    if len(batches) >= 2:
+        a, b = batches[-2], batches[-1]
+        if len(b) * int(lengths[b[0]]) < min_frames and (len(a) + len(b)) * int(lengths[a[0]]) <= 1.25 * max_frames:
+            batches[-2:] = [np.concatenate([a, b])]
+
+    def deal(bs):
+        cost = [_batch_cost(lengths, b) for b in bs]
+        load = [0.0] * world
+        owner = [0] * len(bs)
+        for j in sorted(range(len(bs)), key=lambda j: (-cost[j], j)):
+            r = int(np.argmin(load))
+            owner[j] = r
+            load[r] += cost[j]
+        return owner, load, cost
+
+    owner, load, cost = deal(batches)
+    for _ in range(8 * world):
+        if world == 1 or max(load) <= balance * (sum(load) / world):
+            break
+        r = int(np.argmax(load))
+        mine = [j for j in range(len(batches)) if owner[j] == r and len(batches[j]) >= 2]
+        if not mine:
+            break
+        j = max(mine, key=lambda j: cost[j])
+        b = batches[j]
+        batches[j:j + 1] = [b[0::2], b[1::2]]
+        owner, load, cost = deal(batches)
+    plan = [[] for _ in range(world)]
+    for j in sorted(range(len(batches)), key=lambda j: (-cost[j], j)):
+        plan[owner[j]].append(batches[j])
+    return plan
+
+
 class PackedUtterances:
     """Every utterance's frames in ONE (pinned) host buffer ``[sum T_i, F]`` plus offsets -- the form a feature loader
     should hand over: no per-batch host padding, the device builds padded batches itself with one gather."""
@@ -58,6 +127,28 @@ class PackedUtterances:
         view = self.data.numpy()
         for f, o in zip(feats, self.offsets[:-1]):
             view[o:o + f.shape[0]] = f
+
+    @classmethod
+    def sparse(cls, lengths, owned, pin=True):
+        """For a sharded job: every utterance's LENGTH (the plan needs all of them) but frames only for the utterances
+        this rank will embed (``owned``: {index: [T_i, F] array}); the others take no memory and must not be asked for."""
+        lengths = np.asarray(lengths, np.int64)
+        F = next(iter(owned.values())).shape[1] if owned else 1
+        self = cls.__new__(cls)
+        self.lengths = lengths
+        have = np.zeros(len(lengths), np.int64)
+        for i, f in owned.items():
+            if f.shape[0] != lengths[i]:
+                raise ValueError('utterance %d has %d frames, lengths says %d' % (i, f.shape[0], lengths[i]))
+            have[i] = f.shape[0]
+        self.offsets = np.concatenate([[0], np.cumsum(have)])
+        self.data = torch.empty((int(self.offsets[-1]), F), dtype=torch.float32)
+        if pin and torch.cuda.is_available() and self.data.numel():
+            self.data = self.data.pin_memory()
+        view = self.data.numpy()
+        for i, f in owned.items():
+            view[self.offsets[i]:self.offsets[i] + f.shape[0]] = f
+        return self
 
     def __len__(self):
         return len(self.lengths)
@@ -80,10 +171,11 @@ def bucket_plan(lengths, max_frames, min_ratio=0.8, max_batch=None):
     return batches
 
 
-def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400, min_ratio=0.8, max_batch=None):
+def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400, min_ratio=0.8, max_batch=None, batches=None):
     """Embed ``packed`` utterances ``indices``: their frames go to the device once (one async copy per utterance from
     the pinned buffer, no host padding), then every batch is ONE device gather into ``[B, Tmax, F]`` with frame indices
     clamped to the utterance (the kernels ignore frames >= length, so the padding content does not matter).
+    ``batches`` (index arrays INTO ``indices``) overrides the local bucket plan.
     Returns ``[len(indices), E]`` in the order of ``indices``."""
     indices = np.asarray(indices)
     if len(indices) == 0:
@@ -98,8 +190,8 @@ def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400
     starts_d = torch.from_numpy(starts[:-1]).to(dev)
     L_d = torch.from_numpy(L).to(dev)
     out = None
-    for b in bucket_plan(L, max_frames, min_ratio, max_batch):
-        bt = torch.from_numpy(b).to(dev)
+    for b in (bucket_plan(L, max_frames, min_ratio, max_batch) if batches is None else batches):
+        bt = torch.from_numpy(np.asarray(b)).to(dev)
         Tmax = int(L[b].max())
         t = torch.arange(Tmax, device=dev)
         rows = starts_d[bt, None] + torch.minimum(t[None, :], L_d[bt, None] - 1)          # [B, Tmax] source frame of every slot
@@ -164,7 +256,7 @@ def pad_batch(feats, idx, multiple=1):
     return x, L
 
 
-def extract_local(embed_fn, feats, indices, device, max_frames=256 * 400, max_batch=None):
+def extract_local(embed_fn, feats, indices, device, max_frames=256 * 400, max_batch=None, batches=None):
     """Embed ``feats[i] for i in indices`` in padded, length-masked batches.  ``embed_fn(x [B,T,F], lengths [B])
     -> [B,E]`` (e.g. ``net.getEmbedding``).  Returns ``[len(indices), E]`` in the order of ``indices``."""
     indices = np.asarray(indices)
@@ -172,7 +264,8 @@ def extract_local(embed_fn, feats, indices, device, max_frames=256 * 400, max_ba
         return None
     lengths = np.array([feats[i].shape[0] for i in indices])
     out = None
-    for b in batch_plan(lengths, max_frames, max_batch):
+    for b in (batch_plan(lengths, max_frames, max_batch) if batches is None else batches):
+        b = np.asarray(b)
         x, L = pad_batch(feats, indices[b])
         xt = torch.from_numpy(x)
         if torch.device(device).type == 'cuda':
@@ -184,10 +277,13 @@ def extract_local(embed_fn, feats, indices, device, max_frames=256 * 400, max_ba
     return out
 
 
-def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, max_batch=None, embedding_size=None, min_ratio=0.8):
-    """Every rank embeds its shard, then one all-gather; returns ``[N, E]`` embeddings of ALL utterances, in
+def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, max_batch=None, embedding_size=None, min_ratio=0.5,
+                    min_frames=32 * 400, planner='global'):
+    """Every rank embeds its share, then one all-gather; returns ``[N, E]`` embeddings of ALL utterances, in
     the original order, on every rank.  Without an initialised process group it is the single-GPU path.
-    ``feats``: list of ``[T_i, F]`` arrays (host-padded batches) or a ``PackedUtterances`` (device-built batches)."""
+    ``feats``: list of ``[T_i, F]`` arrays (host-padded batches) or a ``PackedUtterances`` (device-built batches).
+    ``planner='global'`` (default): batches are formed over the whole list and whole batches dealt to the ranks by
+    estimated time (``global_plan``); ``'snake'``: round 1's plan (utterances dealt by count, batches per rank)."""
     import torch.distributed as dist
     N = len(feats)
     is_packed = isinstance(feats, PackedUtterances)
@@ -195,11 +291,21 @@ def extract_sharded(embed_fn, feats, device, group=None, max_frames=256 * 400, m
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if distributed else 1
     rank = dist.get_rank(group) if distributed else 0
-    plan = shard_plan(lengths, world)
+    if planner == 'snake':
+        plan = shard_plan(lengths, world)
+        if is_packed:
+            local = extract_local_packed(embed_fn, feats, plan[rank], device, max_frames, min_ratio=min_ratio, max_batch=max_batch)
+        else:
+            local = extract_local(embed_fn, feats, plan[rank], device, max_frames, max_batch)
+        return _gather_shards(local, plan, N, device, group, embedding_size)
+    gp = global_plan(lengths, world, max_frames, min_ratio, min_frames)
+    plan = [np.concatenate(bs) if bs else np.zeros((0,), np.int64) for bs in gp]
+    offs = np.concatenate([[0], np.cumsum([len(b) for b in gp[rank]])]).astype(np.int64)
+    local_batches = [np.arange(offs[j], offs[j + 1]) for j in range(len(gp[rank]))]      # positions inside plan[rank]
     if is_packed:
-        local = extract_local_packed(embed_fn, feats, plan[rank], device, max_frames, min_ratio=min_ratio, max_batch=max_batch)
+        local = extract_local_packed(embed_fn, feats, plan[rank], device, batches=local_batches)
     else:
-        local = extract_local(embed_fn, feats, plan[rank], device, max_frames, max_batch)
+        local = extract_local(embed_fn, feats, plan[rank], device, batches=local_batches)
     return _gather_shards(local, plan, N, device, group, embedding_size)
 
 
@@ -211,7 +317,7 @@ def _gather_shards(local, plan, N, device, group, embedding_size):
         out = torch.empty_like(local)
         out[torch.from_numpy(plan[0]).to(local.device)] = local
         return out
-    per = max(len(p) for p in plan)                       # shards differ by at most one utterance: pad to equal
+    per = max(len(p) for p in plan)                       # shards are padded to the largest (they differ when batches, not utterances, are dealt)
     E = local.shape[1] if local is not None else embedding_size
     if E is None:
         raise ValueError('a rank with an empty shard needs embedding_size')
@@ -277,12 +383,60 @@ def score_cross(emb, enrol_idx, test_idx):
     return utils.score_matrix(e, t)
 
 
-def validate(embed_fn, utterances, client_trials, impostor_trials, device, **kw):
+def _rank_world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def rank_slice(n, rank, world):
+    """Rows [lo, hi) of an n-row job that rank ``rank`` of ``world`` owns (contiguous, sizes differ by at most one)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def score_cross_sharded(emb, enrol_idx, test_idx, group=None, gather=True):
+    """Cross-product scoring with the ENROL rows split over the ranks (every rank scores
+    ``[Ne/R, E] x [E, Nt]``).  ``gather=False`` returns this rank's ``(row offset, [rows, Nt])`` slice; ``gather=True``
+    all-gathers the slices into the full ``[Ne, Nt]`` matrix on every rank."""
+    import torch.distributed as dist
+    rank, world = _rank_world(group)
+    enrol_idx, test_idx = np.asarray(enrol_idx), np.asarray(test_idx)
+    lo, hi = rank_slice(len(enrol_idx), rank, world)
+    local = score_cross(emb, enrol_idx[lo:hi], test_idx) if hi > lo else emb.new_zeros((0, len(test_idx)))
+    if not gather or world == 1:
+        return (lo, local) if not gather else local
+    per = -(-len(enrol_idx) // world)
+    send = emb.new_zeros((per, len(test_idx)))
+    send[:hi - lo] = local
+    recv = emb.new_empty((world * per, len(test_idx)))
+    dist.all_gather_into_tensor(recv, send, group=group)
+    rows = [recv[r * per:r * per + (rank_slice(len(enrol_idx), r, world)[1] - rank_slice(len(enrol_idx), r, world)[0])] for r in range(world)]
+    return torch.cat(rows, 0)
+
+
+def validate(embed_fn, utterances, client_trials, impostor_trials, device, group=None, score_fn=None, count_fn=None, **kw):
     """The reference's validation pass (scripts/train.py:158-184: __extract_scores on the client and impostor
     trial lists, then __calculate_EER) without its per-trial forwards: every utterance is embedded once (sharded over
-    the ranks when a process group is up), both trial lists are scored by one kernel each, and the 200-threshold
-    FAR/FRR sweep runs on the device.  ``*_trials``: ``[M,2]`` utterance-index pairs.  Returns (EER, CL, IM)."""
-    emb = extract_sharded(embed_fn, utterances, device, **kw)
-    CL = score_trial_list(emb, client_trials)
-    IM = score_trial_list(emb, impostor_trials)
-    return utils.calculate_EER(CL, IM), CL, IM
+    the ranks when a process group is up), every rank scores ITS SLICE of both trial lists with one kernel each and
+    counts its scores against the 200 thresholds on the device; the [2, 200] count vectors are summed over the ranks
+    (one small all-reduce) and the FAR/FRR sweep finishes identically everywhere.  ``*_trials``: ``[M,2]``
+    utterance-index pairs.  Returns (EER, CL, IM) with CL / IM this rank's slices of the scores.
+    ``score_fn(emb, trials)`` / ``count_fn(scores)`` default to the CUDA kernels (``score_trial_list``,
+    ``utils.threshold_ge_counts``); the multi-process host-logic tests inject CPU stand-ins."""
+    import torch.distributed as dist
+    score_fn = score_fn or score_trial_list
+    count_fn = count_fn or utils.threshold_ge_counts
+    emb = extract_sharded(embed_fn, utterances, device, group=group, **kw)
+    rank, world = _rank_world(group)
+    client_trials, impostor_trials = np.asarray(client_trials), np.asarray(impostor_trials)
+    c0, c1 = rank_slice(len(client_trials), rank, world)
+    i0, i1 = rank_slice(len(impostor_trials), rank, world)
+    CL = score_fn(emb, client_trials[c0:c1]) if c1 > c0 else emb.new_zeros((0,))
+    IM = score_fn(emb, impostor_trials[i0:i1]) if i1 > i0 else emb.new_zeros((0,))
+    ge = torch.stack([count_fn(CL), count_fn(IM)])
+    if world > 1:
+        dist.all_reduce(ge, group=group)
+    return utils.eer_from_counts(ge[0].cpu().numpy(), len(client_trials), ge[1].cpu().numpy(), len(impostor_trials)), CL, IM

@@ -38,6 +38,29 @@ def test_shard_plan_is_balanced_partition():
         assert max(frames) / min(frames) < 1.1
 
 
+def test_global_plan_partitions_balances_and_respects_budget():
+    """BASELINE configs[3] lengths (2-20 s): every utterance in exactly one batch, batches within the frame budget (the
+    merged leftover may pass it by 25 %), rank loads within a few % of each other, and far fewer small batches than
+    per-rank bucketing."""
+    for world in (1, 2, 4, 8):
+        rs = np.random.RandomState(0)
+        L = (100 * rs.uniform(2, 20, size=256 * world)).astype(np.int64)
+        gp = extract.global_plan(L, world)
+        allidx = np.sort(np.concatenate([b for bs in gp for b in bs]))
+        assert np.array_equal(allidx, np.arange(len(L)))
+        for bs in gp:
+            for b in bs:
+                assert len(b) * L[b].max() <= 1.25 * 256 * 400
+        loads = [sum(extract._batch_cost(L, b) for b in bs) for bs in gp]
+        assert max(loads) <= 1.05 * np.mean(loads)
+        small = sum(1 for bs in gp for b in bs if len(b) * L[b].max() < 16 * 400)
+        old_small = sum(1 for p in extract.shard_plan(L, world) for b in extract.bucket_plan(L[p], 256 * 400, 0.8) if len(b) * L[p][b].max() < 16 * 400)
+        assert small <= 1 and old_small >= 2
+    # degenerate inputs
+    assert extract.global_plan(np.array([5]), 4) == [[np.array([0])], [], [], []] or sum(len(bs) for bs in extract.global_plan(np.array([5]), 4)) == 1
+    assert sum(len(bs) for bs in extract.global_plan(np.zeros((0,), np.int64), 2)) == 0
+
+
 def test_batch_plan_respects_budget_and_covers_all():
     lengths = np.random.RandomState(2).randint(200, 2000, size=57)
     batches = extract.batch_plan(lengths, max_frames=8000, max_batch=6)
@@ -61,6 +84,17 @@ def test_packed_path_and_bucket_plan():
     assert torch.allclose(emb, want, rtol=1e-5, atol=1e-5)
 
 
+def test_sparse_packed_holds_only_owned_utterances():
+    feats = make_feats(9, seed=11)
+    L = [f.shape[0] for f in feats]
+    owned = {i: feats[i] for i in (1, 4, 8)}
+    sp = extract.PackedUtterances.sparse(L, owned, pin=False)
+    assert len(sp) == 9 and sp.data.shape[0] == sum(L[i] for i in owned)
+    emb = extract.extract_local_packed(stub_embed, sp, [8, 1, 4], 'cpu', max_frames=10 ** 6)
+    want = torch.cat([stub_embed(torch.from_numpy(feats[i])[None], torch.tensor([L[i]])) for i in (8, 1, 4)])
+    assert torch.allclose(emb, want, rtol=1e-5, atol=1e-5)
+
+
 def test_single_process_matches_per_utterance():
     feats = make_feats(23, seed=3)
     emb = extract.extract_sharded(stub_embed, feats, 'cpu', max_frames=600)
@@ -80,6 +114,48 @@ def _worker(rank, world, port, n):
         assert torch.allclose(emb, want, rtol=1e-5, atol=1e-5), 'rank %d: gathered embeddings out of order' % rank
     finally:
         dist.destroy_process_group()
+
+
+def _validate_worker(rank, world, port):
+    """validate(): every rank scores its slice of the trial lists; the threshold counts are summed over the ranks, so the
+    EER equals the single-process sweep over all scores."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from doubleattentionspeakerverification_b200 import utils
+        feats = make_feats(13, seed=8)
+        rs = np.random.RandomState(1)
+        cl = np.stack([rs.randint(0, 13, 41), rs.randint(0, 13, 41)], 1)
+        im = np.stack([rs.randint(0, 13, 30), rs.randint(0, 13, 30)], 1)
+
+        def score(emb, trials):
+            t = torch.as_tensor(trials)
+            return torch.nn.functional.cosine_similarity(emb[t[:, 0]], emb[t[:, 1]], dim=-1)
+
+        def count(scores):
+            return (scores.double()[None, :] >= torch.from_numpy(utils.EER_THRESHOLDS)[:, None]).sum(1)
+
+        eer, CL, IM = extract.validate(stub_embed, feats, cl, im, 'cpu', embedding_size=4, max_frames=500, score_fn=score, count_fn=count)
+        want = torch.cat([stub_embed(torch.from_numpy(f)[None], torch.tensor([f.shape[0]])) for f in feats])
+        ge = [count(score(want, t)).numpy() for t in (cl, im)]
+        assert eer == utils.eer_from_counts(ge[0], len(cl), ge[1], len(im))
+        lo, hi = extract.rank_slice(len(cl), rank, world)
+        assert CL.numel() == hi - lo and torch.allclose(CL, score(want, cl[lo:hi]), atol=1e-6)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_validate_slices_trials_and_sums_counts():
+    mp.spawn(_validate_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_rank_slices_cover_rows():
+    for n in (0, 1, 7, 1024):
+        for world in (1, 2, 3, 8):
+            sl = [extract.rank_slice(n, r, world) for r in range(world)]
+            assert sl[0][0] == 0 and sl[-1][1] == n and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+            assert max(h - l for l, h in sl) - min(h - l for l, h in sl) <= 1
 
 
 def _free_port():
