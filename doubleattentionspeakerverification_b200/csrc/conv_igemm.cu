@@ -54,6 +54,8 @@ struct ConvParams {
     int sa;                  // reuse mode: stages of the separate A (weight tile) ring
     int pair;                // 1: CTA pairs (cta_group::2): 256 channels x N pixels per pair, each CTA loads half of the patch
     int w_f16, x_f16;        // operand formats of the MMA: weights / activations are fp16 (else bf16)
+    int balanced;            // ragged batches: tiles with valid frames are compacted through a per-CTA prefix table so that every
+                             // CTA gets the same number of them (and of the all-masked tiles, which only store zeros)
     int RT;                  // pair mode: frames of the patch half one CTA loads (without halo)
     int split_t;             // pair mode: halves split along t (BB == 1) or along the utterance (BB == 2)
 };
@@ -84,6 +86,50 @@ DASV_DEVICE bool conv_tile_masked(const ConvParams& p, const ConvTile& c) {
     for (int bb = 0; bb < p.BB; ++bb)
         if (conv_len(p, c.b0 + bb) > c.t0) return false;
     return true;
+}
+
+// ---- balanced schedule for ragged batches.  A group = the BB utterances of one patch column; its first vt t-tiles
+// hold valid frames, the rest are all-masked.  vpre[g] = number of valid tiles in groups < g (built once per CTA).
+constexpr int kConvMaxGroups = 2047;
+
+DASV_DEVICE int conv_group_vt(const ConvParams& p, int g) {
+    int Lmax = 0;
+    for (int bb = 0; bb < p.BB; ++bb) Lmax = max(Lmax, conv_len(p, g * p.BB + bb));
+    return (Lmax + p.BT - 1) / p.BT;
+}
+
+struct ConvSched {
+    const int* vpre;         // [n_bt + 1] (balanced mode)
+    int n_pass0, n_pass1;    // tiles of the main pass (valid ones when balanced, else all) and of the zero-fill pass
+    int per_t;               // tiles per (group, t-tile): n_mt_eff * n_ft
+};
+
+// Tile q of pass `pass`.  Unbalanced mode (no lengths, or too many groups): the plain order, masked tiles flagged.
+DASV_DEVICE ConvTile conv_tile_at(const ConvParams& p, const ConvSched& sc, int q, int pass, int n_mt_eff, int rank, bool& masked) {
+    if (!p.balanced) {
+        const ConvTile c = conv_decode_tile(p, q, n_mt_eff, rank);
+        masked = conv_tile_masked(p, c);
+        return c;
+    }
+    const int per_g = sc.per_t * p.n_tt;
+    int lo = 0, hi = p.n_bt;             // the group g with pre(g) <= q < pre(g + 1)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        const int pre = pass == 0 ? sc.vpre[mid] : mid * per_g - sc.vpre[mid];
+        if (pre <= q) lo = mid; else hi = mid;
+    }
+    const int g = lo;
+    int local = q - (pass == 0 ? sc.vpre[g] : g * per_g - sc.vpre[g]);
+    const int vt = (sc.vpre[g + 1] - sc.vpre[g]) / sc.per_t;
+    ConvTile c;
+    c.m = local % n_mt_eff;
+    if (p.pair) c.m = c.m * 2 + rank;
+    local /= n_mt_eff;
+    c.f0 = (local % p.n_ft) * p.BF;
+    c.t0 = (local / p.n_ft + (pass == 0 ? 0 : vt)) * p.BT;
+    c.b0 = g * p.BB;
+    masked = pass != 0;
+    return c;
 }
 
 DASV_DEVICE void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -135,6 +181,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t* acc_full = aempty + p.sa;         // [2]
     uint64_t* acc_empty = acc_full + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    int* vpre = reinterpret_cast<int*>(tmem_slot + 4);     // [n_bt + 1], balanced mode only (the host sized the window for it)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                  // 0 = leader of the CTA pair
@@ -164,6 +211,27 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // everything above overlapped the previous kernel's tail (programmatic dependent launch); x, the mask and the
     // memory behind y belong to earlier kernels of the stream from here on
     griddep_wait();
+    ConvSched sched{vpre, n_tiles, 0, n_mt_eff * p.n_ft};
+    if (p.balanced) {
+        if (warp == 3) {                                    // the spare role warp scans the groups' valid-tile counts
+            int carry = 0;
+            for (int g0 = 0; g0 < p.n_bt; g0 += 32) {
+                const int g = g0 + lane;
+                int v = g < p.n_bt ? conv_group_vt(p, g) * sched.per_t : 0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, v, off);
+                    if (lane >= off) v += u;
+                }
+                if (g < p.n_bt) vpre[g + 1] = carry + v;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
+            if (lane == 0) vpre[0] = 0;
+        }
+        __syncthreads();
+        sched.n_pass0 = vpre[p.n_bt];
+        sched.n_pass1 = n_tiles - sched.n_pass0;
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -171,9 +239,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // tap-row reuse: per (64-channel slice, dx) ONE activation patch with a +-1 frame halo, then the three
             // weight tiles of that tap column (dy = -1, 0, +1); 3x less activation traffic than one box per tap.
             uint32_t sb = 0, bph = 0, sa = 0, aph = 0;
-            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-                const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
-                if (conv_tile_masked(p, c)) continue;
+            for (int tile = tile0; tile < sched.n_pass0; tile += tile_step) {
+                bool tile_masked;
+                const ConvTile c = conv_tile_at(p, sched, tile, 0, n_mt_eff, static_cast<int>(rank), tile_masked);
+                if (tile_masked) continue;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     for (int dxi = 0; dxi < 3; ++dxi) {
                         mbar_wait(&empty[sb], bph ^ 1u);
@@ -207,9 +276,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         } else if (lane == 0) {
             uint32_t st = 0, ph = 0;
-            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-                const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
-                if (conv_tile_masked(p, c)) continue;
+            for (int tile = tile0; tile < sched.n_pass0; tile += tile_step) {
+                bool tile_masked;
+                const ConvTile c = conv_tile_at(p, sched, tile, 0, n_mt_eff, static_cast<int>(rank), tile_masked);
+                if (tile_masked) continue;
                 for (int tap = 0; tap < 9; ++tap) {
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                     for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -228,9 +298,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0 && rank == 0) {           // in pair mode only the leader issues (for both CTAs)
             const uint32_t idesc = umma_idesc_f16kind(PAIR ? 2 * kConvTileM : kConvTileM, static_cast<uint32_t>(p.Npad), p.w_f16 != 0, p.x_f16 != 0);
             uint32_t st = 0, ph = 0, sa = 0, aph = 0, acc_it = 0;
-            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-                const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
-                if (conv_tile_masked(p, c)) continue;
+            for (int tile = tile0; tile < sched.n_pass0; tile += tile_step) {
+                bool tile_masked;
+                const ConvTile c = conv_tile_at(p, sched, tile, 0, n_mt_eff, static_cast<int>(rank), tile_masked);
+                if (tile_masked) continue;
                 const uint32_t as = acc_it & 1u, accph = (acc_it >> 1) & 1u;
                 mbar_wait(&acc_empty[as], accph ^ 1u);
                 tc_fence_after();
@@ -302,11 +373,12 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int ch = q * 32 + lane;                           // channel within the 128-wide tile
         unsigned char* my_stage = stage + half * (2 * kConvEpiBytes);
         uint32_t acc_it = 0, chunk_it = 0;
-        for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-            const ConvTile c = conv_decode_tile(p, tile, n_mt_eff, static_cast<int>(rank));
+        for (int pass = 0; pass < 2; ++pass)                    // pass 1 (balanced mode): the all-masked tiles, zeros only
+        for (int tile = tile0; tile < (pass == 0 ? sched.n_pass0 : sched.n_pass1); tile += tile_step) {
+            bool masked;
+            const ConvTile c = conv_tile_at(p, sched, tile, pass, n_mt_eff, static_cast<int>(rank), masked);
             const int n = c.m * kConvTileM + ch;
             const bool n_ok = n < Cout;
-            const bool masked = conv_tile_masked(p, c);
             const int ot0 = p.pool ? (c.t0 >> 1) : c.t0, of0 = p.pool ? (c.f0 >> 1) : c.f0;
             uint32_t tcol = 0;
             if (!masked) {
@@ -487,7 +559,7 @@ struct ConvPlan {
 // MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
 // ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
-static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms) {
+static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged) {
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
     for (int BF = 2; BF <= F && BF <= 256; BF += 2) {
@@ -520,7 +592,10 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int
                 const double ingest = (128.0 + b_rows) * 32.0 / 52.0;                   // bytes per 16-deep step / ~52 B/clk effective
                 double step = Npad / 2.0 > ingest ? Npad / 2.0 : ingest;
                 if (step < 40.0) step = 40.0;                                           // issue + operand-fetch floor of one MMA
-                const double cost = waves * (step * ksteps + 700.0);
+                double cost = waves * (step * ksteps + 700.0);
+                // ragged batches: the tile that straddles an utterance's end computes rows that are masked afterwards
+                // (half a tile height per utterance on average, against ~3/4 of the padded length in valid rows)
+                if (ragged) cost *= 1.0 + (0.5 * BT) / (0.75 * T + 1.0);
                 if (cost < best.cost) best = ConvPlan{BF, BT, BB, N, Npad, cost};
             }
         }
@@ -538,8 +613,8 @@ using namespace dasv;
 struct ConvKey {
     const void* x; const void* wp;
     int B, T, F, Cin, Cout, flags, y_dtype, dgrad, dev;   // flags include the operand-format bits
-    int env_reuse, env_pair, env_sb;
-    char env_plan[24];
+    int env_reuse, env_pair, env_sb, ragged;   // ragged: lengths given (the plan then prefers low tiles)
+    char env_plan[20];
 };
 struct ConvEntry {
     ConvKey key;
@@ -596,8 +671,8 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     if (k.env_pair >= 0) pair = k.env_pair;
     if (!reuse || cout_pad % (2 * kConvTileM) != 0) pair = 0;
     const int sms = sm_count();
-    ConvPlan pl = conv_plan(B, T, F, Cin, Cout, pool, reuse ? 2 : 0, pair != 0, sms);
-    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Cin, Cout, pool, 2, false, sms); }
+    ConvPlan pl = conv_plan(B, T, F, Cin, Cout, pool, reuse ? 2 : 0, pair != 0, sms, k.ragged != 0);
+    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Cin, Cout, pool, 2, false, sms, k.ragged != 0); }
     if (k.env_plan[0]) {                                         // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
         int bf = 0, bt = 0, bb = 0;
         if (sscanf(k.env_plan, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
@@ -644,11 +719,13 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (k.y_dtype == 0);
     p.relu = (flags & 1) ? 1 : 0;
     p.w_f16 = (flags & 16) ? 1 : 0; p.x_f16 = (flags & 32) ? 1 : 0;
+    p.balanced = (k.ragged && p.n_bt <= kConvMaxGroups && !getenv("DASV_CONV_UNBALANCED")) ? 1 : 0;
     p.reuse = reuse;
     p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
     p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;
     p.b_bytes = static_cast<uint32_t>(box_b) * box_t * pl.BF * 128u;
-    const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512;     // staging + alignment slack + barriers
+    // staging + alignment slack + barriers (+ the valid-tile prefix table of a ragged batch)
+    const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512 + (p.balanced ? ((static_cast<uint32_t>(p.n_bt) + 1u) * 4u + 15u) / 16u * 16u : 0u);
     const uint32_t kAvail = 227u * 1024u - kFixed;
     if (reuse) {
         // ring 1 = activation patches (+ the rows a 16-padded, 2-frame-shifted MMA view may touch), ring 2 = weight tiles
@@ -710,7 +787,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     memset(&k, 0, sizeof(k));
     k.x = x; k.wp = wp; k.B = B; k.T = T; k.F = F; k.Cin = Cin; k.Cout = Cout; k.flags = flags; k.y_dtype = y_dtype;
     if (cudaGetDevice(&k.dev) != cudaSuccess) { set_error("conv3x3_igemm_bf16: no current device"); cudaGetLastError(); return 1; }
-    k.env_reuse = 1; k.env_pair = -1; k.env_sb = 0;
+    k.env_reuse = 1; k.env_pair = -1; k.env_sb = 0; k.ragged = lengths != nullptr;
     if (const char* e = getenv("DASV_CONV_REUSE")) k.env_reuse = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_PAIR")) k.env_pair = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_SB")) k.env_sb = atoi(e);
