@@ -172,35 +172,65 @@ def bucket_plan(lengths, max_frames, min_ratio=0.8, max_batch=None):
 
 
 def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400, min_ratio=0.8, max_batch=None, batches=None):
-    """Embed ``packed`` utterances ``indices``: their frames go to the device once (one async copy per utterance from
-    the pinned buffer, no host padding), then every batch is ONE device gather into ``[B, Tmax, F]`` with frame indices
-    clamped to the utterance (the kernels ignore frames >= length, so the padding content does not matter).
-    ``batches`` (index arrays INTO ``indices``) overrides the local bucket plan.
+    """Embed ``packed`` utterances ``indices``.  Per batch: the frames of its utterances go to the device (one async copy
+    per utterance from the pinned buffer, no host padding) on a COPY STREAM, so the transfer of batch k+1 runs under the
+    kernels of batch k; then ONE device gather builds ``[B, Tmax, F]`` with frame indices clamped to the utterance (the
+    kernels ignore frames >= length, so the padding content does not matter).  The smallest batch goes first: its copy
+    is the only one nothing hides.  ``batches`` (index arrays INTO ``indices``) overrides the local bucket plan.
     Returns ``[len(indices), E]`` in the order of ``indices``."""
     indices = np.asarray(indices)
     if len(indices) == 0:
         return None
     dev = torch.device(device)
     L = packed.lengths[indices]
-    starts = np.concatenate([[0], np.cumsum(L)])
-    frames = torch.empty((int(starts[-1]), packed.data.shape[1]), device=dev, dtype=torch.float32)
-    for j, i in enumerate(indices):
-        o = int(packed.offsets[i])
-        frames[int(starts[j]):int(starts[j + 1])].copy_(packed.data[o:o + int(L[j])], non_blocking=True)
-    starts_d = torch.from_numpy(starts[:-1]).to(dev)
-    L_d = torch.from_numpy(L).to(dev)
+    if batches is None:
+        batches = bucket_plan(L, max_frames, min_ratio, max_batch)
+    batches = sorted((np.asarray(b) for b in batches), key=lambda b: int(L[b].sum()))
+    cuda = dev.type == 'cuda'
+    if cuda:
+        compute = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream.wait_stream(compute)
+    staged = []
+    for b in batches:                                            # enqueue every batch's transfer up front, in processing order
+        Lb = L[b]
+        starts = np.concatenate([[0], np.cumsum(Lb)])
+        with (torch.cuda.stream(copy_stream) if cuda else _NullCtx()):
+            frames = torch.empty((int(starts[-1]), packed.data.shape[1]), device=dev, dtype=torch.float32)
+            for j, i in enumerate(indices[b]):
+                o = int(packed.offsets[i])
+                frames[int(starts[j]):int(starts[j + 1])].copy_(packed.data[o:o + int(Lb[j])], non_blocking=True)
+            starts_d = torch.from_numpy(starts[:-1]).to(dev, non_blocking=True)
+            L_d = torch.from_numpy(Lb).to(dev, non_blocking=True)
+            ev = None
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+        staged.append((b, frames, starts_d, L_d, ev))
     out = None
-    for b in (bucket_plan(L, max_frames, min_ratio, max_batch) if batches is None else batches):
-        bt = torch.from_numpy(np.asarray(b)).to(dev)
+    for b, frames, starts_d, L_d, ev in staged:
+        if cuda:
+            compute.wait_event(ev)
+            frames.record_stream(compute)
+            starts_d.record_stream(compute)
+            L_d.record_stream(compute)
         Tmax = int(L[b].max())
         t = torch.arange(Tmax, device=dev)
-        rows = starts_d[bt, None] + torch.minimum(t[None, :], L_d[bt, None] - 1)          # [B, Tmax] source frame of every slot
+        rows = starts_d[:, None] + torch.minimum(t[None, :], L_d[:, None] - 1)             # [B, Tmax] source frame of every slot
         x = frames[rows]                                                                   # one gather: padded batch
-        emb = embed_fn(x, L_d[bt].to(torch.int32))
+        emb = embed_fn(x, L_d.to(torch.int32))
         if out is None:
             out = torch.empty((len(indices), emb.shape[1]), device=emb.device, dtype=emb.dtype)
-        out[bt] = emb
+        out[torch.from_numpy(b).to(dev)] = emb
     return out
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def extract_sharded_audio(embed_fn, waves, sfr, device, group=None, embedding_size=None, feature_fn=None, **kw):

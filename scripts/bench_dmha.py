@@ -6,7 +6,7 @@ import torch
 from doubleattentionspeakerverification_b200 import ops, synth
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'both'
-B, T, D, H = 512, 200, 1024, 16
+B, T, D, H = int(os.environ.get('BENCH_B', 512)), 200, 1024, 16     # BENCH_B: other utterance counts (tail / quantisation studies)
 PEAK = 6538.3
 dev = 'cuda'
 gen = torch.Generator(device=dev).manual_seed(0)
@@ -45,4 +45,4 @@ for name, dt in (('fp32', torch.float32), ('bf16', torch.bfloat16)):
         us = time_us(lambda i: ops.dmha_fwd(xs[i & 1], q, a, lengths=L, need_align=False))
         out['%s_%s' % (name, case)] = (round(us, 1), round(nbytes / us / 1e3 / PEAK, 3))
     del xs
-print({k: os.environ[k] for k in os.environ if k.startswith('DASV_')}, out, flush=True)
+print({k: os.environ[k] for k in os.environ if k.startswith(('DASV_', 'BENCH_'))}, out, flush=True)
