@@ -197,7 +197,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32'])
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16', 'fp32x3', 'fp32'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-dmha', action='store_true')
@@ -503,7 +503,7 @@ def main():
     # ---- the other precisions of the same step (fp16 operands; fp32 parity path) as secondary numbers
     if extras is not None and 'error' not in extras:
         try:
-            for prec, bsz, reps in (('fp16', Bn, 5), ('fp32', 32, 2)):
+            for prec, bsz, reps in (('fp16', Bn, 5), ('fp32x3', Bn, 3), ('fp32', 32, 2)):
                 if prec == args.precision:
                     continue
                 c2 = synth.example_config()
@@ -539,7 +539,7 @@ def main():
         d2h = emb_host.numel() * 4
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
+                'dtype': {'bf16': 'bf16', 'fp16': 'f16', 'fp32': 'f32', 'fp32x3': 'f32 (3 x bf16 split)'}[args.precision], 'data': 'synthetic',
                 'config': workload_config(world, Bn),
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': ms_e2e / args.steps},

@@ -10,7 +10,10 @@ Inference (no autograd) runs on this package's sm_100a kernels, NHWC end to end:
     format, but both operands must have the same one: a mixed pair is an illegal instruction on B200): three more
     mantissa bits than bf16 at the same speed (embedding cosine 0.99991 -> 0.99999, trial-score error 1e-3 -> 2e-4 on the
     exampleModel config), for models whose activations stay below 65504; stores saturate instead of overflowing.
-  * ``precision='fp32'``: CUDA-core fp32 implicit GEMM + separate pool kernel (the 1e-4 parity path).
+  * ``precision='fp32x3'``: fp32 parity ON the tensor cores: every fp32 activation and weight travels as two bf16 numbers
+    (hi = bf16(v), lo = bf16(v - hi)) and a product is three MMAs, hi*hi + hi*lo + lo*hi, accumulated in fp32 (error ~2^-16
+    per product; embeddings within 1e-4 of the reference, measured ~1e-5) -- the same kernels at a third of the bf16 rate.
+  * ``precision='fp32'``: CUDA-core fp32 implicit GEMM + separate pool kernel (plain fp32 FMAs; the slowest path).
   * ``precision='auto'`` (default): bf16 when the channel counts allow it, else fp32.
 Under autograd the default is torch (cuDNN) convolutions in fp32, numerically the reference's own training path.
 ``train_kernels=True`` (with bf16 precision and channel counts that are multiples of 64) switches training to this
@@ -72,6 +75,8 @@ class _VGG(nn.Module):
             with torch.no_grad():
                 if kind == 'f32':
                     packed = ops.pack_conv_weight_f32(w.detach())
+                elif kind == 'x3':
+                    packed = ops.pack_conv_weight_x3(w.detach())
                 else:
                     packed = ops.pack_conv_weight_bf16(w.detach(), torch.float16 if kind == 'f16' else torch.bfloat16)
             hit = (tag, packed)
@@ -79,7 +84,7 @@ class _VGG(nn.Module):
         return hit[1]
 
     def resolved_precision(self):
-        if self.precision in ('bf16', 'fp16', 'fp32'):
+        if self.precision in ('bf16', 'fp16', 'fp32', 'fp32x3'):
             return self.precision
         ok = all(getattr(self, n).in_channels % 64 == 0 and getattr(self, n).out_channels % 8 == 0 for n in self._names[1:])
         return 'bf16' if ok else 'fp32'
@@ -92,8 +97,8 @@ class _VGG(nn.Module):
         for _ in range(len(self._names) // 2):
             even = even and f % 2 == 0
             f = (f + 1) // 2
-        if prec in ('bf16', 'fp16') and not even:
-            if self.precision in ('bf16', 'fp16'):
+        if prec in ('bf16', 'fp16', 'fp32x3') and not even:
+            if self.precision in ('bf16', 'fp16', 'fp32x3'):
                 raise ValueError('the tensor-core path needs an even number of frequency bins in front of every pool (got %d)' % feature_size)
             return 'fp32'
         return prec
@@ -154,22 +159,23 @@ class _VGG(nn.Module):
         L = None if lengths is None else torch.as_tensor(lengths, device=x.device).to(torch.int32)
         c11 = getattr(self, self._names[0])
         nblocks = len(self._names) // 2
-        if prec in ('bf16', 'fp16'):
+        if prec in ('bf16', 'fp16', 'fp32x3'):
             act = torch.float16 if prec == 'fp16' else torch.bfloat16
-            wk = 'f16' if prec == 'fp16' else 'bf16'       # both MMA operands must have the same 16-bit format
+            x3 = prec == 'fp32x3'
+            wk = 'x3' if x3 else ('f16' if prec == 'fp16' else 'bf16')       # both MMA operands must have the same 16-bit format
             # conv11 is bound by its NHWC 16-bit write (2.1 GB per 256 x 4 s batch at the 3.95 TB/s pure-write bandwidth)
-            h = ops.conv11_direct(x, c11.weight, c11.bias, L, out_dtype=act)
+            h = ops.conv11_direct(x, c11.weight, c11.bias, L, out_dtype=act, split=x3)
             for blk in range(nblocks):
                 if blk > 0:
                     c = getattr(self, self._names[2 * blk])
-                    h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk], wk), c.bias, c.out_channels, L)
+                    h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk], wk), c.bias, c.out_channels, L, x3=x3)
                 c = getattr(self, self._names[2 * blk + 1])
                 last = blk == nblocks - 1
                 # CTA pairs (cta_group::2) measured faster on the pooled layers with >= 256 input channels (conv22 +3 %,
                 # conv32 +9 %, conv42 +1 %) and slower elsewhere; results are bit-identical either way
                 pair = c.in_channels >= 256 and c.out_channels % 256 == 0
                 h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk + 1], wk), c.bias, c.out_channels, L,
-                                           pool=True, ref_layout=last, out_dtype=torch.float32, pair=pair)
+                                           pool=True, ref_layout=last, out_dtype=torch.float32, pair=pair, x3=x3)
                 if L is not None:
                     L = (L + 1) // 2
             return h

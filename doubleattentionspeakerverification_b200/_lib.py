@@ -27,6 +27,7 @@ SIGNATURES = {
     'dasv_packed_conv_weight_bf16_elems': (_sz, [_i, _i]),
     'dasv_pack_conv_weight_bf16': (_i, [_vp, _vp, _i, _i, _vp]),
     'dasv_pack_conv_weight_16': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'dasv_pack_conv_weight_x3': (_i, [_vp, _vp, _i, _i, _vp]),
     'dasv_conv3x3_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_maxpool2x2': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_igemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

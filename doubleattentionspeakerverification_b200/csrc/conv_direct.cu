@@ -15,7 +15,7 @@ namespace dasv {
 // (channel group fastest), so the 16-byte stores of neighbouring threads form one contiguous run.
 constexpr int kC11Rows = 8;
 
-template <int OUT>      // 0 = f32, 1 = bf16, 2 = f16 output (the C ABI's dtype codes)
+template <int OUT>      // 0 = f32, 1 = bf16, 2 = f16 output (the C ABI's dtype codes); 3 = split bf16 [hi(Cout) | lo(Cout)] per pixel
 __global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const int32_t* __restrict__ lengths,
                                                            void* __restrict__ y, int B, int T, int F, int Cout) {
@@ -91,7 +91,23 @@ __global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restr
             a1[e] = valid ? fmaxf(a1[e], 0.f) : 0.f;
         }
         const size_t o = (static_cast<size_t>(b) * T + t) * row_elems + static_cast<size_t>(f) * Cout + cg * 8;
-        if (OUT != 0) {
+        if (OUT == 3) {
+            // fp32x3 mode: v = hi + lo with hi = bf16(v), lo = bf16(v - hi); pixel pitch 2 * Cout
+            const size_t o2 = (static_cast<size_t>(b) * T + t) * (2 * row_elems) + static_cast<size_t>(f) * (2 * Cout) + cg * 8;
+            uint16_t* yb = static_cast<uint16_t*>(y);
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                const float* a = px == 0 ? a0 : a1;
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    hi[e] = pack_bf16(a[2 * e], a[2 * e + 1]);
+                    lo[e] = pack_bf16(a[2 * e] - bf16_lo(hi[e]), a[2 * e + 1] - bf16_hi(hi[e]));
+                }
+                *reinterpret_cast<uint4*>(yb + o2 + px * 2 * Cout) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(yb + o2 + px * 2 * Cout + Cout) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        } else if (OUT != 0) {
             uint4 v;
             v.x = pack16<OUT>(a0[0], a0[1]); v.y = pack16<OUT>(a0[2], a0[3]);
             v.z = pack16<OUT>(a0[4], a0[5]); v.w = pack16<OUT>(a0[6], a0[7]);
@@ -276,7 +292,7 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
                                   void* y, int y_dtype, int B, int T, int F, int Cout, void* stream) {
     if (!x || !w || !bias || !y) { set_error("conv11_direct: null argument"); return 1; }
     if (Cout % 8 != 0 || Cout <= 0) { set_error("conv11_direct: Cout=%d must be a positive multiple of 8", Cout); return 1; }
-    if (y_dtype < 0 || y_dtype > 2) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
+    if (y_dtype < 0 || y_dtype > 3) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
     if (Cout > 2048) { set_error("conv11_direct: Cout=%d > 2048", Cout); return 1; }
     if (F % 2 != 0) { set_error("conv11_direct: F=%d must be even", F); return 1; }
     if (B <= 0 || T <= 0) return 0;
@@ -288,6 +304,7 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
     cudaError_t e;
     if (y_dtype == 1) e = launch_pdl(conv11_direct_kernel<1>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout);
     else if (y_dtype == 2) e = launch_pdl(conv11_direct_kernel<2>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout);
+    else if (y_dtype == 3) e = launch_pdl(conv11_direct_kernel<3>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout);
     else e = launch_pdl(conv11_direct_kernel<0>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout);
     if (e != cudaSuccess) { set_error("conv11_direct: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("conv11_direct");
@@ -314,6 +331,26 @@ extern "C" int dasv_pack_conv_weight_16(const float* w, void* packed, int Cout, 
     if (dtype == 2) pack_w_bf16_kernel<2><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<uint16_t*>(packed), Cout, Cin, cp);
     else pack_w_bf16_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<uint16_t*>(packed), Cout, Cin, cp);
     return check_launch("pack_conv_weight_16");
+}
+
+// fp32x3 mode: [Cout_pad][9][3*Cin] bf16 = per tap [hi(w) | hi(w) | lo(w)], to be contracted with activations laid out
+// [hi(x) | lo(x)] and read as [hi(x) | lo(x) | hi(x)]:  w*x ~= hi(w)hi(x) + hi(w)lo(x) + lo(w)hi(x)  (error ~2^-16 |w x|).
+__global__ void pack_w_x3_kernel(const float* __restrict__ w, uint16_t* __restrict__ p, int Cout, int Cin, int Cout_pad) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // [co][tap][3*Cin]
+    if (i >= static_cast<size_t>(Cout_pad) * 27 * Cin) return;
+    const int j = i % (3 * Cin), tap = (i / (3 * Cin)) % 9, co = i / (static_cast<size_t>(Cin) * 27);
+    const int ci = j % Cin, seg = j / Cin;
+    const float v = co < Cout ? w[(static_cast<size_t>(co) * Cin + ci) * 9 + tap] : 0.f;
+    const uint16_t hi = cvt_bf16_bits(v);
+    p[i] = seg < 2 ? hi : cvt_bf16_bits(v - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+}
+
+extern "C" int dasv_pack_conv_weight_x3(const float* w, void* packed, int Cout, int Cin, void* stream) {
+    if (!w || !packed) { set_error("pack_conv_weight_x3: null argument"); return 1; }
+    const int cp = (Cout + 127) / 128 * 128;
+    const size_t n = static_cast<size_t>(cp) * 27 * Cin;
+    pack_w_x3_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<uint16_t*>(packed), Cout, Cin, cp);
+    return check_launch("pack_conv_weight_x3");
 }
 
 extern "C" int dasv_pack_conv_weight_bf16(const float* w, void* packed, int Cout, int Cin, void* stream) {

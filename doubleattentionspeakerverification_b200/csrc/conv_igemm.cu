@@ -40,7 +40,9 @@ struct ConvParams {
     int BF, BT, BB;          // patch: BF frequency bins x BT frames x BB utterances
     int N, Npad;             // pixels per patch, rounded up to 16 (UMMA N)
     int n_ft, n_tt, n_bt, n_mt;
-    int kchunks;             // Cin / 64
+    int kchunks;             // K slices of 64 channels per tap: Cin / 64 (3 * Cin / 64 in split mode)
+    int a_tap_stride;        // columns of the packed weights per tap: Cin (3 * Cin in split mode)
+    int kcx_wrap;            // split mode: K slices >= this one re-read the activation slices from the start (x_hi again)
     int stages;
     int pool, ref_layout, y_f32;
     int relu;                // 0: linear epilogue (input-gradient pass), only without POOL
@@ -158,12 +160,13 @@ DASV_DEVICE uint32_t bf16x2_positive_mask(uint32_t v) {
 template <bool F32, int ACT>
 DASV_DEVICE void conv_store(void* y, size_t idx, float v) {
     if (F32) static_cast<float*>(y)[idx] = v;
-    else static_cast<uint16_t*>(y)[idx] = cvt16_bits<ACT>(v);
+    else static_cast<uint16_t*>(y)[idx] = cvt16_bits<ACT == 3 ? 1 : ACT>(v);
 }
 
 // DGRAD = false: the forward layer (bias + ReLU (+ pool)).  DGRAD = true: the input-gradient pass (linear epilogue, optional
 // ReLU-backward mask); a separate instantiation so that the forward's epilogue carries none of its branches.
-// ACT = format of a 16-bit output (the C ABI's dtype codes): 1 = bf16, 2 = fp16 (saturating).
+// ACT = format of a 16-bit output: 1 = bf16, 2 = fp16 (saturating), 3 = split bf16 (the fp32x3 mode: an fp32 value v is
+// stored as hi = bf16(v) in channel c and lo = bf16(v - hi) in channel Cout + c of a 2*Cout-channel tensor).
 template <bool PAIR, bool DGRAD = false, int ACT = 1>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
@@ -244,6 +247,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const ConvTile c = conv_tile_at(p, sched, tile, 0, n_mt_eff, static_cast<int>(rank), tile_masked);
                 if (tile_masked) continue;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
+                    const int kcx = kc >= p.kcx_wrap ? kc - p.kcx_wrap : kc;     // activation slice of this K slice
                     for (int dxi = 0; dxi < 3; ++dxi) {
                         mbar_wait(&empty[sb], bph ^ 1u);
                         if (PAIR) {
@@ -252,10 +256,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             const int tq = c.t0 + (p.split_t ? static_cast<int>(rank) * p.RT : 0);
                             const int bq = c.b0 + (p.split_t ? 0 : static_cast<int>(rank));
                             if (rank == 0) mbar_arrive_expect_tx(&full[sb], 2u * p.b_bytes);
-                            tma_load_4d_2sm(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kc * kConvKC, c.f0 + dxi - 1, tq - 1, bq);
+                            tma_load_4d_2sm(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kcx * kConvKC, c.f0 + dxi - 1, tq - 1, bq);
                         } else {
                             mbar_arrive_expect_tx(&full[sb], p.b_bytes);
-                            tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kc * kConvKC, c.f0 + dxi - 1, c.t0 - 1, c.b0);
+                            tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kcx * kConvKC, c.f0 + dxi - 1, c.t0 - 1, c.b0);
                         }
                         if (++sb == static_cast<uint32_t>(p.stages)) { sb = 0; bph ^= 1u; }
                         for (int dyi = 0; dyi < 3; ++dyi) {
@@ -263,11 +267,11 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             if (PAIR) {
                                 if (rank == 0) mbar_arrive_expect_tx(&afull[sa], 2u * kConvABytes);
                                 tma_load_2d_2sm(ring_a + static_cast<size_t>(sa) * kConvABytes, &tmA, &afull[sa],
-                                                (dyi * 3 + dxi) * p.Cin + kc * kConvKC, c.m * kConvTileM);
+                                                (dyi * 3 + dxi) * p.a_tap_stride + kc * kConvKC, c.m * kConvTileM);
                             } else {
                                 mbar_arrive_expect_tx(&afull[sa], kConvABytes);
                                 tma_load_2d(ring_a + static_cast<size_t>(sa) * kConvABytes, &tmA, &afull[sa],
-                                            (dyi * 3 + dxi) * p.Cin + kc * kConvKC, c.m * kConvTileM);
+                                            (dyi * 3 + dxi) * p.a_tap_stride + kc * kConvKC, c.m * kConvTileM);
                             }
                             if (++sa == static_cast<uint32_t>(p.sa)) { sa = 0; aph ^= 1u; }
                         }
@@ -286,8 +290,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         mbar_wait(&empty[st], ph ^ 1u);
                         unsigned char* a_sm = ring + static_cast<size_t>(st) * p.stage_bytes;
                         mbar_arrive_expect_tx(&full[st], kConvABytes + p.b_bytes);
-                        tma_load_2d(a_sm, &tmA, &full[st], tap * p.Cin + kc * kConvKC, c.m * kConvTileM);
-                        tma_load_4d(a_sm + kConvABytes, &tmB, &full[st], kc * kConvKC, c.f0 + dx, c.t0 + dy, c.b0);
+                        tma_load_2d(a_sm, &tmA, &full[st], tap * p.a_tap_stride + kc * kConvKC, c.m * kConvTileM);
+                        tma_load_4d(a_sm + kConvABytes, &tmB, &full[st], (kc >= p.kcx_wrap ? kc - p.kcx_wrap : kc) * kConvKC, c.f0 + dx, c.t0 + dy, c.b0);
                         if (++st == static_cast<uint32_t>(p.stages)) { st = 0; ph ^= 1u; }
                     }
                 }
@@ -436,7 +440,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
             // ---------------- NHWC bf16 output: this half's chunks of kConvEpiChunk output pixels
             const int n_chunks = (NO + kConvEpiChunk - 1) / kConvEpiChunk;
-            for (int ck = half; ck < n_chunks; ck += 2) {
+            constexpr int kParts = ACT == 3 ? 2 : 1;                // split output: the chunk is staged and stored twice (hi, lo)
+            auto cvt_out = [](float v, int part) -> uint16_t {
+                if (ACT != 3) return cvt16_bits<ACT == 3 ? 1 : ACT>(v);
+                const uint16_t hi = cvt_bf16_bits(v);
+                return part == 0 ? hi : cvt_bf16_bits(v - __uint_as_float(static_cast<uint32_t>(hi) << 16));
+            };
+            for (int ck = half; ck < n_chunks; ck += 2)
+            for (int part = 0; part < kParts; ++part) {
                 const int o0 = ck * kConvEpiChunk;
                 const int cnt = min(kConvEpiChunk, NO - o0);
                 unsigned char* buf = my_stage + (chunk_it & 1u) * kConvEpiBytes;
@@ -466,7 +477,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
                                     if (g16 * 16 + j < cnt)
-                                        dst[(g16 * 16 + j) * kConvTileM] = cvt16_bits<ACT>(DGRAD ? __uint_as_float(r[j]) + bias : fmaxf(__uint_as_float(r[j]) + bias, 0.f));
+                                        dst[(g16 * 16 + j) * kConvTileM] = cvt_out(DGRAD ? __uint_as_float(r[j]) + bias : fmaxf(__uint_as_float(r[j]) + bias, 0.f), part);
                             }
                         }
                     } else {
@@ -494,7 +505,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 if (j0 + u < cnt) {
                                     float m = fmaxf(__uint_as_float(v[u][0]), __uint_as_float(v[u][1]));
                                     if (r1[u]) m = fmaxf(m, fmaxf(__uint_as_float(v[u][2]), __uint_as_float(v[u][3])));
-                                    dst[(j0 + u) * kConvTileM] = cvt16_bits<ACT>(fmaxf(m + bias, 0.f));   // max and +bias/ReLU commute
+                                    dst[(j0 + u) * kConvTileM] = cvt_out(fmaxf(m + bias, 0.f), part);   // max and +bias/ReLU commute
                                 }
                             }
                         }
@@ -519,7 +530,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 uint4 val = make_uint4(0u, 0u, 0u, 0u);
                                 if (!masked && t_in < conv_len(p, b))
                                     val = *reinterpret_cast<const uint4*>(buf + po * (kConvTileM * 2) + seg * 16);
-                                const size_t yoff = ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c.m * kConvTileM + seg * 8;
+                                const size_t yoff = ((static_cast<size_t>(b) * OT + to) * OF + fo) * (kParts * Cout) + part * Cout + c.m * kConvTileM + seg * 8;
                                 if (DGRAD && p.mask != nullptr) {    // fused ReLU backward: keep the gradient where the activation was > 0
                                     const uint4 mv = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mask) + yoff);
                                     val.x &= bf16x2_positive_mask(mv.x); val.y &= bf16x2_positive_mask(mv.y);
@@ -560,6 +571,7 @@ struct ConvPlan {
 // ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
 static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged) {
+    // Cin here = the contraction depth per tap (3 * Cin in split mode)
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
     for (int BF = 2; BF <= F && BF <= 256; BF += 2) {
@@ -633,19 +645,21 @@ static bool conv_key_eq(const ConvKey& a, const ConvKey& b) { return memcmp(&a, 
 
 // The dynamic shared memory limit of a kernel variant is raised once per device (to the architectural 227 KB).
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvParams);
-// variant = pair * 3 + {0: forward bf16 out, 1: input-gradient pass (bf16), 2: forward fp16 out}
+// variant = pair * 4 + {0: forward bf16 out, 1: input-gradient pass (bf16), 2: forward fp16 out, 3: forward split-bf16 out}
 static ConvKernelFn conv_kernel_variant(int variant) {
     switch (variant) {
         case 0: return conv3x3_igemm_kernel<false, false, 1>;
         case 1: return conv3x3_igemm_kernel<false, true, 1>;
         case 2: return conv3x3_igemm_kernel<false, false, 2>;
-        case 3: return conv3x3_igemm_kernel<true, false, 1>;
-        case 4: return conv3x3_igemm_kernel<true, true, 1>;
-        default: return conv3x3_igemm_kernel<true, false, 2>;
+        case 3: return conv3x3_igemm_kernel<false, false, 3>;
+        case 4: return conv3x3_igemm_kernel<true, false, 1>;
+        case 5: return conv3x3_igemm_kernel<true, true, 1>;
+        case 6: return conv3x3_igemm_kernel<true, false, 2>;
+        default: return conv3x3_igemm_kernel<true, false, 3>;
     }
 }
 static int conv_raise_smem(int variant, int dev) {
-    static bool done[6][64] = {};
+    static bool done[8][64] = {};
     if (dev >= 0 && dev < 64 && done[variant][dev]) return 0;
     const int kMax = 227 * 1024;
     cudaError_t e = cudaFuncSetAttribute(conv_kernel_variant(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
@@ -671,8 +685,11 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     if (k.env_pair >= 0) pair = k.env_pair;
     if (!reuse || cout_pad % (2 * kConvTileM) != 0) pair = 0;
     const int sms = sm_count();
-    ConvPlan pl = conv_plan(B, T, F, Cin, Cout, pool, reuse ? 2 : 0, pair != 0, sms, k.ragged != 0);
-    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Cin, Cout, pool, 2, false, sms, k.ragged != 0); }
+    const bool x3 = (flags & 64) != 0;                           // split operands (fp32x3 mode)
+    const int Kc = x3 ? 3 * Cin : Cin;                           // contraction depth per tap
+    const int Cx = x3 ? 2 * Cin : Cin;                           // channels of the x tensor
+    ConvPlan pl = conv_plan(B, T, F, Kc, Cout, pool, reuse ? 2 : 0, pair != 0, sms, k.ragged != 0);
+    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Kc, Cout, pool, 2, false, sms, k.ragged != 0); }
     if (k.env_plan[0]) {                                         // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
         int bf = 0, bt = 0, bb = 0;
         if (sscanf(k.env_plan, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
@@ -688,8 +705,8 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     const int box_b = pair ? 1 : pl.BB;
 
     {
-        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(9) * Cin, static_cast<cuuint64_t>(cout_pad)};
-        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(9) * Cin * 2};
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(9) * Kc, static_cast<cuuint64_t>(cout_pad)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(9) * Kc * 2};
         const cuuint32_t box[2] = {kConvKC, kConvTileM};
         const cuuint32_t es[2] = {1, 1};
         CUresult r = encode(&en.tmA, (flags & 16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
@@ -698,10 +715,10 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
         if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: weight tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
     }
     {
-        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(F), static_cast<cuuint64_t>(T),
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cx), static_cast<cuuint64_t>(F), static_cast<cuuint64_t>(T),
                                     static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cin) * 2, static_cast<cuuint64_t>(F) * Cin * 2,
-                                       static_cast<cuuint64_t>(T) * F * Cin * 2};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cx) * 2, static_cast<cuuint64_t>(F) * Cx * 2,
+                                       static_cast<cuuint64_t>(T) * F * Cx * 2};
         const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(box_t),
                                    static_cast<cuuint32_t>(box_b)};
         const cuuint32_t es[4] = {1, 1, 1, 1};
@@ -715,7 +732,9 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     p.B = B; p.T = T; p.F = F; p.Cin = Cin; p.Cout = Cout;
     p.BF = pl.BF; p.BT = pl.BT; p.BB = pl.BB; p.N = pl.N; p.Npad = pl.Npad;
     p.n_ft = F / pl.BF; p.n_tt = (T + pl.BT - 1) / pl.BT; p.n_bt = (B + pl.BB - 1) / pl.BB; p.n_mt = cout_pad / kConvTileM;
-    p.kchunks = Cin / kConvKC;
+    p.kchunks = Kc / kConvKC;
+    p.a_tap_stride = Kc;
+    p.kcx_wrap = x3 ? 2 * Cin / kConvKC : 0x7fffffff;
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (k.y_dtype == 0);
     p.relu = (flags & 1) ? 1 : 0;
     p.w_f16 = (flags & 16) ? 1 : 0; p.x_f16 = (flags & 32) ? 1 : 0;
@@ -778,6 +797,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     if (((flags & 16) != 0) != ((flags & 32) != 0)) {            // measured on B200: a mixed pair faults (illegal instruction)
         set_error("conv3x3_igemm_bf16: tcgen05 kind::f16 needs both operands in the same format (set both or neither of DASV_CONV_W_F16, DASV_CONV_X_F16)"); return 1;
     }
+    if ((flags & 64) && ((flags & 48) || !(flags & 1))) { set_error("conv3x3_igemm_bf16: the split (fp32x3) mode is bf16, forward only"); return 1; }
     if (!(flags & 1) && (flags & 48)) { set_error("conv3x3_igemm_bf16: the input-gradient pass is bf16 only"); return 1; }
     if (B <= 0 || T <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15)) {
@@ -818,7 +838,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     }
     p.bias = bias; p.lengths = lengths; p.y = y; p.mask = mask;
 
-    const int variant = (pair ? 3 : 0) + (p.relu ? (act == 2 ? 2 : 0) : 1);
+    const int variant = (pair ? 4 : 0) + (p.relu ? ((flags & 64) ? 3 : (act == 2 ? 2 : 0)) : 1);
     if (conv_raise_smem(variant, k.dev)) return 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));

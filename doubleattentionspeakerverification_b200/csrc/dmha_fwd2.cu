@@ -14,6 +14,12 @@
 //     per-stage descriptor (utterance, first frame, frame count, last-stage flag) written before the stage's mbarrier
 //     is armed.  With ragged lengths this removes the makespan penalty of a static round-robin deal (a CTA that drew
 //     two long utterances no longer decides the kernel time).  Without a workspace the deal is static.
+//   * Tried and dropped (round 2): a tenth warp that runs the whole end-of-utterance stage while the consumers move on
+//     (partials handed over through a pair of mbarriers, lanes mapped (head, part of dh) so that no shuffle sits in the
+//     merge loop): bit-identical, but slower -- bf16 full 43.3 -> 46.7 us, ragged sorted 35.1 -> 41.3 us: one warp takes
+//     2-3 us for what eight warps do in well under 1 us, and that latency lands on the end of every CTA's last utterance,
+//     which is where this kernel loses its time (B=2960 utterances: 0.92 of the HBM peak for bf16, 1.07 of the copy figure
+//     for fp32; B=512: a fixed ~10 us of launch, ramp and tail on top of 33 us of streaming).
 //   * Tried and dropped: cutting the flattened (utterance, frame) stream into equal per-CTA ranges with partial
 //     states + tickets in the workspace (bit-exact, but the per-segment finish -- partial write, fence, ticket, merge,
 //     ~3-4 us -- cost more than the 13 % tail it removed: fp32 83.8 us vs 76.1 us at B=512,T=200,D=1024,H=16).
@@ -120,10 +126,13 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
     }
     __syncthreads();
     if (tid == 0) griddep_launch();
-    griddep_wait();                 // programmatic dependent launch: x, the deal counter and the outputs' memory belong to earlier kernels
+    // Programmatic dependent launch: x, the deal counter and the memory behind the outputs belong to earlier kernels of the
+    // stream.  The producer waits for them before its first claim; the consumers first stage the query and att (module
+    // parameters, never written by a kernel that lets its dependents start early) and wait afterwards.
 
     if (warp == kDmhaConsumerWarps) {
         if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
+            griddep_wait();
             int st = 0;
             uint32_t ph = 0;
             int b = p.ws_cnt ? atomicAdd(p.ws_cnt, 1) : static_cast<int>(blockIdx.x);
@@ -164,6 +173,7 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
     if (p.att != nullptr)
         for (int i = tid; i < dh; i += kDmhaConsumerThreads) a_sm[i] = p.att[i];
     named_bar_sync(1, kDmhaConsumerThreads);
+    griddep_wait();
 
     const int grp = warp * RPW + lane / G, lig = lane % G;
     const int head = grp % H, slot = grp / H;       // this group's head and frame slot (frames f = slot mod S)

@@ -7,7 +7,8 @@ import torch
 from . import _lib
 
 F32, BF16, F16 = 0, 1, 2
-CONV_RELU, CONV_POOL, CONV_REF_LAYOUT, CONV_PAIR, CONV_W_F16, CONV_X_F16 = 1, 2, 4, 8, 16, 32
+CONV_RELU, CONV_POOL, CONV_REF_LAYOUT, CONV_PAIR, CONV_W_F16, CONV_X_F16, CONV_X3 = 1, 2, 4, 8, 16, 32, 64
+SPLIT_BF16 = 3
 
 
 def _dev(t, name):
@@ -160,18 +161,30 @@ def pack_conv_weight_bf16(w, dtype=torch.bfloat16):
     return p
 
 
-def conv11_direct(x, w, bias, lengths=None, out_dtype=torch.float32):
-    """x [B,T,F] f32 -> relu(conv3x3(x) + bias) as NHWC [B,T,F,Cout]."""
+def conv11_direct(x, w, bias, lengths=None, out_dtype=torch.float32, split=False):
+    """x [B,T,F] f32 -> relu(conv3x3(x) + bias) as NHWC [B,T,F,Cout]; ``split=True``: [B,T,F,2*Cout] bf16 holding every fp32
+    value as hi = bf16(v) (channel c) and lo = bf16(v - hi) (channel Cout + c), the activation format of the fp32x3 mode."""
     x = _f32(x, 'x')
     B, T, Fq = x.shape
     w, bias = _f32(w, 'w'), _f32(bias, 'bias')
     Cout = w.shape[0]
     with torch.cuda.device(x.device):
         lengths = _lengths(lengths, B, x.device)
-        y = torch.empty((B, T, Fq, Cout), device=x.device, dtype=out_dtype)
-        rc = _lib.lib().dasv_conv11_direct(_p(x), _p(w), _p(bias), _p(lengths), _p(y), _dtype_code(y, 'y'), B, T, Fq, Cout, _stream())
+        y = torch.empty((B, T, Fq, 2 * Cout if split else Cout), device=x.device, dtype=torch.bfloat16 if split else out_dtype)
+        rc = _lib.lib().dasv_conv11_direct(_p(x), _p(w), _p(bias), _p(lengths), _p(y), SPLIT_BF16 if split else _dtype_code(y, 'y'), B, T, Fq, Cout, _stream())
         _lib.check(rc, 'dasv_conv11_direct')
     return y
+
+
+def pack_conv_weight_x3(w):
+    """w [Cout,Cin,3,3] f32 -> [Cout_pad][9][3*Cin] bf16 = per tap [hi | hi | lo]: the A operand of the fp32x3 mode."""
+    w = _f32(w, 'w')
+    Cout, Cin = w.shape[0], w.shape[1]
+    with torch.cuda.device(w.device):
+        n = 3 * int(_lib.lib().dasv_packed_conv_weight_bf16_elems(Cout, Cin))
+        p = torch.empty((n,), device=w.device, dtype=torch.bfloat16)
+        _lib.check(_lib.lib().dasv_pack_conv_weight_x3(_p(w), _p(p), Cout, Cin, _stream()), 'dasv_pack_conv_weight_x3')
+    return p
 
 
 def conv11_tc(x, w, bias, lengths=None):
@@ -216,7 +229,7 @@ def maxpool2x2(x, ref_layout=False, out_dtype=None):
     return y
 
 
-def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False, relu=True):
+def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False, relu=True, x3=False):
     """tcgen05 implicit-GEMM conv3x3 + bias + ReLU (+ fused 2x2 ceil max-pool) on NHWC 16-bit activations (bf16 or fp16; the
     output has the input's format) with bf16 or fp16 packed weights, fp32 accumulation."""
     _dev(x, 'x')
@@ -226,15 +239,20 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
     B, T, Fq, Cin = x.shape
     flags = (CONV_RELU if relu else 0) | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0) | (CONV_PAIR if pair else 0)
     flags |= (CONV_W_F16 if wp.dtype == torch.float16 else 0) | (CONV_X_F16 if x.dtype == torch.float16 else 0)
+    if x3:                                                   # fp32x3 mode: x is [hi | lo] split bf16 (2 * Cin channels), so is an NHWC y
+        if x.dtype != torch.bfloat16 or Cin % 2:
+            raise _lib.DasvError('conv3x3_igemm_bf16: the fp32x3 mode takes split bf16 activations')
+        flags |= CONV_X3
+        Cin //= 2
     with torch.cuda.device(x.device):
         lengths = _lengths(lengths, B, x.device)
         if pool:
             if Fq % 2:
                 raise _lib.DasvError('conv3x3_igemm_bf16: the pooled epilogue needs an even number of bins (F=%d)' % Fq)
             T2, F2 = (T + 1) // 2, Fq // 2
-            shape = (B, T2, Cout * F2) if ref_layout else (B, T2, F2, Cout)
+            shape = (B, T2, Cout * F2) if ref_layout else (B, T2, F2, 2 * Cout if x3 else Cout)
         else:
-            shape = (B, T, Fq, Cout)
+            shape = (B, T, Fq, 2 * Cout if x3 else Cout)
         if ref_layout and out_dtype != torch.float32:
             out_dtype = x.dtype
         y = torch.empty(shape, device=x.device, dtype=out_dtype if ref_layout else x.dtype)

@@ -28,6 +28,7 @@ extern "C" {
 #define DASV_F32 0
 #define DASV_BF16 1
 #define DASV_F16 2
+#define DASV_SPLIT_BF16 3            /* conv11 output only: [hi(C) | lo(C)] bf16 pairs of fp32 values (fp32x3 mode) */
 
 /* conv flags */
 #define DASV_CONV_RELU 1        /* apply ReLU after bias (set by the VGG blocks; clear = linear, for the input-gradient pass, no POOL) */
@@ -36,6 +37,7 @@ extern "C" {
 #define DASV_CONV_PAIR 8        /* run on CTA pairs (tcgen05 cta_group::2, 256 channels x N pixels per pair); same results */
 #define DASV_CONV_W_F16 16      /* wp was packed as fp16 (dasv_pack_conv_weight_16 with DASV_F16) */
 #define DASV_CONV_X_F16 32      /* x (and an NHWC y) are fp16 instead of bf16; fp16 stores saturate at +-65504 */
+#define DASV_CONV_X3 64         /* fp32x3 mode: x is [B,T,F,2*Cin] split bf16, wp from dasv_pack_conv_weight_x3, an NHWC y is [..,2*Cout] split bf16 */
 
 int dasv_abi_version(void);
 const char* dasv_last_error(void);
@@ -114,6 +116,12 @@ int dasv_pack_conv_weight_bf16(const float* w, void* packed, int Cout, int Cin, 
 /* The same packing with the 16-bit format chosen: dtype DASV_BF16 or DASV_F16 (three more mantissa bits; weights sit far
  * inside fp16's range).  Pass DASV_CONV_W_F16 to the convolution for fp16-packed weights. */
 int dasv_pack_conv_weight_16(const float* w, void* packed, int Cout, int Cin, int dtype, void* stream);
+/* fp32-parity mode on the tensor cores ("fp32x3"): an fp32 value v travels as two bf16 numbers hi = bf16(v),
+ * lo = bf16(v - hi); w*x ~= hi(w)hi(x) + hi(w)lo(x) + lo(w)hi(x) with fp32 accumulation (error ~2^-16 per product).
+ * Weights: [Cout_pad][9][3*Cin] bf16 = per tap [hi | hi | lo] (3x dasv_packed_conv_weight_bf16_elems elements).
+ * Activations: NHWC with 2*C channels [hi(C) | lo(C)] (dasv_conv11_direct with y_dtype DASV_SPLIT_BF16, and the
+ * NHWC output of dasv_conv3x3_igemm_bf16 with DASV_CONV_X3).  Three MMAs per product: a third of the bf16 rate. */
+int dasv_pack_conv_weight_x3(const float* w, void* packed, int Cout, int Cin, void* stream);
 
 /* fp32 CUDA-core implicit-GEMM conv3x3 + bias + ReLU (+ row mask): the fp32-parity path
  * (1e-4 relative) for conv12..conv42 (CNNs.py:73-85).  x [B,T,F,Cin] f32, wp packed f32,

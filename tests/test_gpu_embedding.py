@@ -63,6 +63,21 @@ def test_embedding_bf16(name):
         assert abs(float(s[0]) - float(s_ref[0])) < 1e-3             # north_star trial-score bar
 
 
+@pytest.mark.parametrize('name', ['k512', 'example', 'example_b2'])
+def test_embedding_fp32x3(name):
+    """precision='fp32x3': the north_star fp32 bar (1e-4) on the tensor cores (bf16 hi/lo operands, three MMAs per product)."""
+    g = golden('embed_%s.npz' % name)
+    net, x = build(g, 'fp32x3')
+    with torch.no_grad():
+        emb = net.getEmbedding(dev(x))
+    report('embedding_fp32x3[%s]' % name, max_rel=max_rel(emb.cpu().numpy(), g['emb']))
+    assert max_rel(emb.cpu().numpy(), g['emb']) < 1e-4
+    if 'emb_varlen' in g.files:
+        with torch.no_grad():
+            ev = net.getEmbedding(dev(x), lengths=dev(g['lengths']))
+        assert max_rel(ev.cpu().numpy(), g['emb_varlen']) < 1e-4
+
+
 def test_embedding_fp16_operands(precision='fp16'):
     """precision='fp16' (fp16 activations and weights on the same kernels) on the exampleModel fixtures."""
     for name in ('example', 'example_b2'):
@@ -186,7 +201,7 @@ def _ragged():
     return g, feats, wseed
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'fp32x3', 'bf16'])
 def test_variable_length_extraction_and_trials(precision):
     """configs[3]/[4] at reduced scale: ten 2-20 s utterances (T = 456 ... 1938, T' up to 122) through the bucketed, padded +
     masked extractor (host-padded list AND device-packed path) against the LIVE REFERENCE run per utterance at batch 1
@@ -207,7 +222,7 @@ def test_variable_length_extraction_and_trials(precision):
     for tag, got in (('list', emb), ('packed', emb_packed), ('batch1', single)):
         got = got.cpu().numpy()
         report('ragged[%s,%s]' % (precision, tag), max_rel=max_rel(got, want), min_cos=min_cosine(got, want))
-        if precision == 'fp32':
+        if precision in ('fp32', 'fp32x3'):
             assert max_rel(got, want) < 1e-4
         else:
             assert min_cosine(got, want) >= 0.9999

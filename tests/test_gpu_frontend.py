@@ -147,6 +147,51 @@ def test_igemm_operand_formats(xdt, wdt, B, T, F, Cin, Cout, pool, ref, pair):
     assert max_rel(y.float().cpu().numpy(), ref_y) < tol
 
 
+@pytest.mark.parametrize('B,T,F,Cin,Cout,pool,ref,pair', [(2, 21, 40, 128, 128, True, False, False), (3, 13, 20, 128, 256, False, False, True),
+                                                         (3, 26, 10, 512, 512, True, True, True), (2, 9, 10, 64, 136, True, True, False),
+                                                         (2, 12, 20, 256, 256, True, False, True)])
+def test_igemm_fp32x3_vs_oracle(B, T, F, Cin, Cout, pool, ref, pair):
+    """fp32x3 mode: arbitrary fp32 activations and weights as bf16 hi/lo pairs, three MMAs per product, against the fp32
+    oracle: 3e-5 (the dropped lo*lo term and the pairs' own rounding are ~2^-16 per product).  NHWC outputs come back split."""
+    rs = np.random.RandomState(17 + B + Cin)
+    x = np.maximum(rs.standard_normal((B, T, F, Cin)), 0).astype(np.float32)
+    w = (rs.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    bias = (rs.standard_normal((Cout,)) * 0.1).astype(np.float32)
+    lengths = rs.randint(1, T + 1, size=(B,)).astype(np.int32)
+    lengths[0] = T
+    x = po._zero_rows(x, lengths)
+    ref_y = po._zero_rows(po.relu(po.conv3x3_same(x, w, bias)), lengths)
+    if pool:
+        ref_y = po.maxpool2x2_ceil(ref_y)
+        if ref:
+            Bq, T2, F2, C = ref_y.shape
+            ref_y = ref_y.transpose(0, 1, 3, 2).reshape(Bq, T2, C * F2)
+    xt = dev(x)
+    hi = xt.to(torch.bfloat16)
+    xs = torch.cat([hi, (xt - hi.float()).to(torch.bfloat16)], dim=-1).contiguous()
+    y = ops.conv3x3_igemm_bf16(xs, ops.pack_conv_weight_x3(dev(w)), dev(bias), Cout, lengths=dev(lengths), pool=pool, ref_layout=ref,
+                               out_dtype=torch.float32, pair=pair, x3=True)
+    if not ref:
+        assert y.dtype == torch.bfloat16 and y.shape[-1] == 2 * Cout
+        y = y[..., :Cout].float() + y[..., Cout:].float()
+    assert tuple(y.shape) == ref_y.shape
+    assert max_rel(y.cpu().numpy(), ref_y) < 3e-5
+
+
+def test_conv11_split_output():
+    rs = np.random.RandomState(6)
+    x = (2 * rs.standard_normal((2, 9, 80))).astype(np.float32)
+    w = rs.standard_normal((16, 1, 3, 3)).astype(np.float32)
+    b = rs.standard_normal((16,)).astype(np.float32)
+    L = np.array([9, 4], np.int32)
+    want = ops.conv11_direct(dev(x), dev(w), dev(b), dev(L))
+    y = ops.conv11_direct(dev(x), dev(w), dev(b), dev(L), split=True)
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (2, 9, 80, 32)
+    got = y[..., :16].float() + y[..., 16:].float()
+    assert float((got - want).abs().max()) <= 2 ** -15 * float(want.abs().max())
+    assert torch.equal(y[..., :16], want.to(torch.bfloat16))
+
+
 def test_fp16_store_saturates():
     """fp16 activations saturate at the largest finite value instead of overflowing to infinity."""
     x = torch.full((1, 4, 80), 3.0e4, device='cuda')
