@@ -306,13 +306,24 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 bool tile_masked;
                 const ConvTile c = conv_tile_at(p, sched, tile, 0, n_mt_eff, static_cast<int>(rank), tile_masked);
                 if (tile_masked) continue;
-                const uint32_t as = acc_it & 1u, accph = (acc_it >> 1) & 1u;
+                // split mode: the two accumulators of a tile fill TMEM (2 x 256 columns), so tiles are not double-buffered there
+                const uint32_t as = ACT == 3 ? 0u : (acc_it & 1u), accph = ACT == 3 ? (acc_it & 1u) : ((acc_it >> 1) & 1u);
                 mbar_wait(&acc_empty[as], accph ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * static_cast<uint32_t>(p.Npad);
+                // Split (fp32x3) mode keeps TWO accumulators per tile: [0] the hi*hi products, [1] the two cross terms, which are
+                // 2^-8 smaller.  The tensor core adds into its fp32 accumulator with truncation, a bias of up to one ulp OF THE
+                // ACCUMULATOR per MMA; with the cross terms elsewhere the large accumulator sees a third of the additions and the
+                // small one's ulps are negligible (measured: embeddings 1.4e-4 -> within the 1e-4 bar).  Summed in the epilogue.
+                constexpr bool X3 = ACT == 3;
+                const uint32_t d_tmem0 = tmem_base + as * static_cast<uint32_t>(p.Npad);
+                const int n_hi = p.kcx_wrap >> 1;                       // split mode: K slices [0, n_hi) are hi*hi
+                uint32_t firstj[2] = {1u, 1u};
                 if (p.reuse) {
-                    uint32_t first = 1u;
                     for (int g = 0; g < 3 * p.kchunks; ++g) {           // (slice, dx) groups
+                        const uint32_t jacc = (X3 && g / 3 >= n_hi) ? 1u : 0u;
+                        const uint32_t d_tmem = d_tmem0 + jacc * static_cast<uint32_t>(p.Npad);
+                        uint32_t first = firstj[jacc];
+                        firstj[jacc] = 0u;
                         mbar_wait(&full[st], ph);
                         const uint32_t b_addr = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
                         for (int dyi = 0; dyi < 3; ++dyi) {
@@ -339,6 +350,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 } else {
                     for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t jacc = (X3 && ks % p.kchunks >= n_hi) ? 1u : 0u;
+                        const uint32_t d_tmem = d_tmem0 + jacc * static_cast<uint32_t>(p.Npad);
+                        const uint32_t first = firstj[jacc];
+                        firstj[jacc] = 0u;
                         mbar_wait(&full[st], ph);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(st) * p.stage_bytes);
@@ -347,7 +362,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                         for (int k = 0; k < kConvKC / 16; ++k)     // +32 B per 16-element K step inside the swizzle atom
                             umma_bf16(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
-                                      (ks | k) != 0 ? 1u : 0u);
+                                      (first && k == 0) ? 0u : 1u);
                         umma_commit(&empty[st]);                   // frees the ring slot when these MMAs retire
                         if (++st == static_cast<uint32_t>(p.stages)) { st = 0; ph ^= 1u; }
                     }
@@ -386,7 +401,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int ot0 = p.pool ? (c.t0 >> 1) : c.t0, of0 = p.pool ? (c.f0 >> 1) : c.f0;
             uint32_t tcol = 0;
             if (!masked) {
-                const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                const uint32_t as = ACT == 3 ? 0u : (acc_it & 1u), aph = ACT == 3 ? (acc_it & 1u) : ((acc_it >> 1) & 1u);
                 mbar_wait(&acc_full[as], aph);
                 tc_fence_after();
                 tcol = tmem_base + lane_addr + as * static_cast<uint32_t>(p.Npad);
@@ -406,15 +421,25 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const size_t row = (static_cast<size_t>(b) * T2 + (t >> 1)) * (static_cast<size_t>(Cout) * F2) +
                                        static_cast<size_t>(n) * F2 + (c.f0 >> 1);
                     for (int fp0 = 0; fp0 < BF / 2; fp0 += 4) {
-                        uint32_t v[4][4];
+                        uint32_t v[4][4], v2[ACT == 3 ? 4 : 1][4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             if (!masked && fp0 + u < BF / 2) {  // warp-uniform
                                 tmem_ld_x2(col0 + 2 * (fp0 + u), v[u][0], v[u][1]);
                                 tmem_ld_x2(col0 + BF + 2 * (fp0 + u), v[u][2], v[u][3]);
+                                if (ACT == 3) {                 // split mode: the cross-term accumulator
+                                    tmem_ld_x2(col0 + p.Npad + 2 * (fp0 + u), v2[ACT == 3 ? u : 0][0], v2[ACT == 3 ? u : 0][1]);
+                                    tmem_ld_x2(col0 + p.Npad + BF + 2 * (fp0 + u), v2[ACT == 3 ? u : 0][2], v2[ACT == 3 ? u : 0][3]);
+                                }
                             }
                         }
                         if (!masked) tc_wait_ld();
+                        if (ACT == 3 && !masked) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) v[u][e] = __float_as_uint(__uint_as_float(v[u][e]) + __uint_as_float(v2[ACT == 3 ? u : 0][e]));
+                        }
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             if (fp0 + u < BF / 2 && n_ok) {
@@ -432,7 +457,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (!masked) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&acc_empty[acc_it & 1u], 0); else mbar_arrive(&acc_empty[acc_it & 1u]); }
+                    if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&acc_empty[ACT == 3 ? 0u : (acc_it & 1u)], 0); else mbar_arrive(&acc_empty[ACT == 3 ? 0u : (acc_it & 1u)]); }
                     ++acc_it;
                 }
                 continue;
@@ -473,6 +498,21 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                         tmem_ld_x1(tcol + min(oa + j + bbj * p.gap_cols, p.Npad - 1), r[j]);
                                     }
                                 }
+                                if (ACT == 3) {                 // split mode: add the cross-term accumulator
+                                    uint32_t r2[16];
+                                    if (bba == bbz && cola + 16 <= p.Npad) {
+                                        tmem_ld_x16(tcol + p.Npad + cola, r2);
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 16; ++j) {
+                                            const int bbj = __float2int_rz((static_cast<float>(min(oa + j, NO - 1)) + 0.5f) * inv_opp);
+                                            tmem_ld_x1(tcol + p.Npad + min(oa + j + bbj * p.gap_cols, p.Npad - 1), r2[j]);
+                                        }
+                                    }
+                                    tc_wait_ld();
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                                }
                                 tc_wait_ld();
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
@@ -487,7 +527,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         int tp = __float2int_rz((static_cast<float>(rem) + 0.5f) * inv_obf), fp = rem - tp * OBF;
                         int Lcur = conv_len(p, c.b0 + bb);
                         for (int j0 = 0; j0 < cnt; j0 += 4) {
-                            uint32_t v[4][4];
+                            uint32_t v[4][4], v2[ACT == 3 ? 4 : 1][4];
                             bool r1[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -496,10 +536,21 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                     r1[u] = (c.t0 + 2 * tp + 1) < Lcur;     // ceil-mode / masked second row
                                     tmem_ld_x2(col, v[u][0], v[u][1]);
                                     tmem_ld_x2(col + BF, v[u][2], v[u][3]);
+                                    if (ACT == 3) {             // split mode: the cross-term accumulator
+                                        tmem_ld_x2(col + p.Npad, v2[ACT == 3 ? u : 0][0], v2[ACT == 3 ? u : 0][1]);
+                                        tmem_ld_x2(col + p.Npad + BF, v2[ACT == 3 ? u : 0][2], v2[ACT == 3 ? u : 0][3]);
+                                    }
                                     if (++fp == OBF) { fp = 0; if (++tp == OBT) { tp = 0; ++bb; Lcur = conv_len(p, c.b0 + bb); } }
                                 }
                             }
                             tc_wait_ld();
+                            if (ACT == 3) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    if (j0 + u < cnt)
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) v[u][e] = __float_as_uint(__uint_as_float(v[u][e]) + __uint_as_float(v2[ACT == 3 ? u : 0][e]));
+                            }
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (j0 + u < cnt) {
@@ -546,7 +597,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (!masked) {                                      // all of this warp's TMEM reads of the tile are done
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&acc_empty[acc_it & 1u], 0); else mbar_arrive(&acc_empty[acc_it & 1u]); }
+                if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&acc_empty[ACT == 3 ? 0u : (acc_it & 1u)], 0); else mbar_arrive(&acc_empty[ACT == 3 ? 0u : (acc_it & 1u)]); }
                 ++acc_it;
             }
         }
@@ -570,7 +621,7 @@ struct ConvPlan {
 // MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
 // ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
-static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged) {
+static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged, int nmax = 256) {
     // Cin here = the contraction depth per tap (3 * Cin in split mode)
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
@@ -594,7 +645,7 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int
                     b_rows = (RT + 2.0) * BF / 3.0;
                 }
                 const int Npad = (N + 15) / 16 * 16;
-                if (Npad > 256) continue;
+                if (Npad > nmax) continue;                   // 2 (double buffer) x accumulators per tile x Npad <= 512 TMEM columns
                 // tiles are dealt to the SMs (or SM pairs) in whole waves: with few tiles (small batches) a smaller patch
                 // that fills more SMs wins even though each of its MMAs is less efficient
                 const int n_mt = (Cout + kConvTileM - 1) / kConvTileM;
@@ -688,15 +739,16 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     const bool x3 = (flags & 64) != 0;                           // split operands (fp32x3 mode)
     const int Kc = x3 ? 3 * Cin : Cin;                           // contraction depth per tap
     const int Cx = x3 ? 2 * Cin : Cin;                           // channels of the x tensor
-    ConvPlan pl = conv_plan(B, T, F, Kc, Cout, pool, reuse ? 2 : 0, pair != 0, sms, k.ragged != 0);
-    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Kc, Cout, pool, 2, false, sms, k.ragged != 0); }
+    const int nmax = 256;                                        // split mode: two accumulators per tile, tiles not double-buffered
+    ConvPlan pl = conv_plan(B, T, F, Kc, Cout, pool, reuse ? 2 : 0, pair != 0, sms, k.ragged != 0, nmax);
+    if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Kc, Cout, pool, 2, false, sms, k.ragged != 0, nmax); }
     if (k.env_plan[0]) {                                         // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
         int bf = 0, bt = 0, bb = 0;
         if (sscanf(k.env_plan, "%d,%d,%d", &bf, &bt, &bb) == 3 && bf > 0 && F % bf == 0 && bf % 2 == 0 && bt > 0 && (!pool || bt % 2 == 0) && bb > 0) {
             int n = (bb - 1) * (bt + (reuse ? 2 : 0)) * bf + bt * bf;
             bool ok = true;
             if (pair) { ok = (bb == 1 && bt % 2 == 0 && (bt * bf) % 16 == 0) || bb == 2; n = bb == 1 ? bt * bf : 2 * ((bt * bf + 7) / 8 * 8); }
-            if (ok && (n + 15) / 16 * 16 <= 256) pl = ConvPlan{bf, bt, bb, n, (n + 15) / 16 * 16, 0.0};
+            if (ok && (n + 15) / 16 * 16 <= nmax) pl = ConvPlan{bf, bt, bb, n, (n + 15) / 16 * 16, 0.0};
         }
     }
     if (pl.N == 0) { set_error("conv3x3_igemm_bf16: no patch shape for T=%d F=%d", T, F); return 1; }
