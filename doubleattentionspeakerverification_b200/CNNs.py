@@ -62,6 +62,7 @@ class _VGG(nn.Module):
                 self._names.append(name)
                 cin = cout
         self.precision = precision
+        self.fuse_first = True          # conv11 inside conv12's kernel on the 16-bit inference paths
         self._packed = {}
 
     # ---------------------------------------------------------------- weight packing cache
@@ -163,9 +164,18 @@ class _VGG(nn.Module):
             act = torch.float16 if prec == 'fp16' else torch.bfloat16
             x3 = prec == 'fp32x3'
             wk = 'x3' if x3 else ('f16' if prec == 'fp16' else 'bf16')       # both MMA operands must have the same 16-bit format
-            # conv11 is bound by its NHWC 16-bit write (2.1 GB per 256 x 4 s batch at the 3.95 TB/s pure-write bandwidth)
-            h = ops.conv11_direct(x, c11.weight, c11.bias, L, out_dtype=act, split=x3)
-            for blk in range(nblocks):
+            # conv11's output (2.1 GB of bf16 per 256 x 4 s batch) never goes to HBM: conv12's kernel computes it per tile
+            # (ops.conv12_fused); the stand-alone kernel remains for the split (fp32x3) format and other channel counts
+            c12 = getattr(self, self._names[1])
+            fuse = self.fuse_first and not x3 and c11.out_channels in (64, 128) and x.size(2) % 2 == 0
+            if fuse:
+                h = ops.conv12_fused(x, c11.weight, c11.bias, self._pack(self._names[1], wk), c12.bias, c12.out_channels, L,
+                                     pool=True, act_dtype=act)
+                if L is not None:
+                    L = (L + 1) // 2
+            else:
+                h = ops.conv11_direct(x, c11.weight, c11.bias, L, out_dtype=act, split=x3)
+            for blk in range(1 if fuse else 0, nblocks):
                 if blk > 0:
                     c = getattr(self, self._names[2 * blk])
                     h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk], wk), c.bias, c.out_channels, L, x3=x3)

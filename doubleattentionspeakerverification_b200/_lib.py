@@ -31,6 +31,8 @@ SIGNATURES = {
     'dasv_conv3x3_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_maxpool2x2': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_igemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasv_conv12_fused_workspace_bytes': (_sz, [_i]),
+    'dasv_conv12_fused_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_wgrad_workspace_bytes': (_sz, [_i, _i, _i, _i, _i]),
     'dasv_conv3x3_wgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -26,6 +26,7 @@
 namespace dasv {
 
 constexpr int kConvThreads = 384;              // 4 role warps + 8 epilogue warps
+constexpr int kConvFuseThreads = 128;          // fused first layer: 4 more warps compute conv11 patches
 constexpr int kConvTileM = 128;                 // output channels per CTA tile = TMEM lanes
 constexpr int kConvKC = 64;                     // channels per K slice (64 bf16 = one 128-byte swizzle row)
 constexpr uint32_t kConvABytes = kConvTileM * kConvKC * 2;
@@ -56,6 +57,13 @@ struct ConvParams {
     int sa;                  // reuse mode: stages of the separate A (weight tile) ring
     int pair;                // 1: CTA pairs (cta_group::2): 256 channels x N pixels per pair, each CTA loads half of the patch
     int w_f16, x_f16;        // operand formats of the MMA: weights / activations are fp16 (else bf16)
+    // fused first layer (FUSE11 kernels): conv11 (1 -> Cin channels, scripts/CNNs.py:72) is computed by four extra warps
+    // into a per-CTA, double-buffered scratch patch in global memory (L2-resident) that the TMA producer reads instead of x
+    const float* x0;         // [B,T,F] f32 input of conv11
+    const float* w11;        // [Cin,1,3,3] f32
+    const float* b11;        // [Cin] f32
+    void* scratch;           // [grid][2][BT+2][BF+2][Cin] 16-bit
+    uint32_t fuse_off;       // byte offset of the fused path's shared memory (input patch + barriers) from the barrier block
     int balanced;            // ragged batches: tiles with valid frames are compacted through a per-CTA prefix table so that every
                              // CTA gets the same number of them (and of the all-masked tiles, which only store zeros)
     int RT;                  // pair mode: frames of the patch half one CTA loads (without halo)
@@ -167,8 +175,8 @@ DASV_DEVICE void conv_store(void* y, size_t idx, float v) {
 // ReLU-backward mask); a separate instantiation so that the forward's epilogue carries none of its branches.
 // ACT = format of a 16-bit output: 1 = bf16, 2 = fp16 (saturating), 3 = split bf16 (the fp32x3 mode: an fp32 value v is
 // stored as hi = bf16(v) in channel c and lo = bf16(v - hi) in channel Cout + c of a 2*Cout-channel tensor).
-template <bool PAIR, bool DGRAD = false, int ACT = 1>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <bool PAIR, bool DGRAD = false, int ACT = 1, bool FUSE11 = false>
+__global__ void __launch_bounds__(kConvThreads + (FUSE11 ? kConvFuseThreads : 0), 1)
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand.
@@ -185,6 +193,9 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t* acc_empty = acc_full + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     int* vpre = reinterpret_cast<int*>(tmem_slot + 4);     // [n_bt + 1], balanced mode only (the host sized the window for it)
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(full) + p.fuse_off);   // [2] FUSE11: scratch patch written
+    uint64_t* s_free = s_full + 2;                                                                          // [2] FUSE11: its MMAs have retired
+    float* x_sm = reinterpret_cast<float*>(s_free + 2);                                                    // FUSE11: [(BT+4)][(BF+4)] input patch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                  // 0 = leader of the CTA pair
@@ -198,6 +209,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < p.sa; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 16 : 8); }
+        if (FUSE11) for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 1); }
         fence_mbar_init();
     }
     if (threadIdx.x == 32) griddep_launch();   // the stream's next kernel may begin its own prologue (it waits for this grid below)
@@ -241,11 +253,13 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0 && p.reuse) {
             // tap-row reuse: per (64-channel slice, dx) ONE activation patch with a +-1 frame halo, then the three
             // weight tiles of that tap column (dy = -1, 0, +1); 3x less activation traffic than one box per tap.
-            uint32_t sb = 0, bph = 0, sa = 0, aph = 0;
+            uint32_t sb = 0, bph = 0, sa = 0, aph = 0, fit = 0;
             for (int tile = tile0; tile < sched.n_pass0; tile += tile_step) {
                 bool tile_masked;
                 const ConvTile c = conv_tile_at(p, sched, tile, 0, n_mt_eff, static_cast<int>(rank), tile_masked);
                 if (tile_masked) continue;
+                const int slot = static_cast<int>(blockIdx.x) * 2 + static_cast<int>(fit & 1u);    // FUSE11: this tile's scratch patch
+                if (FUSE11) { mbar_wait(&s_full[fit & 1u], (fit >> 1) & 1u); ++fit; }
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     const int kcx = kc >= p.kcx_wrap ? kc - p.kcx_wrap : kc;     // activation slice of this K slice
                     for (int dxi = 0; dxi < 3; ++dxi) {
@@ -259,7 +273,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             tma_load_4d_2sm(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kcx * kConvKC, c.f0 + dxi - 1, tq - 1, bq);
                         } else {
                             mbar_arrive_expect_tx(&full[sb], p.b_bytes);
-                            tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kcx * kConvKC, c.f0 + dxi - 1, c.t0 - 1, c.b0);
+                            if (FUSE11)      // the scratch patch holds frames t0-1 .. t0+BT and bins f0-1 .. f0+BF, zeros outside the image
+                                tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kcx * kConvKC, dxi, 0, slot);
+                            else
+                                tma_load_4d(ring + static_cast<size_t>(sb) * p.stage_bytes, &tmB, &full[sb], kcx * kConvKC, c.f0 + dxi - 1, c.t0 - 1, c.b0);
                         }
                         if (++sb == static_cast<uint32_t>(p.stages)) { sb = 0; bph ^= 1u; }
                         for (int dyi = 0; dyi < 3; ++dyi) {
@@ -368,8 +385,75 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 }
                 if (PAIR) umma_commit_2sm(&acc_full[as], 3); else umma_commit(&acc_full[as]);   // accumulator complete -> epilogue(s)
+                if (FUSE11) umma_commit(&s_free[acc_it & 1u]);      // ... and the tile's scratch patch may be overwritten
                 ++acc_it;
             }
+        }
+    } else if (FUSE11 && warp >= 12) {
+        // ------------------------------------------------------------ fused first layer: conv11 + bias + ReLU of the tile's
+        // haloed region, one tile ahead of the MMAs.  A thread owns 8 output channels (weights in registers, packed for
+        // fma.rn.f32x2) and every PL-th pixel; the arithmetic and its order are conv11_direct_kernel's, so the values are
+        // bit-identical to the unfused path.
+        const int tid11 = static_cast<int>(threadIdx.x) - kConvThreads;
+        const int C1 = p.Cin, CG = C1 / 8, PL = kConvFuseThreads / CG;
+        const int cg = tid11 % CG, pl = tid11 / CG;
+        const int PW = p.BF + 2, PH = p.BT + 2, XW = p.BF + 4, XH = p.BT + 4;
+        uint64_t wr2[9][4], br2[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            br2[e >> 1] = pack_f32x2(p.b11[cg * 8 + e], p.b11[cg * 8 + e + 1]);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap)
+                wr2[tap][e >> 1] = pack_f32x2(p.w11[(cg * 8 + e) * 9 + tap], p.w11[(cg * 8 + e + 1) * 9 + tap]);
+        }
+        uint32_t fit = 0;
+        for (int tile = tile0; tile < sched.n_pass0; tile += tile_step) {
+            bool tile_masked;
+            const ConvTile c = conv_tile_at(p, sched, tile, 0, n_mt_eff, static_cast<int>(rank), tile_masked);
+            if (tile_masked) continue;
+            const uint32_t buf = fit & 1u;
+            if (fit >= 2) mbar_wait(&s_free[buf], ((fit >> 1) - 1u) & 1u);      // the MMAs of the tile that used this patch are done
+            const int L = conv_len(p, c.b0);
+            named_bar_sync(3, kConvFuseThreads);                                 // everybody is done with the previous input patch
+            for (int i = tid11; i < XH * XW; i += kConvFuseThreads) {
+                const int r = i / XW, q = i - r * XW;
+                const int t = c.t0 - 2 + r, f = c.f0 - 2 + q;
+                x_sm[i] = (t >= 0 && t < L && f >= 0 && f < p.F) ? p.x0[(static_cast<size_t>(c.b0) * p.T + t) * p.F + f] : 0.f;
+            }
+            named_bar_sync(3, kConvFuseThreads);
+            uint16_t* sp = static_cast<uint16_t*>(p.scratch) + (static_cast<size_t>(blockIdx.x) * 2 + buf) * PH * PW * C1 + cg * 8;
+            for (int px = pl; px < PH * PW; px += PL) {
+                const int tt = px / PW, ff = px - tt * PW;
+                const int t = c.t0 - 1 + tt, f = c.f0 - 1 + ff;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (t >= 0 && t < L && f >= 0 && f < p.F) {                      // outside: conv12's zero padding / masked rows
+                    uint64_t acc[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[e] = br2[e];
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const float xv = x_sm[(tt + dy) * XW + ff + dx];
+                            const uint64_t x2 = pack_f32x2(xv, xv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[e] = fma_f32x2(x2, wr2[dy * 3 + dx][e], acc[e]);
+                        }
+                    float a[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) unpack_f32x2(acc[e], a[2 * e], a[2 * e + 1]);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], 0.f);
+                    constexpr int A16 = ACT == 2 ? 2 : 1;
+                    v = make_uint4(pack16<A16>(a[0], a[1]), pack16<A16>(a[2], a[3]), pack16<A16>(a[4], a[5]), pack16<A16>(a[6], a[7]));
+                }
+                *reinterpret_cast<uint4*>(sp + static_cast<size_t>(px) * C1) = v;
+            }
+            __threadfence();                                                     // the patch is in L2 ...
+            asm volatile("fence.proxy.async;" ::: "memory");                     // ... and ordered before the TMA (async proxy) reads of it
+            named_bar_sync(3, kConvFuseThreads);
+            if (tid11 == 0) mbar_arrive(&s_full[buf]);
+            ++fit;
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue (TMEM -> regs -> SMEM -> HBM)
@@ -621,7 +705,7 @@ struct ConvPlan {
 // MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
 // ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
-static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged, int nmax = 256) {
+static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged, int nmax = 256, int bbmax = 1 << 30) {
     // Cin here = the contraction depth per tap (3 * Cin in split mode)
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
@@ -632,7 +716,7 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int
             if (BT > T + 1 && BT > 2) break;
             const int n_tt = (T + BT - 1) / BT;
             const int bb_max = 256 / (BF * BT);          // several utterances per patch when one utterance's rows leave room
-            for (int BB = 1; BB <= bb_max && BB <= B; ++BB) {
+            for (int BB = 1; BB <= bb_max && BB <= B && BB <= bbmax; ++BB) {
                 int N = (BB - 1) * (BT + halo) * BF + BT * BF;            // accumulator columns incl. halo gaps
                 double b_rows = halo ? BB * (BT + 2.0) * BF / 3.0 : BB * BT * BF;   // activation rows fetched per tap (per CTA)
                 if (pair) {
@@ -706,11 +790,13 @@ static ConvKernelFn conv_kernel_variant(int variant) {
         case 4: return conv3x3_igemm_kernel<true, false, 1>;
         case 5: return conv3x3_igemm_kernel<true, true, 1>;
         case 6: return conv3x3_igemm_kernel<true, false, 2>;
-        default: return conv3x3_igemm_kernel<true, false, 3>;
+        case 7: return conv3x3_igemm_kernel<true, false, 3>;
+        case 8: return conv3x3_igemm_kernel<false, false, 1, true>;     // conv11 fused in front (bf16 / fp16 activations)
+        default: return conv3x3_igemm_kernel<false, false, 2, true>;
     }
 }
 static int conv_raise_smem(int variant, int dev) {
-    static bool done[8][64] = {};
+    static bool done[10][64] = {};
     if (dev >= 0 && dev < 64 && done[variant][dev]) return 0;
     const int kMax = 227 * 1024;
     cudaError_t e = cudaFuncSetAttribute(conv_kernel_variant(variant), cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
@@ -740,7 +826,9 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     const int Kc = x3 ? 3 * Cin : Cin;                           // contraction depth per tap
     const int Cx = x3 ? 2 * Cin : Cin;                           // channels of the x tensor
     const int nmax = 256;                                        // split mode: two accumulators per tile, tiles not double-buffered
-    ConvPlan pl = conv_plan(B, T, F, Kc, Cout, pool, reuse ? 2 : 0, pair != 0, sms, k.ragged != 0, nmax);
+    const bool fused = (flags & 128) != 0;                       // conv11 computed in front by the kernel itself: one utterance per patch
+    if (fused) pair = 0;
+    ConvPlan pl = conv_plan(B, T, F, Kc, Cout, pool, reuse ? 2 : 0, pair != 0, sms, k.ragged != 0, nmax, fused ? 1 : (1 << 30));
     if (pair && pl.N == 0) { pair = 0; pl = conv_plan(B, T, F, Kc, Cout, pool, 2, false, sms, k.ragged != 0, nmax); }
     if (k.env_plan[0]) {                                         // "BF,BT,BB" tuning override (scripts/bench_conv_layers.py)
         int bf = 0, bt = 0, bb = 0;
@@ -748,6 +836,7 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
             int n = (bb - 1) * (bt + (reuse ? 2 : 0)) * bf + bt * bf;
             bool ok = true;
             if (pair) { ok = (bb == 1 && bt % 2 == 0 && (bt * bf) % 16 == 0) || bb == 2; n = bb == 1 ? bt * bf : 2 * ((bt * bf + 7) / 8 * 8); }
+            if (fused && bb != 1) ok = false;
             if (ok && (n + 15) / 16 * 16 <= nmax) pl = ConvPlan{bf, bt, bb, n, (n + 15) / 16 * 16, 0.0};
         }
     }
@@ -767,10 +856,10 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
         if (r != CUDA_SUCCESS) { set_error("conv3x3_igemm_bf16: weight tensor map encode failed (%d)", static_cast<int>(r)); return 1; }
     }
     {
-        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cx), static_cast<cuuint64_t>(F), static_cast<cuuint64_t>(T),
-                                    static_cast<cuuint64_t>(B)};
-        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cx) * 2, static_cast<cuuint64_t>(F) * Cx * 2,
-                                       static_cast<cuuint64_t>(T) * F * Cx * 2};
+        // fused first layer: the "activation tensor" is the scratch, [slots][BT+2][BF+2][Cin] (k.x points at it)
+        const cuuint64_t dF = fused ? pl.BF + 2 : F, dT = fused ? pl.BT + 2 : T, dB = fused ? 2 * static_cast<cuuint64_t>(sms) : B;
+        const cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cx), dF, dT, dB};
+        const cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cx) * 2, dF * Cx * 2, dT * dF * Cx * 2};
         const cuuint32_t box[4] = {kConvKC, static_cast<cuuint32_t>(pl.BF), static_cast<cuuint32_t>(box_t),
                                    static_cast<cuuint32_t>(box_b)};
         const cuuint32_t es[4] = {1, 1, 1, 1};
@@ -795,8 +884,12 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
     p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;
     p.b_bytes = static_cast<uint32_t>(box_b) * box_t * pl.BF * 128u;
-    // staging + alignment slack + barriers (+ the valid-tile prefix table of a ragged batch)
-    const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512 + (p.balanced ? ((static_cast<uint32_t>(p.n_bt) + 1u) * 4u + 15u) / 16u * 16u : 0u);
+    // staging + alignment slack + barriers (+ the valid-tile prefix table of a ragged batch) (+ the fused first layer's
+    // barriers and input patch)
+    const uint32_t kTable = p.balanced ? ((static_cast<uint32_t>(p.n_bt) + 1u) * 4u + 15u) / 16u * 16u : 0u;
+    const uint32_t kFuse = fused ? (32u + static_cast<uint32_t>(pl.BT + 4) * (pl.BF + 4) * 4u + 15u) / 16u * 16u : 0u;
+    p.fuse_off = 512u + kTable;
+    const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512 + kTable + kFuse;
     const uint32_t kAvail = 227u * 1024u - kFixed;
     if (reuse) {
         // ring 1 = activation patches (+ the rows a 16-padded, 2-frame-shifted MMA view may touch), ring 2 = weight tiles
@@ -833,9 +926,13 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     return 0;
 }
 
+struct ConvFront {            // the fused first layer's own operands (flags bit 128)
+    const float* x0; const float* w11; const float* b11;
+};
+
 static int conv_igemm_launch(const void* x, const void* wp, const float* bias, const int32_t* lengths, const void* mask,
                              void* y, int y_dtype, int flags,
-                             int B, int T, int F, int Cin, int Cout, void* stream) {
+                             int B, int T, int F, int Cin, int Cout, void* stream, const ConvFront* front = nullptr) {
     if (!x || !wp || !y) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
     if (Cin % kConvKC != 0 || Cin <= 0) { set_error("conv3x3_igemm_bf16: Cin=%d must be a positive multiple of 64", Cin); return 1; }
     if (Cout <= 0 || Cout % 8 != 0) { set_error("conv3x3_igemm_bf16: Cout=%d must be a positive multiple of 8", Cout); return 1; }
@@ -848,6 +945,9 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     if (y_dtype != 0 && y_dtype != act) { set_error("conv3x3_igemm_bf16: bad y dtype %d", y_dtype); return 1; }
     if (((flags & 16) != 0) != ((flags & 32) != 0)) {            // measured on B200: a mixed pair faults (illegal instruction)
         set_error("conv3x3_igemm_bf16: tcgen05 kind::f16 needs both operands in the same format (set both or neither of DASV_CONV_W_F16, DASV_CONV_X_F16)"); return 1;
+    }
+    if ((flags & 128) && ((flags & 64) || !(flags & 1) || Cin > 128 || Cin % 8 != 0 || 128 % (Cin / 8) != 0)) {
+        set_error("conv3x3_igemm_bf16: the fused first layer needs a ReLU forward pass in bf16/fp16 and Cin in {64, 128}"); return 1;
     }
     if ((flags & 64) && ((flags & 48) || !(flags & 1))) { set_error("conv3x3_igemm_bf16: the split (fp32x3) mode is bf16, forward only"); return 1; }
     if (!(flags & 1) && (flags & 48)) { set_error("conv3x3_igemm_bf16: the input-gradient pass is bf16 only"); return 1; }
@@ -889,12 +989,13 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
         tmA = hit->tmA; tmB = hit->tmB; p = hit->p; smem = hit->smem; grid = hit->grid; pair = hit->pair;
     }
     p.bias = bias; p.lengths = lengths; p.y = y; p.mask = mask;
+    if (front) { p.x0 = front->x0; p.w11 = front->w11; p.b11 = front->b11; p.scratch = const_cast<void*>(x); }
 
-    const int variant = (pair ? 4 : 0) + (p.relu ? ((flags & 64) ? 3 : (act == 2 ? 2 : 0)) : 1);
+    const int variant = (flags & 128) ? (act == 2 ? 9 : 8) : (pair ? 4 : 0) + (p.relu ? ((flags & 64) ? 3 : (act == 2 ? 2 : 0)) : 1);
     if (conv_raise_smem(variant, k.dev)) return 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kConvThreads);
+    cfg.blockDim = dim3(kConvThreads + ((flags & 128) ? kConvFuseThreads : 0));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[2];
@@ -918,4 +1019,24 @@ extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const floa
 extern "C" int dasv_conv3x3_dgrad_bf16(const void* g, const void* wp_rot, const void* relu_mask, const int32_t* lengths,
                                        void* dx, int B, int T, int F, int Cg, int Cx, void* stream) {
     return conv_igemm_launch(g, wp_rot, nullptr, lengths, relu_mask, dx, 1, 0, B, T, F, Cg, Cx, stream);
+}
+
+// conv11 + conv12 in one kernel (scripts/CNNs.py:72-74): relu(conv11(x0) + b11) never goes to HBM as a tensor.  Four extra warps
+// of the implicit-GEMM kernel compute it per tile (haloed region, zeros outside the image and beyond the utterance) into a
+// per-CTA, double-buffered scratch patch that stays in L2, one tile ahead of the MMAs; the TMA producer reads the patches
+// from there.  Same values as dasv_conv11_direct + dasv_conv3x3_igemm_bf16 (bit-identical), without the 2 x 2.1 GB round trip
+// of the 128-channel tensor.  `scratch`: dasv_conv12_fused_workspace_bytes(C1) bytes, contents irrelevant.
+extern "C" size_t dasv_conv12_fused_workspace_bytes(int C1) {
+    // [2 * SMs] patches of at most (BT+2)(BF+2) <= 520 pixels (BT*BF <= 256) of C1 16-bit channels
+    return static_cast<size_t>(2) * sm_count() * 520 * (C1 > 0 ? C1 : 0) * 2;
+}
+
+extern "C" int dasv_conv12_fused_bf16(const float* x0, const float* w11, const float* b11, const void* wp, const float* bias,
+                                      const int32_t* lengths, void* y, void* scratch, int y_dtype, int flags,
+                                      int B, int T, int F, int C1, int Cout, void* stream) {
+    if (!x0 || !w11 || !b11 || !bias || !scratch) { set_error("conv12_fused: null argument"); return 1; }
+    if (flags & (4 | 8 | 64 | 128)) { set_error("conv12_fused: flags may hold RELU, POOL and the operand formats only"); return 1; }
+    if ((reinterpret_cast<uintptr_t>(scratch) & 127) != 0) { set_error("conv12_fused: scratch must be 128-byte aligned"); return 1; }
+    const ConvFront front{x0, w11, b11};
+    return conv_igemm_launch(scratch, wp, bias, lengths, nullptr, y, y_dtype, flags | 128, B, T, F, C1, Cout, stream, &front);
 }

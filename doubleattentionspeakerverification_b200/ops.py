@@ -262,6 +262,35 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
     return y
 
 
+_scratch_cache = {}
+
+
+def conv12_fused(x, w11, b11, wp, bias, Cout, lengths=None, pool=True, act_dtype=torch.bfloat16):
+    """conv11 + conv12 in one kernel: x [B,T,F] f32 -> relu(conv12(relu(conv11(x)))) (+ pool) as NHWC ``act_dtype``; the
+    C1-channel tensor in between never goes to HBM.  Bit-identical to conv11_direct + conv3x3_igemm_bf16."""
+    x = _f32(x, 'x')
+    B, T, Fq = x.shape
+    w11, b11 = _f32(w11, 'w11'), _f32(b11, 'b11')
+    C1 = w11.shape[0]
+    if wp.dtype != act_dtype:
+        raise _lib.DasvError('conv12_fused: packed weights and activations must share their 16-bit format')
+    flags = CONV_RELU | (CONV_POOL if pool else 0) | ((CONV_W_F16 | CONV_X_F16) if act_dtype == torch.float16 else 0)
+    with torch.cuda.device(x.device):
+        lengths = _lengths(lengths, B, x.device)
+        L = _lib.lib()
+        key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream, C1)
+        ws = _scratch_cache.get(key)                         # per (device, stream): kernels of one stream run one after another
+        if ws is None:
+            ws = torch.empty((int(L.dasv_conv12_fused_workspace_bytes(C1)),), device=x.device, dtype=torch.uint8)
+            _scratch_cache[key] = ws
+        shape = (B, (T + 1) // 2, Fq // 2, Cout) if pool else (B, T, Fq, Cout)
+        y = torch.empty(shape, device=x.device, dtype=act_dtype)
+        rc = L.dasv_conv12_fused_bf16(_p(x), _p(w11), _p(b11), _p(wp), _p(_f32(bias, 'bias')), _p(lengths), _p(y), _p(ws),
+                                      _dtype_code(y, 'y'), flags, B, T, Fq, C1, Cout, _stream())
+        _lib.check(rc, 'dasv_conv12_fused_bf16')
+    return y
+
+
 # ------------------------------------------------------------------------------------ tail / scoring
 def fc_tail(pooled, w1t, b1, w2t, b2, bn_scale, bn_shift):
     pooled = _f32(pooled, 'pooled')

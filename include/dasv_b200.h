@@ -150,6 +150,16 @@ int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, co
                             void* y, int y_dtype, int flags,
                             int B, int T, int F, int Cin, int Cout, void* stream);
 
+/* conv11 + conv12 of the front-end in ONE kernel (CNNs.py:72-74): x0 [B,T,F] f32, w11 [C1,1,3,3] f32, b11 [C1] f32, then
+ * exactly dasv_conv3x3_igemm_bf16 on relu(conv11(x0) + b11) with wp [Cout][9][C1], bias, lengths, y, y_dtype, flags
+ * (DASV_CONV_RELU | DASV_CONV_POOL | the operand formats).  The C1-channel tensor never exists in HBM: four extra warps
+ * compute it per tile into a per-CTA scratch patch (L2-resident) one tile ahead of the MMAs.  Bit-identical to the two
+ * separate calls.  C1 in {64, 128}; scratch: dasv_conv12_fused_workspace_bytes(C1) bytes, 128-byte aligned. */
+size_t dasv_conv12_fused_workspace_bytes(int C1);
+int dasv_conv12_fused_bf16(const float* x0, const float* w11, const float* b11, const void* wp, const float* bias,
+                           const int32_t* lengths, void* y, void* scratch, int y_dtype, int flags,
+                           int B, int T, int F, int C1, int Cout, void* stream);
+
 /* Input gradient of the same convolution: dx = conv3x3(g, W') with the rotated, transposed weights
  * W'[ci][co][ky][kx] = W[co][ci][2-ky][2-kx] packed by dasv_pack_conv_weight_bf16 (wp_rot), linear epilogue, on the
  * forward's tensor-core kernel.  g [B,T,F,Cg] bf16 (Cg = the conv's output channels), dx [B,T,F,Cx] bf16.

@@ -192,6 +192,35 @@ def test_conv11_split_output():
     assert torch.equal(y[..., :16], want.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize('B,T,F,C1,Cout,pool,act,with_len', [(2, 37, 80, 128, 128, True, torch.bfloat16, True),
+                                                             (3, 16, 80, 64, 64, True, torch.bfloat16, False),
+                                                             (1, 5, 80, 128, 128, True, torch.float16, False),
+                                                             (4, 50, 40, 128, 256, False, torch.bfloat16, True),
+                                                             (2, 401, 80, 128, 128, True, torch.bfloat16, True),
+                                                             (9, 23, 20, 64, 136, True, torch.float16, True)])
+def test_conv12_fused_equals_separate_kernels(B, T, F, C1, Cout, pool, act, with_len):
+    """conv11 computed inside conv12's kernel (per-tile scratch patches in L2) == conv11_direct followed by the implicit
+    GEMM, bit for bit, including masked rows, image borders and ragged lengths."""
+    rs = np.random.RandomState(B * 7 + T)
+    x = dev((2 * rs.standard_normal((B, T, F))).astype(np.float32))
+    w11 = dev((rs.standard_normal((C1, 1, 3, 3)) * 0.5).astype(np.float32))
+    b11 = dev((rs.standard_normal((C1,)) * 0.1).astype(np.float32))
+    w12 = dev((rs.standard_normal((Cout, C1, 3, 3)) * np.sqrt(2.0 / (9 * C1))).astype(np.float32))
+    b12 = dev((rs.standard_normal((Cout,)) * 0.1).astype(np.float32))
+    L = None
+    if with_len:
+        Ln = rs.randint(1, T + 1, size=(B,)).astype(np.int32)
+        Ln[0] = T
+        L = dev(Ln)
+    wp = ops.pack_conv_weight_bf16(w12, act)
+    h = ops.conv11_direct(x, w11, b11, L, out_dtype=act)
+    want = ops.conv3x3_igemm_bf16(h, wp, b12, Cout, L, pool=pool)
+    for _ in range(2):                                             # twice: the scratch buffers are reused
+        got = ops.conv12_fused(x, w11, b11, wp, b12, Cout, L, pool=pool, act_dtype=act)
+        assert got.dtype == act and got.shape == want.shape
+        assert torch.equal(got, want)
+
+
 def test_fp16_store_saturates():
     """fp16 activations saturate at the largest finite value instead of overflowing to infinity."""
     x = torch.full((1, 4, 80), 3.0e4, device='cuda')
