@@ -62,7 +62,11 @@ class _VGG(nn.Module):
                 self._names.append(name)
                 cin = cout
         self.precision = precision
-        self.fuse_first = True          # conv11 inside conv12's kernel on the 16-bit inference paths
+        # conv11 inside conv12's kernel (ops.conv12_fused).  Off by default: it removes the 2 x 2.1 GB round trip of conv11's
+        # output (ncu: DRAM read of the layer 2.1 GB -> 33 MB) but its FMA warps take issue slots from the MMA and epilogue
+        # warps (tensor pipe 71 % -> 54 % active): 2.38 ms against 0.77 + 1.78 ms for the two kernels, and no gain per step
+        # under the power cap (profiles/r2_fused_conv12_summary.txt).
+        self.fuse_first = False
         self._packed = {}
 
     # ---------------------------------------------------------------- weight packing cache
@@ -164,8 +168,8 @@ class _VGG(nn.Module):
             act = torch.float16 if prec == 'fp16' else torch.bfloat16
             x3 = prec == 'fp32x3'
             wk = 'x3' if x3 else ('f16' if prec == 'fp16' else 'bf16')       # both MMA operands must have the same 16-bit format
-            # conv11's output (2.1 GB of bf16 per 256 x 4 s batch) never goes to HBM: conv12's kernel computes it per tile
-            # (ops.conv12_fused); the stand-alone kernel remains for the split (fp32x3) format and other channel counts
+            # conv11 is bound by its NHWC 16-bit write (2.1 GB per 256 x 4 s batch at the 3.95 TB/s pure-write bandwidth);
+            # fuse_first computes it inside conv12's kernel instead (see __init__)
             c12 = getattr(self, self._names[1])
             fuse = self.fuse_first and not x3 and c11.out_channels in (64, 128) and x.size(2) % 2 == 0
             if fuse:

@@ -26,7 +26,7 @@
 namespace dasv {
 
 constexpr int kConvThreads = 384;              // 4 role warps + 8 epilogue warps
-constexpr int kConvFuseThreads = 128;          // fused first layer: 4 more warps compute conv11 patches
+constexpr int kConvFuseThreads = 256;          // fused first layer: 8 more warps compute conv11 patches
 constexpr int kConvTileM = 128;                 // output channels per CTA tile = TMEM lanes
 constexpr int kConvKC = 64;                     // channels per K slice (64 bf16 = one 128-byte swizzle row)
 constexpr uint32_t kConvABytes = kConvTileM * kConvKC * 2;
@@ -395,16 +395,25 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // fma.rn.f32x2) and every PL-th pixel; the arithmetic and its order are conv11_direct_kernel's, so the values are
         // bit-identical to the unfused path.
         const int tid11 = static_cast<int>(threadIdx.x) - kConvThreads;
-        const int C1 = p.Cin, CG = C1 / 8, PL = kConvFuseThreads / CG;
+        const int C1 = p.Cin, CG = C1 / 4, PL = kConvFuseThreads / CG;          // a thread owns 4 channels (two packed pairs)
         const int cg = tid11 % CG, pl = tid11 / CG;
         const int PW = p.BF + 2, PH = p.BT + 2, XW = p.BF + 4, XH = p.BT + 4;
-        uint64_t wr2[9][4], br2[4];
+        uint64_t wr2[9][2], br2[2];
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-            br2[e >> 1] = pack_f32x2(p.b11[cg * 8 + e], p.b11[cg * 8 + e + 1]);
+        for (int e = 0; e < 4; e += 2) {
+            br2[e >> 1] = pack_f32x2(p.b11[cg * 4 + e], p.b11[cg * 4 + e + 1]);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap)
-                wr2[tap][e >> 1] = pack_f32x2(p.w11[(cg * 8 + e) * 9 + tap], p.w11[(cg * 8 + e + 1) * 9 + tap]);
+                wr2[tap][e >> 1] = pack_f32x2(p.w11[(cg * 4 + e) * 9 + tap], p.w11[(cg * 4 + e + 1) * 9 + tap]);
+        }
+        // trip table (once per CTA): pixel pair -> {offset of its 3x4 input window in x_sm | tt << 16 | ff << 24, offset of its
+        // two output pixels in the scratch patch}, so that a trip costs one LDS.64 instead of divisions and multiplies
+        const int HW = PW >> 1, n_pairs = PH * HW;
+        uint2* trip_sm = reinterpret_cast<uint2*>(x_sm + ((XH * XW + 3) & ~3));
+        for (int i = tid11; i < n_pairs; i += kConvFuseThreads) {
+            const int tt = i / HW, ff = 2 * (i - tt * HW);
+            trip_sm[i] = make_uint2(static_cast<uint32_t>(tt * XW + ff) | (static_cast<uint32_t>(tt) << 16) | (static_cast<uint32_t>(ff) << 24),
+                                    static_cast<uint32_t>((tt * PW + ff) * C1));
         }
         uint32_t fit = 0;
         for (int tile = tile0; tile < sched.n_pass0; tile += tile_step) {
@@ -421,33 +430,57 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 x_sm[i] = (t >= 0 && t < L && f >= 0 && f < p.F) ? p.x0[(static_cast<size_t>(c.b0) * p.T + t) * p.F + f] : 0.f;
             }
             named_bar_sync(3, kConvFuseThreads);
-            uint16_t* sp = static_cast<uint16_t*>(p.scratch) + (static_cast<size_t>(blockIdx.x) * 2 + buf) * PH * PW * C1 + cg * 8;
-            for (int px = pl; px < PH * PW; px += PL) {
-                const int tt = px / PW, ff = px - tt * PW;
-                const int t = c.t0 - 1 + tt, f = c.f0 - 1 + ff;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (t >= 0 && t < L && f >= 0 && f < p.F) {                      // outside: conv12's zero padding / masked rows
-                    uint64_t acc[4];
+            uint16_t* sp = static_cast<uint16_t*>(p.scratch) + (static_cast<size_t>(blockIdx.x) * 2 + buf) * PH * PW * C1 + cg * 4;
+            // two horizontally adjacent pixels per trip (they share 12 of their 18 input taps); PW is even.  A tile whose whole
+            // haloed region lies inside the image and the utterance (most of them) skips the per-pixel checks.
+            const bool interior = c.t0 >= 1 && c.t0 + p.BT < L && c.f0 >= 1 && c.f0 + p.BF < p.F;
+            for (int pp = pl; pp < n_pairs; pp += PL) {
+                const uint2 tr = trip_sm[pp];
+                bool ok0 = true, ok1 = true;
+                if (!interior) {
+                    const int t = c.t0 - 1 + static_cast<int>((tr.x >> 16) & 0xffu), f = c.f0 - 1 + static_cast<int>(tr.x >> 24);
+                    const bool row_ok = t >= 0 && t < L;
+                    ok0 = row_ok && f >= 0 && f < p.F;
+                    ok1 = row_ok && f + 1 >= 0 && f + 1 < p.F;
+                }
+                uint2 v0 = make_uint2(0u, 0u), v1 = v0;                          // outside: conv12's zero padding / masked rows
+                if (ok0 || ok1) {
+                    const float* xw = x_sm + (tr.x & 0xffffu);
+                    float xv[3][4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[e] = br2[e];
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xv[dy][j] = xw[dy * XW + j];
+                    uint64_t accA[2], accB[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { accA[e] = br2[e]; accB[e] = br2[e]; }
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                         for (int dx = 0; dx < 3; ++dx) {
-                            const float xv = x_sm[(tt + dy) * XW + ff + dx];
-                            const uint64_t x2 = pack_f32x2(xv, xv);
+                            const uint64_t xa = pack_f32x2(xv[dy][dx], xv[dy][dx]);
+                            const uint64_t xb = pack_f32x2(xv[dy][dx + 1], xv[dy][dx + 1]);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) acc[e] = fma_f32x2(x2, wr2[dy * 3 + dx][e], acc[e]);
+                            for (int e = 0; e < 2; ++e) {
+                                accA[e] = fma_f32x2(xa, wr2[dy * 3 + dx][e], accA[e]);
+                                accB[e] = fma_f32x2(xb, wr2[dy * 3 + dx][e], accB[e]);
+                            }
                         }
-                    float a[8];
+                    float a0[4], a1[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) unpack_f32x2(acc[e], a[2 * e], a[2 * e + 1]);
+                    for (int e = 0; e < 2; ++e) {
+                        unpack_f32x2(accA[e], a0[2 * e], a0[2 * e + 1]);
+                        unpack_f32x2(accB[e], a1[2 * e], a1[2 * e + 1]);
+                    }
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) a[e] = fmaxf(a[e], 0.f);
+                    for (int e = 0; e < 4; ++e) { a0[e] = fmaxf(a0[e], 0.f); a1[e] = fmaxf(a1[e], 0.f); }
                     constexpr int A16 = ACT == 2 ? 2 : 1;
-                    v = make_uint4(pack16<A16>(a[0], a[1]), pack16<A16>(a[2], a[3]), pack16<A16>(a[4], a[5]), pack16<A16>(a[6], a[7]));
+                    if (ok0) v0 = make_uint2(pack16<A16>(a0[0], a0[1]), pack16<A16>(a0[2], a0[3]));
+                    if (ok1) v1 = make_uint2(pack16<A16>(a1[0], a1[1]), pack16<A16>(a1[2], a1[3]));
                 }
-                *reinterpret_cast<uint4*>(sp + static_cast<size_t>(px) * C1) = v;
+                uint16_t* dst = sp + tr.y;
+                *reinterpret_cast<uint2*>(dst) = v0;
+                *reinterpret_cast<uint2*>(dst + C1) = v1;
             }
             __threadfence();                                                     // the patch is in L2 ...
             asm volatile("fence.proxy.async;" ::: "memory");                     // ... and ordered before the TMA (async proxy) reads of it
@@ -887,7 +920,8 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     // staging + alignment slack + barriers (+ the valid-tile prefix table of a ragged batch) (+ the fused first layer's
     // barriers and input patch)
     const uint32_t kTable = p.balanced ? ((static_cast<uint32_t>(p.n_bt) + 1u) * 4u + 15u) / 16u * 16u : 0u;
-    const uint32_t kFuse = fused ? (32u + static_cast<uint32_t>(pl.BT + 4) * (pl.BF + 4) * 4u + 15u) / 16u * 16u : 0u;
+    const uint32_t kFuse = fused ? (32u + ((static_cast<uint32_t>(pl.BT + 4) * (pl.BF + 4) + 3u) & ~3u) * 4u      // barriers + input patch
+                                    + static_cast<uint32_t>(pl.BT + 2) * ((pl.BF + 2) / 2) * 8u + 15u) / 16u * 16u : 0u;   // + trip table
     p.fuse_off = 512u + kTable;
     const uint32_t kFixed = 4 * kConvEpiBytes + 1024 + 512 + kTable + kFuse;
     const uint32_t kAvail = 227u * 1024u - kFixed;
@@ -946,7 +980,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     if (((flags & 16) != 0) != ((flags & 32) != 0)) {            // measured on B200: a mixed pair faults (illegal instruction)
         set_error("conv3x3_igemm_bf16: tcgen05 kind::f16 needs both operands in the same format (set both or neither of DASV_CONV_W_F16, DASV_CONV_X_F16)"); return 1;
     }
-    if ((flags & 128) && ((flags & 64) || !(flags & 1) || Cin > 128 || Cin % 8 != 0 || 128 % (Cin / 8) != 0)) {
+    if ((flags & 128) && ((flags & 64) || !(flags & 1) || (Cin != 64 && Cin != 128))) {
         set_error("conv3x3_igemm_bf16: the fused first layer needs a ReLU forward pass in bf16/fp16 and Cin in {64, 128}"); return 1;
     }
     if ((flags & 64) && ((flags & 48) || !(flags & 1))) { set_error("conv3x3_igemm_bf16: the split (fp32x3) mode is bf16, forward only"); return 1; }

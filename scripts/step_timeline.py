@@ -49,7 +49,7 @@ def main():
     print('eager            : %.3f ms/step' % timed(step, args.steps))
 
     # ---- per-slot times: an event after every op of the step
-    names = ['conv11_direct', 'conv3x3_igemm_bf16', 'dmha_fwd', 'fc_tail']
+    names = ['conv11_direct', 'conv12_fused', 'conv3x3_igemm_bf16', 'dmha_fwd', 'fc_tail']
     orig = {n: getattr(ops, n) for n in names}
     marks = []
 

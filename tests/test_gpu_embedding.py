@@ -78,6 +78,17 @@ def test_embedding_fp32x3(name):
         assert max_rel(ev.cpu().numpy(), g['emb_varlen']) < 1e-4
 
 
+def test_embedding_with_fused_first_layer():
+    """fuse_first=True (conv11 computed inside conv12's kernel): the same embeddings, bit for bit."""
+    g = golden('embed_example_b2.npz')
+    net, x = build(g, 'bf16')
+    with torch.no_grad():
+        a = net.getEmbedding(dev(x), lengths=dev(g['lengths']))
+        net.front_end.fuse_first = True
+        b = net.getEmbedding(dev(x), lengths=dev(g['lengths']))
+    assert torch.equal(a, b)
+
+
 def test_embedding_fp16_operands(precision='fp16'):
     """precision='fp16' (fp16 activations and weights on the same kernels) on the exampleModel fixtures."""
     for name in ('example', 'example_b2'):
