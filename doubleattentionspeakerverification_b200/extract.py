@@ -189,7 +189,7 @@ def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400
     cuda = dev.type == 'cuda'
     if cuda:
         compute = torch.cuda.current_stream(dev)
-        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream = _copy_stream(dev)                          # one per device: the caching allocator pools memory per stream
         copy_stream.wait_stream(compute)
     staged = []
     for b in batches:                                            # enqueue every batch's transfer up front, in processing order
@@ -223,6 +223,16 @@ def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400
             out = torch.empty((len(indices), emb.shape[1]), device=emb.device, dtype=emb.dtype)
         out[torch.from_numpy(b).to(dev)] = emb
     return out
+
+
+_copy_streams = {}
+
+
+def _copy_stream(dev):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _copy_streams:
+        _copy_streams[idx] = torch.cuda.Stream(device=dev)
+    return _copy_streams[idx]
 
 
 class _NullCtx:
