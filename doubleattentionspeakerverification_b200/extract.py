@@ -70,13 +70,28 @@ def global_plan(lengths, world, max_frames=256 * 400, min_ratio=0.5, min_frames=
     lengths = np.asarray(lengths)
     order = np.argsort(-lengths, kind='stable')
     batches, cur = [], []
-    for i in order:
-        if cur:
-            Tmax = int(lengths[cur[0]])
-            if (len(cur) + 1) * Tmax > max_frames or (lengths[i] < min_ratio * Tmax and len(cur) * Tmax >= min_frames):
+    if world > 1 and len(lengths) >= 4 * world:
+        # several ranks: cut the sorted list into world * k batches of EQUAL valid frames (k per rank, each close to the frame
+        # budget), so that whole batches deal out evenly and nobody is left with small remainders
+        total = float(lengths.sum())
+        k = max(1, int(np.ceil(total / (world * float(max_frames)))))
+        target = total / (world * k)
+        cum = 0.0
+        for i in order:
+            if cur and ((len(cur) + 1) * int(lengths[cur[0]]) > 1.5 * max_frames or
+                        (cum + 0.5 * float(lengths[i]) >= target * (len(batches) + 1) and len(batches) < world * k - 1)):
                 batches.append(np.array(cur))
                 cur = []
-        cur.append(int(i))
+            cur.append(int(i))
+            cum += float(lengths[i])
+    else:
+        for i in order:
+            if cur:
+                Tmax = int(lengths[cur[0]])
+                if (len(cur) + 1) * Tmax > max_frames or (lengths[i] < min_ratio * Tmax and len(cur) * Tmax >= min_frames):
+                    batches.append(np.array(cur))
+                    cur = []
+            cur.append(int(i))
     if cur:
         batches.append(np.array(cur))
     # a small leftover at the short end joins its neighbour when the sum stays near the budget

@@ -40,7 +40,7 @@ def test_shard_plan_is_balanced_partition():
 
 def test_global_plan_partitions_balances_and_respects_budget():
     """BASELINE configs[3] lengths (2-20 s): every utterance in exactly one batch, batches within the frame budget (the
-    merged leftover may pass it by 25 %), rank loads within a few % of each other, and far fewer small batches than
+    short-utterance batches may pass it by up to 50 % in padded frames), rank loads within a few % of each other, and far fewer small batches than
     per-rank bucketing."""
     for world in (1, 2, 4, 8):
         rs = np.random.RandomState(0)
@@ -50,7 +50,7 @@ def test_global_plan_partitions_balances_and_respects_budget():
         assert np.array_equal(allidx, np.arange(len(L)))
         for bs in gp:
             for b in bs:
-                assert len(b) * L[b].max() <= 1.25 * 256 * 400
+                assert len(b) * L[b].max() <= 1.5 * 256 * 400
         loads = [sum(extract._batch_cost(L, b) for b in bs) for bs in gp]
         assert max(loads) <= 1.05 * np.mean(loads)
         small = sum(1 for bs in gp for b in bs if len(b) * L[b].max() < 16 * 400)
