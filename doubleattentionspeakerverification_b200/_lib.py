@@ -47,6 +47,11 @@ SIGNATURES = {
     'dasv_cosine_matrix_workspace_bytes': (_sz, [_i, _i]),
     'dasv_threshold_counts': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     'dasv_cosine_matrix': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    'dasv_bn1d_train_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _c.c_float, _c.c_float, _vp]),
+    'dasv_bn1d_train_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    'dasv_amsoftmax_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_float, _c.c_float, _vp]),
+    'dasv_amsoftmax_bwd_workspace_bytes': (_sz, [_i, _i]),
+    'dasv_amsoftmax_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_float, _vp]),
     'dasv_logmel_f32': (_i, [_vp, _vp, _i, _c.c_longlong, _vp, _i, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _vp, _i, _vp]),
     'dasv_cmn_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
@@ -54,7 +59,7 @@ SIGNATURES = {
 _LIB = None
 
 # kernels launched per successful C call, and the running count bench.py reports as gpu_launches
-KERNELS_PER_CALL = {'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_bias_grad_bf16': 2, 'dasv_conv11_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
+KERNELS_PER_CALL = {'dasv_amsoftmax_fwd': 3, 'dasv_amsoftmax_bwd': 4, 'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_bias_grad_bf16': 2, 'dasv_conv11_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
 LAUNCHES = {}
 
 

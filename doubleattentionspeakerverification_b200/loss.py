@@ -1,12 +1,29 @@
-"""AM-Softmax classifier head (reference ``scripts/loss.py:14-52``).
+"""AM-Softmax classifier head (reference ``scripts/loss.py:14-52``): ``predictionLayer`` of ``SpeakerClassifier``.
 
-Training-only and OUT OF SCOPE for the extraction path: kept in stock
-PyTorch so ``SpeakerClassifier`` has the reference's ``predictionLayer.W`` parameter and
-``train.py``-style steps run.  The only change is that the margin is scattered on the label's own
-device (the reference round-trips through the CPU, loss.py:45-48).
+On a CUDA device the forward (both L2 normalisations, the cosine GEMM, the margin at the label -- scattered on the
+device, the reference round-trips through the CPU, loss.py:45-48 -- annealing and scale) and the backward through both
+normalisations run on this package's kernels (``csrc/train_tail.cu``).  There is no CPU path: a non-CUDA input raises.
 """
 import torch
 from torch import nn
+
+from . import ops
+
+
+class _AMSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, label, s, margin_scaled):
+        ctx.set_materialize_grads(False)                  # train.py only differentiates the logits: no zero tensor for costh
+        costh, logits, ix, iw = ops.amsoftmax_fwd(x, W, label, s, margin_scaled)
+        ctx.save_for_backward(x, W, costh, ix, iw)
+        ctx.s = s
+        return costh, logits
+
+    @staticmethod
+    def backward(ctx, dcosth, dlogits):
+        x, W, costh, ix, iw = ctx.saved_tensors
+        dx, dW = ops.amsoftmax_bwd(dcosth, dlogits, x, W, costh, ix, iw, ctx.s)
+        return dx, dW, None, None, None
 
 
 class AMSoftmax(nn.Module):
@@ -29,10 +46,7 @@ class AMSoftmax(nn.Module):
     def forward(self, x, label=None, step=0):
         assert x.size(0) == label.size(0)
         assert x.size(1) == self.in_feats
-        xn = x / torch.norm(x, p=2, dim=1, keepdim=True).clamp(min=1e-12)
-        wn = self.W / torch.norm(self.W, p=2, dim=0, keepdim=True).clamp(min=1e-12)
-        costh = torch.mm(xn, wn)
-        margin = torch.zeros_like(costh).scatter_(1, label.view(-1, 1).to(costh.device), self.m)
         alpha = self._alpha(step)
-        combined = ((costh - margin) + alpha * costh) / (1 + alpha)
-        return costh, self.s * combined
+        # s * ((costh - m*onehot) + alpha*costh) / (1 + alpha) = s*costh - s*m/(1+alpha) at the label  (loss.py:37-52)
+        return _AMSoftmaxFn.apply(x.float().contiguous(), self.W, label.to(x.device), float(self.s),
+                                  float(self.s) * float(self.m) / (1 + alpha))

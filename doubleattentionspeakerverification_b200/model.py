@@ -13,6 +13,22 @@ from .loss import AMSoftmax
 from .poolings import Attention, DoubleMHA, MultiHeadAttention
 
 
+class _BN1dTrainFn(torch.autograd.Function):
+    """BatchNorm1d with batch statistics on this package's kernels (scripts/model.py:67 in train mode)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum):
+        y, sm, si = ops.bn1d_train_fwd(x, gamma, beta, running_mean, running_var, eps, momentum)
+        ctx.save_for_backward(x, gamma, sm, si)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, sm, si = ctx.saved_tensors
+        dx, dg, db = ops.bn1d_train_bwd(dy.contiguous(), x, gamma, sm, si)
+        return dx, dg, db, None, None, None, None
+
+
 class SpeakerClassifier(nn.Module):
 
     def __init__(self, parameters, device):
@@ -82,8 +98,16 @@ class SpeakerClassifier(nn.Module):
                                              (embedding0.requires_grad or self.fc1.weight.requires_grad))
         if fused:
             return ops.fc_tail(embedding0.float().contiguous(), *self._tail_params())
-        embedding1 = F.relu(self.fc1(embedding0))
-        return self.b2(F.relu(self.fc2(embedding1)))                  # batch statistics / autograd: stock torch
+        embedding1 = F.relu(self.fc1(embedding0))                     # Linear layers: library GEMMs (cuBLAS through torch)
+        r2 = F.relu(self.fc2(embedding1))
+        b2 = self.b2
+        if (self.training and r2.is_cuda and r2.dtype == torch.float32 and b2.track_running_stats and b2.momentum is not None
+                and b2.affine and r2.size(0) > 1):
+            # batch statistics, running-statistics update and the backward on the package's kernels (csrc/train_tail.cu)
+            with torch.no_grad():
+                b2.num_batches_tracked += 1
+            return _BN1dTrainFn.apply(r2.contiguous(), b2.weight, b2.bias, b2.running_mean, b2.running_var, b2.eps, b2.momentum)
+        return b2(r2)
 
     def getEmbedding(self, x, lengths=None):
         """scripts/model.py:52-59.  ``lengths`` (valid input frames per utterance) enables padded batches.

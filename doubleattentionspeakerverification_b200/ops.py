@@ -467,3 +467,63 @@ def conv11_bwd(x, g, lengths=None):
         ws = torch.empty((max(int(_lib.lib().dasv_conv11_bwd_workspace_bytes(B, T, C)), 16),), device=g.device, dtype=torch.uint8)
         _lib.check(_lib.lib().dasv_conv11_bwd(_p(x), _p(g), _p(lengths), _p(dw), _p(db), _p(ws), 0, B, T, Fq, C, _stream()), 'dasv_conv11_bwd')
     return dw, db
+
+
+# ------------------------------------------------------------------------------------ training-mode tail
+def bn1d_train_fwd(x, gamma, beta, running_mean, running_var, eps, momentum):
+    """BatchNorm1d with batch statistics on x [B,E] f32; running_mean / running_var (or None) are updated in place.
+    Returns (y, save_mean, save_invstd)."""
+    x = _f32(x, 'x')
+    B, E = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        sm = torch.empty((E,), device=x.device, dtype=torch.float32)
+        si = torch.empty((E,), device=x.device, dtype=torch.float32)
+        rc = _lib.lib().dasv_bn1d_train_fwd(_p(x), _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(y), _p(sm), _p(si),
+                                            B, E, float(eps), float(momentum), _stream())
+        _lib.check(rc, 'dasv_bn1d_train_fwd')
+    return y, sm, si
+
+
+def bn1d_train_bwd(dy, x, gamma, save_mean, save_invstd):
+    dy, x = _f32(dy, 'dy'), _f32(x, 'x')
+    B, E = x.shape
+    with torch.cuda.device(x.device):
+        dx = torch.empty_like(x)
+        dg = torch.empty((E,), device=x.device, dtype=torch.float32)
+        db = torch.empty((E,), device=x.device, dtype=torch.float32)
+        rc = _lib.lib().dasv_bn1d_train_bwd(_p(dy), _p(x), _p(gamma), _p(save_mean), _p(save_invstd), _p(dx), _p(dg), _p(db), B, E, _stream())
+        _lib.check(rc, 'dasv_bn1d_train_bwd')
+    return dx, dg, db
+
+
+def amsoftmax_fwd(x, W, label, s, margin_scaled):
+    """x [B,E], W [E,S] f32, label [B] int64 (device) -> (costh, logits, inv_x, inv_w)."""
+    x, W = _f32(x, 'x'), _f32(W, 'W')
+    B, E = x.shape
+    S = W.shape[1]
+    label = _dev(label, 'label').to(torch.int64).contiguous()
+    with torch.cuda.device(x.device):
+        f = dict(device=x.device, dtype=torch.float32)
+        costh, logits = torch.empty((B, S), **f), torch.empty((B, S), **f)
+        ix, iw = torch.empty((B,), **f), torch.empty((S,), **f)
+        rc = _lib.lib().dasv_amsoftmax_fwd(_p(x), _p(W), _p(label), _p(costh), _p(logits), _p(ix), _p(iw), B, E, S,
+                                           float(s), float(margin_scaled), _stream())
+        _lib.check(rc, 'dasv_amsoftmax_fwd')
+    return costh, logits, ix, iw
+
+
+def amsoftmax_bwd(dcosth, dlogits, x, W, costh, inv_x, inv_w, s):
+    x, W = _f32(x, 'x'), _f32(W, 'W')
+    B, E = x.shape
+    S = W.shape[1]
+    with torch.cuda.device(x.device):
+        dcosth = None if dcosth is None else _f32(dcosth, 'dcosth')
+        dlogits = None if dlogits is None else _f32(dlogits, 'dlogits')
+        dx, dW = torch.empty_like(x), torch.empty_like(W)
+        L = _lib.lib()
+        ws = torch.empty((max(int(L.dasv_amsoftmax_bwd_workspace_bytes(B, S)), 16),), device=x.device, dtype=torch.uint8)
+        rc = L.dasv_amsoftmax_bwd(_p(dcosth), _p(dlogits), _p(x), _p(W), _p(costh), _p(inv_x), _p(inv_w), _p(dx), _p(dW), _p(ws),
+                                  B, E, S, float(s), _stream())
+        _lib.check(rc, 'dasv_amsoftmax_bwd')
+    return dx, dW

@@ -240,6 +240,26 @@ int dasv_logmel_f32(const float* wave, const int32_t* n_samples, int B, long lon
  * by the population standard deviation where it exceeds 0.01 (data.py:28-29); rows t >= frames[b] are set to zero. */
 int dasv_cmn_f32(float* feat, const int32_t* frames, int B, int Tmax, int n_mels, int variance, void* stream);
 
+/* ---------------------------------------------------------------- training-mode tail (scripts/model.py:61-71)
+ * BatchNorm1d with batch statistics (model.py:67): y = (x - mean) * rsqrt(var_biased + eps) * gamma + beta over the batch
+ * dimension of x [B,E]; running_mean / running_var (nullable) are updated in place like torch.nn.BatchNorm1d
+ * (momentum, unbiased variance).  save_mean / save_invstd [E] feed the backward. */
+int dasv_bn1d_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                        float* y, float* save_mean, float* save_invstd, int B, int E, float eps, float momentum, void* stream);
+int dasv_bn1d_train_bwd(const float* dy, const float* x, const float* gamma, const float* save_mean, const float* save_invstd,
+                        float* dx, float* dgamma, float* dbeta, int B, int E, void* stream);
+
+/* AM-Softmax (scripts/loss.py:37-52): costh = normalise(x) @ normalise_columns(W), logits = s * costh - margin_scaled at
+ * [b, label[b]] (margin_scaled = s * m / (1 + alpha), alpha = the annealing term of loss.py:28-35).  x [B,E], W [E,S],
+ * label [B] int64 ON THE DEVICE (the reference scatters the margin on the CPU, loss.py:45-48).  inv_x [B] / inv_w [S]
+ * (inverse norms) are outputs kept for the backward, which takes the gradients at both outputs (either nullable). */
+int dasv_amsoftmax_fwd(const float* x, const float* W, const long long* label, float* costh, float* logits,
+                       float* inv_x, float* inv_w, int B, int E, int S, float s, float margin_scaled, void* stream);
+size_t dasv_amsoftmax_bwd_workspace_bytes(int B, int S);
+int dasv_amsoftmax_bwd(const float* dcosth, const float* dlogits, const float* x, const float* W, const float* costh,
+                       const float* inv_x, const float* inv_w, float* dx, float* dW, void* workspace,
+                       int B, int E, int S, float s, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -400,3 +400,63 @@ def test_data_parallel_replicas_train_the_front_end():
     single.square().sum().backward()
     for n, p in net.front_end.named_parameters():
         assert float((got[n] - p.grad).abs().max()) <= 1e-4 * float(p.grad.abs().max()) + 1e-7, n
+
+
+@pytest.mark.parametrize('B,E,S,m,s_,step,annealing', [(4, 32, 6, 0.4, 30.0, 0, False), (37, 400, 5994, 0.4, 30.0, 0, False),
+                                                      (16, 64, 130, 0.3, 15.0, 5000, True)])
+def test_amsoftmax_kernels_vs_reference_formula(B, E, S, m, s_, step, annealing):
+    """AM-Softmax forward + backward on the package's kernels against scripts/loss.py:37-52 restated in torch ops
+    (oracle/torch_port.am_softmax) and differentiated by autograd: outputs and both gradients at 1e-5."""
+    from oracle import torch_port as tp
+    from doubleattentionspeakerverification_b200 import loss as dasv_loss
+    gen = torch.Generator(device='cuda').manual_seed(B + S)
+    x = torch.randn(B, E, device='cuda', generator=gen)
+    label = torch.randint(0, S, (B,), device='cuda', generator=gen)
+    head = dasv_loss.AMSoftmax(E, S, m=m, s=s_, annealing=annealing).cuda()
+    gl = torch.randn(B, S, device='cuda', generator=gen) / S
+    gc = torch.randn(B, S, device='cuda', generator=gen) / S
+    xk = x.clone().requires_grad_(True)
+    costh, logits = head(xk, label, step)
+    ((logits * gl).sum() + (costh * gc).sum()).backward()
+    xr = x.cpu().double().requires_grad_(True)
+    Wr = head.W.detach().cpu().double().requires_grad_(True)
+    cr, lr = tp.am_softmax(xr, Wr, label.cpu(), m, s_, step, annealing)
+    ((lr * gl.cpu().double()).sum() + (cr * gc.cpu().double()).sum()).backward()
+
+    def close(a, b, tol=1e-5):
+        return float((a.detach().cpu().double() - b.detach()).abs().max()) <= tol * max(float(b.detach().abs().max()), 1e-30)
+    assert close(costh, cr) and close(logits, lr)
+    assert close(xk.grad, xr.grad) and close(head.W.grad, Wr.grad)
+    # only the logits differentiated (train.py:219): the costh gradient is absent, not a zero tensor
+    head.zero_grad()
+    xk2 = x.clone().requires_grad_(True)
+    _, lg2 = head(xk2, label, step)
+    torch.nn.functional.cross_entropy(lg2, label).backward()
+    xr2 = x.cpu().double().requires_grad_(True)
+    Wr2 = head.W.detach().cpu().double().requires_grad_(True)
+    torch.nn.functional.cross_entropy(tp.am_softmax(xr2, Wr2, label.cpu(), m, s_, step, annealing)[1], label.cpu()).backward()
+    assert close(xk2.grad, xr2.grad) and close(head.W.grad, Wr2.grad)
+
+
+@pytest.mark.parametrize('B,E', [(4, 32), (256, 400), (33, 70)])
+def test_bn1d_train_kernels_vs_torch(B, E):
+    """Train-mode BatchNorm1d (model.py:67): outputs, running statistics and all three gradients against torch's own."""
+    from doubleattentionspeakerverification_b200 import model as dasv_model
+    gen = torch.Generator(device='cuda').manual_seed(B)
+    x = torch.relu(torch.randn(B, E, device='cuda', generator=gen)) * 3
+    bn = torch.nn.BatchNorm1d(E).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    g = torch.randn(B, E, device='cuda', generator=gen)
+    xr = x.clone().requires_grad_(True)
+    yr = bn(xr)
+    (yr * g).sum().backward()
+    want = (yr.detach(), xr.grad, bn.weight.grad.clone(), bn.bias.grad.clone(), bn.running_mean.clone(), bn.running_var.clone())
+    bn.zero_grad()
+    xk = x.clone().requires_grad_(True)
+    yk = dasv_model._BN1dTrainFn.apply(xk, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum)
+    (yk * g).sum().backward()
+    got = (yk.detach(), xk.grad, bn.weight.grad, bn.bias.grad, rm, rv)
+    for a, b in zip(got, want):
+        assert float((a - b).abs().max()) <= 2e-5 * max(float(b.abs().max()), 1.0)
