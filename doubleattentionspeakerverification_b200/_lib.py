@@ -74,7 +74,11 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise DasvError('%s is missing: build it with `python -m doubleattentionspeakerverification_b200.build` '
                             '(this package has no CPU or PyTorch fallback)' % LIB_PATH)
-        h = ctypes.CDLL(LIB_PATH)
+        try:
+            h = ctypes.CDLL(LIB_PATH)
+        except OSError:
+            import torch  # noqa: F401  (loads libcudart.so.12, which the library links dynamically)
+            h = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(h, name)      # AttributeError if the library does not export a declared symbol
             fn.restype = res
