@@ -187,20 +187,6 @@ def pack_conv_weight_x3(w):
     return p
 
 
-def conv11_tc(x, w, bias, lengths=None):
-    """Tensor-core conv11: x [B,T,F] f32 -> relu(conv3x3(x) + bias) as NHWC bf16 [B,T,F,Cout]."""
-    x = _f32(x, 'x')
-    B, T, Fq = x.shape
-    w, bias = _f32(w, 'w'), _f32(bias, 'bias')
-    Cout = w.shape[0]
-    with torch.cuda.device(x.device):
-        lengths = _lengths(lengths, B, x.device)
-        y = torch.empty((B, T, Fq, Cout), device=x.device, dtype=torch.bfloat16)
-        rc = _lib.lib().dasv_conv11_tc_bf16(_p(x), _p(w), _p(bias), _p(lengths), _p(y), B, T, Fq, Cout, _stream())
-        _lib.check(rc, 'dasv_conv11_tc_bf16')
-    return y
-
-
 def conv3x3_f32(x, wp, bias, lengths=None):
     """fp32 CUDA-core conv3x3 + bias + ReLU on NHWC; wp from pack_conv_weight_f32."""
     x = _f32(x, 'x')

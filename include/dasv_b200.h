@@ -99,12 +99,6 @@ int dasv_attention_fwd(const void* x, int x_dtype, const int32_t* lengths, const
 int dasv_conv11_direct(const float* x, const float* w, const float* bias, const int32_t* lengths,
                        void* y, int y_dtype, int B, int T, int F, int Cout, void* stream);
 
-/* Same layer on the tensor cores (bf16 NHWC output only): K = 9 becomes K = 32 through bf16 hi/lo splits
- * (w*x ~= wh*xh + wl*xh + wh*xl, fp32-like accuracy), operands built in shared memory by the kernel itself, one
- * tcgen05.mma pair per 128 channels x 256 pixels; bound by the output write instead of the FMA pipe. */
-int dasv_conv11_tc_bf16(const float* x, const float* w, const float* bias, const int32_t* lengths,
-                        void* y, int B, int T, int F, int Cout, void* stream);
-
 /* Weight re-packing (done once per module, cached by the caller):
  *   f32 path : w [Cout,Cin,3,3] f32 -> [9][Cin][Cout] f32
  *   bf16 path: w [Cout,Cin,3,3] f32 -> [Cout_pad][9][Cin] bf16 (K-major A operand for tcgen05;

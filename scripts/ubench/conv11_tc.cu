@@ -1,3 +1,5 @@
+// NOT part of libdasv_b200.so since round 2 (measured slower than the CUDA-core conv11: both are bound by the NHWC write).
+// Kept as a worked example of tcgen05 operands built in shared memory by the kernel itself (K = 9 -> 32 by bf16 hi/lo splits).
 // conv11 (Conv2d(1, Cout, 3, padding 1) + bias + ReLU, scripts/CNNs.py:72) on the tensor cores.
 //
 // The CUDA-core kernel (conv_direct.cu) is FMA-pipe bound: 9.4 GFMA per 256-utterance batch take ~0.7 ms against a
