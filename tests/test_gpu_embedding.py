@@ -78,6 +78,28 @@ def test_embedding_fp32x3(name):
         assert max_rel(ev.cpu().numpy(), g['emb_varlen']) < 1e-4
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_short_and_odd_lengths_equal_per_utterance_runs(precision):
+    """Degenerate lengths in one padded batch (1, 2, 3, 15, 17, 33 frames next to a full one; T not a multiple of the 16x
+    down-sampling): every row equals the batch-1 run of the truncated utterance, and the fp32 rows equal the CPU oracle."""
+    from oracle import torch_port as tp
+    cfg = synth.example_config(kernel_size=512, embedding_size=64, heads_number=16, num_spkrs=3)
+    cfg.precision = precision
+    sd = synth.make_state_dict(cfg, 9)
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), sd).cuda().eval()
+    lengths = [37, 1, 2, 3, 15, 17, 33]
+    x = synth.make_logmel(len(lengths), 37, seed=12)
+    with torch.no_grad():
+        got = net.getEmbedding(dev(x), lengths=dev(np.array(lengths, np.int32)))
+        for b, L in enumerate(lengths):
+            one = net.getEmbedding(dev(x[b:b + 1, :L]))
+            assert min_cosine(one.cpu().numpy(), got[b:b + 1].cpu().numpy()) > 0.99999, (b, L)
+            if precision == 'fp32':
+                want = tp.get_embedding(torch.from_numpy(x[b:b + 1, :L]), tp.as_torch(sd), cfg).numpy()
+                assert max_rel(got[b:b + 1].cpu().numpy(), want) < 1e-4, (b, L)
+    assert bool(torch.isfinite(got).all())
+
+
 def test_embedding_with_fused_first_layer():
     """fuse_first=True (conv11 computed inside conv12's kernel): the same embeddings, bit for bit."""
     g = golden('embed_example_b2.npz')
