@@ -22,6 +22,8 @@
 //     for fp32; B=512: a fixed ~10 us of launch, ramp and tail on top of 33 us of streaming).
 //   * Tried and dropped (round 2): one more ring stage per CTA (80 instead of 64 KB in flight) paid for with a single copy of
 //     the merge scratch and a trailing barrier per utterance: bf16 full 43.1 -> 43.6 us, ragged 38.4 -> 38.9 us.
+//   * Tried and dropped (round 2): ONE 16-warp CTA per SM with a 9-stage ring (all of an SM's bytes in flight for one utterance):
+//     bf16 full 43.1 -> 59.7 us, fp32 68.7 -> 73.9 us -- the end-of-utterance stage idles the whole SM without a second CTA.
 //   * Tried and dropped: cutting the flattened (utterance, frame) stream into equal per-CTA ranges with partial
 //     states + tickets in the workspace (bit-exact, but the per-segment finish -- partial write, fence, ticket, merge,
 //     ~3-4 us -- cost more than the 13 % tail it removed: fp32 83.8 us vs 76.1 us at B=512,T=200,D=1024,H=16).
