@@ -1061,8 +1061,8 @@ extern "C" int dasv_conv3x3_dgrad_bf16(const void* g, const void* wp_rot, const 
 // from there.  Same values as dasv_conv11_direct + dasv_conv3x3_igemm_bf16 (bit-identical), without the 2 x 2.1 GB round trip
 // of the 128-channel tensor.  `scratch`: dasv_conv12_fused_workspace_bytes(C1) bytes, contents irrelevant.
 extern "C" size_t dasv_conv12_fused_workspace_bytes(int C1) {
-    // [2 * SMs] patches of at most (BT+2)(BF+2) <= 520 pixels (BT*BF <= 256) of C1 16-bit channels
-    return static_cast<size_t>(2) * sm_count() * 520 * (C1 > 0 ? C1 : 0) * 2;
+    // [2 * SMs] patches of at most (BT+2)(BF+2) = BT*BF + 2(BT+BF) + 4 <= 256 + 2*257 + 4 = 774 pixels of C1 16-bit channels
+    return static_cast<size_t>(2) * sm_count() * 776 * (C1 > 0 ? C1 : 0) * 2;
 }
 
 extern "C" int dasv_conv12_fused_bf16(const float* x0, const float* w11, const float* b11, const void* wp, const float* bias,
