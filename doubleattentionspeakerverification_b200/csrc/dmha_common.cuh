@@ -66,7 +66,7 @@ struct DmhaFwdParams {
     int B, T, D, H, dh;
     int fps, stages, S;
     float scale_log2;   // log2(e) / sqrt(H): scores are kept in log2 units for ex2.approx
-    int pitch3, rowcopy3; // dmha_fwd3.cu: smem row pitch (bytes), 1 = one bulk copy per frame
+    int pitch3, rowcopy3; // used by scripts/ubench/dmha_fwd3.cu only (warp-MMA variant, no longer part of the library)
     int* ws_cnt;        // dmha_fwd2.cu: utterance counter for the dynamic deal (NULL = static round-robin)
 };
 
@@ -107,8 +107,6 @@ __host__ __device__ inline DmhaFwdSmem dmha_fwd_smem(int D, int H, int dh, int S
 // v2 forward (dmha_fwd2.cu): returns 0 = launched, 1 = error (message set), -1 = shape outside its mapping.
 int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream);
 size_t dmha_fwd2_workspace_bytes(int B, int D, int H);
-// v3 forward for bf16 features (dmha_fwd3.cu, warp-level MMA); same return convention and workspace.
-int dmha_fwd3_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream);
 
 struct DmhaBwdParams {
     const unsigned char* x;

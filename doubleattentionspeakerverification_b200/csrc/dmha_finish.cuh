@@ -1,4 +1,4 @@
-// End-of-utterance stage shared by the DoubleMHA forward kernels (dmha_fwd2.cu, dmha_fwd3.cu): merge the S frame
+// End-of-utterance stage shared by the DoubleMHA forward kernels (dmha_fwd.cu, dmha_fwd2.cu): merge the S frame
 // slots of every head, normalise the context vectors, run the attention over heads (poolings.py:45-51, :61-71) and
 // write out / ctx / lse / headw / the normalised alignment.  Called by all consumer threads after each of them has
 // stored its partial state: pm[h*S+s] (reference max, log2 units), pl[h*S+s] (sum of weights), pacc[(h*S+s)*dh+d]
@@ -84,7 +84,7 @@ DASV_DEVICE void dmha_finish_utterance(const DmhaFwdParams& p, int b, int Lb, in
     named_bar_sync(1, kThreads);   // pacc/pm/u/w are reused by the next utterance
 }
 
-// Same stage with two barriers instead of four (dmha_fwd3.cu): the caller alternates between two copies of the scratch
+// Same stage with two barriers instead of four (dmha_fwd2.cu): the caller alternates between two copies of the scratch
 // buffers (utterance parity), so no trailing barrier is needed before they are reused, and every warp computes the
 // softmax over heads itself instead of waiting for warp 0.  u_sm / w_sm / pm / pl / pacc are the copies of this parity.
 template <int NCW>

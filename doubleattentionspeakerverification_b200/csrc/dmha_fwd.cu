@@ -373,12 +373,6 @@ extern "C" int dasv_dmha_fwd(const void* x, int x_dtype, const int32_t* lengths,
     p.ws_cnt = nullptr;
     p.scale_log2 = kLog2e / sqrtf(static_cast<float>(H));     // d_k = query.size(-1) = H (poolings.py:75)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool bf16 = x_dtype == 1;
-
-    if (bf16) {   // bf16 features: tensor-core dot products (dmha_fwd3.cu); -1 = shape outside its mapping
-        const int r = dmha_fwd3_launch(p, x_dtype, workspace, s);
-        if (r >= 0) return r;
-    }
     {   // v2 mapping (dmha_fwd2.cu): 0 = launched, 1 = error, -1 = shape outside the mapping
         const int r = dmha_fwd2_launch(p, x_dtype, workspace, s);
         if (r >= 0) return r;

@@ -1,3 +1,6 @@
+// NOT part of libdasv_b200.so since round 2: the warp-MMA (mma.sync) bf16 pooling forward measured equal to the CUDA-core kernel
+// (43.4 vs 43.5 us at the microbench shape: both sit on the same launch / ramp / tail floor).  Kept as a worked example of
+// ldmatrix + HMMA with hi/lo split fp32 operands.  To build it again: add dmha_fwd3_launch back to dmha_common.cuh / dmha_fwd.cu.
 // Fused DoubleMHA pooling forward for bf16 features, v3: the per-row dot products and weighted sums go through the
 // warp-level tensor-core path (mma.sync m16n8k16, bf16 x bf16 -> fp32) so that the kernel is bound by HBM, not by
 // instruction issue.  Same semantics and outputs as dmha_fwd2.cu (scripts/poolings.py:73-80, :100-109, :45-51, :61-71,

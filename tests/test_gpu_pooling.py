@@ -196,35 +196,6 @@ def test_dynamic_schedule_is_bit_identical_to_static_deal(monkeypatch):
     assert max_rel(dyn['out'].cpu().numpy(), f['out']) < TOL
 
 
-@pytest.mark.parametrize('B,T,D,H', [(7, 53, 1024, 8), (5, 100, 256, 16), (3, 47, 2048, 32), (4, 16, 128, 4),
-                                     (6, 130, 1536, 24), (300, 37, 512, 16)])
-def test_bf16_tensor_core_path(B, T, D, H, monkeypatch):
-    """The opt-in warp-MMA kernel for bf16 features (dmha_fwd3.cu, DASV_DMHA_MMA=1): same answers as the oracle and as
-    the default CUDA-core kernel, whatever sits in the frames past an utterance's length (NaN included), ragged tiles,
-    empty utterances."""
-    monkeypatch.setenv('DASV_DMHA_MMA', '1')
-    c = synth.make_pooling_case(B, T, D, H, seed=B + T, with_lengths=True)
-    lengths = c['lengths'].copy()
-    lengths[0] = 0 if B > 2 else lengths[0]                       # an empty utterance
-    x = dev(c['x'], torch.bfloat16)
-    xo = x.float().cpu().numpy()
-    q, a, L = dev(c['query']), dev(c['att']), dev(lengths)
-    f = po.dmha_forward(xo[1:], c['query'], c['att'], lengths=lengths[1:])
-    r = ops.dmha_fwd(x, q, a, lengths=L)
-    for k, ko in (('out', 'out'), ('ctx', 'ctx'), ('headw', 'w'), ('align', 'align'), ('lse', 'lse')):
-        assert max_rel(r[k][1:].cpu().numpy(), f[ko]) < TOL, k
-    t = torch.arange(T, device='cuda')[None, :, None]
-    xn = torch.where(t < L[:, None, None], x, torch.full_like(x, float('nan')))
-    rn = ops.dmha_fwd(xn, q, a, lengths=L)
-    monkeypatch.delenv('DASV_DMHA_MMA')
-    rc = ops.dmha_fwd(x, q, a, lengths=L)
-    rcn = ops.dmha_fwd(xn, q, a, lengths=L)
-    for k in ('out', 'ctx', 'lse', 'headw', 'align'):
-        assert torch.equal(rn[k][1:], r[k][1:]), k                  # padding content is never read into the math
-        assert max_rel(r[k][1:].cpu().numpy(), rc[k][1:].cpu().numpy()) < 2e-5, k
-        assert torch.equal(rcn[k][1:], rc[k][1:]), k
-
-
 def test_attention_and_head_attention_train_under_autograd():
     """pooling_method='Attention' (scripts/model.py:35-36) and the stand-alone HeadAttention are trainable: under
     autograd they use torch ops; values equal the forward kernels, gradients flow to input and parameter."""
