@@ -29,7 +29,8 @@ SIGNATURES = {
     'dasv_pack_conv_weight_x3': (_i, [_vp, _vp, _i, _i, _vp]),
     'dasv_conv3x3_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_maxpool2x2': (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    'dasv_conv3x3_igemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'dasv_conv3x3_igemm_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'dasv_conv3x3_igemm_workspace_bytes': (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
     'dasv_conv12_fused_workspace_bytes': (_sz, [_i]),
     'dasv_conv12_fused_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'dasv_conv3x3_dgrad_bf16': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -58,7 +59,7 @@ SIGNATURES = {
 _LIB = None
 
 # kernels launched per successful C call, and the running count bench.py reports as gpu_launches
-KERNELS_PER_CALL = {'dasv_amsoftmax_fwd': 3, 'dasv_amsoftmax_bwd': 4, 'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_bias_grad_bf16': 2, 'dasv_conv11_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
+KERNELS_PER_CALL = {'dasv_conv3x3_igemm_bf16+splitk': 2, 'dasv_amsoftmax_fwd': 3, 'dasv_amsoftmax_bwd': 4, 'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_bias_grad_bf16': 2, 'dasv_conv11_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
 LAUNCHES = {}
 
 

@@ -64,6 +64,11 @@ struct ConvParams {
     const float* b11;        // [Cin] f32
     void* scratch;           // [grid][2][BT+2][BF+2][Cin] 16-bit
     uint32_t fuse_off;       // byte offset of the fused path's shared memory (input patch + barriers) from the barrier block
+    // split-K for launches with too few tiles to fill the SMs (small batches): a tile's K slices are dealt to `splitk` CTAs,
+    // each stores its raw fp32 accumulator to ws [splitk][B*T*F][Cout]; conv_splitk_finish_kernel sums, adds the bias and
+    // applies ReLU / pool / format.  kpc = K slices per split.
+    int splitk, kpc;
+    float* ws;
     int balanced;            // ragged batches: tiles with valid frames are compacted through a per-CTA prefix table so that every
                              // CTA gets the same number of them (and of the all-masked tiles, which only store zeros)
     int RT;                  // pair mode: frames of the patch half one CTA loads (without halo)
@@ -71,11 +76,13 @@ struct ConvParams {
 };
 
 struct ConvTile {
-    int m, f0, t0, b0;
+    int m, f0, t0, b0, split;
 };
 
 DASV_DEVICE ConvTile conv_decode_tile(const ConvParams& p, int tile, int n_mt_eff, int rank) {
     ConvTile c;
+    c.split = 0;
+    if (p.splitk > 1) { c.split = tile % p.splitk; tile /= p.splitk; }      // the K splits of a tile run side by side
     c.m = tile % n_mt_eff;
     if (p.pair) c.m = c.m * 2 + rank;        // a pair owns two adjacent 128-channel tiles
     int pt = tile / n_mt_eff;
@@ -132,6 +139,7 @@ DASV_DEVICE ConvTile conv_tile_at(const ConvParams& p, const ConvSched& sc, int 
     int local = q - (pass == 0 ? sc.vpre[g] : g * per_g - sc.vpre[g]);
     const int vt = (sc.vpre[g + 1] - sc.vpre[g]) / sc.per_t;
     ConvTile c;
+    c.split = 0;
     c.m = local % n_mt_eff;
     if (p.pair) c.m = c.m * 2 + rank;
     local /= n_mt_eff;
@@ -200,7 +208,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                  // 0 = leader of the CTA pair
     const int n_mt_eff = PAIR ? p.n_mt / 2 : p.n_mt;
-    const int n_tiles = n_mt_eff * p.n_ft * p.n_tt * p.n_bt;
+    const int n_tiles = n_mt_eff * p.n_ft * p.n_tt * p.n_bt * (p.splitk > 1 ? p.splitk : 1);
     const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int ksteps = 9 * p.kchunks;
@@ -260,7 +268,9 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (tile_masked) continue;
                 const int slot = static_cast<int>(blockIdx.x) * 2 + static_cast<int>(fit & 1u);    // FUSE11: this tile's scratch patch
                 if (FUSE11) { mbar_wait(&s_full[fit & 1u], (fit >> 1) & 1u); ++fit; }
-                for (int kc = 0; kc < p.kchunks; ++kc) {
+                const int kc0 = p.splitk > 1 ? c.split * p.kpc : 0;
+                const int kc1 = p.splitk > 1 ? min(p.kchunks, kc0 + p.kpc) : p.kchunks;
+                for (int kc = kc0; kc < kc1; ++kc) {
                     const int kcx = kc >= p.kcx_wrap ? kc - p.kcx_wrap : kc;     // activation slice of this K slice
                     for (int dxi = 0; dxi < 3; ++dxi) {
                         mbar_wait(&empty[sb], bph ^ 1u);
@@ -336,7 +346,8 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int n_hi = p.kcx_wrap >> 1;                       // split mode: K slices [0, n_hi) are hi*hi
                 uint32_t firstj[2] = {1u, 1u};
                 if (p.reuse) {
-                    for (int g = 0; g < 3 * p.kchunks; ++g) {           // (slice, dx) groups
+                    const int n_groups = 3 * (p.splitk > 1 ? min(p.kchunks, (c.split + 1) * p.kpc) - c.split * p.kpc : p.kchunks);
+                    for (int g = 0; g < n_groups; ++g) {                // (slice, dx) groups
                         const uint32_t jacc = (X3 && g / 3 >= n_hi) ? 1u : 0u;
                         const uint32_t d_tmem = d_tmem0 + jacc * static_cast<uint32_t>(p.Npad);
                         uint32_t first = firstj[jacc];
@@ -524,6 +535,31 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tcol = tmem_base + lane_addr + as * static_cast<uint32_t>(p.Npad);
             }
             const float bias = (n_ok && p.bias != nullptr) ? p.bias[n] : 0.f;
+
+            if (p.splitk > 1) {
+                // split-K: this CTA's partial sums go to the workspace as they are ([pixel][Cout] fp32: a warp's 32 channels
+                // are one 128-byte run); the finishing kernel adds the splits.  The halves take alternate 16-column groups.
+                float* wsp = p.ws + static_cast<size_t>(c.split) * p.B * T * F * Cout;
+                for (int cg0 = half * 16; cg0 < p.Npad; cg0 += 32) {
+                    uint32_t r[16];
+                    tmem_ld_x16(tcol + cg0, r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = cg0 + j;
+                        const int bb = col / UC, rem = col - bb * UC;
+                        const int tl = rem / BF, fl = rem - tl * BF;
+                        const int b = c.b0 + bb, t = c.t0 + tl;
+                        if (bb < p.BB && tl < BT && b < p.B && t < T && n_ok)
+                            wsp[((static_cast<size_t>(b) * T + t) * F + c.f0 + fl) * Cout + n] = __uint_as_float(r[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[acc_it & 1u]);
+                ++acc_it;
+                continue;
+            }
 
             if (p.ref_layout) {
                 // pooled[b, t2, n*F2 + f2] = relu(max over the valid 2x2 window + bias)   (feature = c*F' + f, CNNs.py:88-89)
@@ -728,6 +764,59 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
+// Second half of a split-K launch: y = format(relu(max over the pool window (sum over splits of ws) + bias)).
+// ws [S][B,T,F,Cout] fp32; a thread owns 4 channels of one output pixel.  ACT: 0 = fp32, 1 = bf16, 2 = fp16 output.
+template <int ACT>
+__global__ void __launch_bounds__(256)
+conv_splitk_finish_kernel(const float* __restrict__ ws, int S, const float* __restrict__ bias, void* __restrict__ y,
+                          int B, int T, int F, int Cout, int pool, int ref, int relu) {
+    griddep_launch();
+    griddep_wait();
+    const int OT = pool ? (T + 1) / 2 : T, OF = pool ? F / 2 : F, C4 = Cout / 4;
+    const size_t total = static_cast<size_t>(B) * OT * OF * C4;
+    const size_t split_stride = static_cast<size_t>(B) * T * F * Cout;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c4 = static_cast<int>(i % C4);
+        size_t r = i / C4;
+        const int fo = static_cast<int>(r % OF); r /= OF;
+        const int to = static_cast<int>(r % OT);
+        const int b = static_cast<int>(r / OT);
+        const int t0 = pool ? 2 * to : to, f0 = pool ? 2 * fo : fo;
+        const int nt = pool ? ((t0 + 1 < T) ? 2 : 1) : 1, nf = pool ? 2 : 1;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int dt = 0; dt < nt; ++dt)
+            for (int df = 0; df < nf; ++df) {
+                const float* src = ws + ((static_cast<size_t>(b) * T + t0 + dt) * F + f0 + df) * Cout + c4 * 4;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int sidx = 0; sidx < S; ++sidx) {              // fixed order: deterministic
+                    const float4 v = *reinterpret_cast<const float4*>(src + sidx * split_stride);
+                    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                }
+                m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
+            }
+        const float4 bv = *reinterpret_cast<const float4*>(bias + c4 * 4);
+        float o[4] = {m.x + bv.x, m.y + bv.y, m.z + bv.z, m.w + bv.w};
+        if (relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+        }
+        if (ref) {                                              // [B,T',C*F'] with feature index c*F'+f (CNNs.py:88-89)
+            const size_t row = (static_cast<size_t>(b) * OT + to) * (static_cast<size_t>(Cout) * OF);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const size_t idx = row + static_cast<size_t>(c4 * 4 + e) * OF + fo;
+                if (ACT == 0) static_cast<float*>(y)[idx] = o[e];
+                else static_cast<uint16_t*>(y)[idx] = cvt16_bits<ACT == 0 ? 1 : ACT>(o[e]);
+            }
+        } else {
+            const size_t idx = ((static_cast<size_t>(b) * OT + to) * OF + fo) * Cout + c4 * 4;
+            if (ACT == 0) *reinterpret_cast<float4*>(static_cast<float*>(y) + idx) = make_float4(o[0], o[1], o[2], o[3]);
+            else *reinterpret_cast<uint2*>(static_cast<uint16_t*>(y) + idx) =
+                     make_uint2(pack16<ACT == 0 ? 1 : ACT>(o[0], o[1]), pack16<ACT == 0 ? 1 : ACT>(o[2], o[3]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- host side
 struct ConvPlan {
     int BF, BT, BB, N, Npad;
@@ -738,7 +827,8 @@ struct ConvPlan {
 // MMA costs Npad/2 tensor cycles; the SM can ingest ~64 B/clk from L2 (measured: every layer plateaus at
 // ~15 TB/s chip-wide; layers needing > 55 B/clk already lose tensor time), so a step also costs its operand bytes / 52.  `halo` = 2 in tap-row reuse mode (patches carry
 // +-1 frame and utterances inside a patch are separated by 2 halo rows of accumulator columns).
-static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged, int nmax = 256, int bbmax = 1 << 30) {
+static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int halo, bool pair, int sms, bool ragged, int nmax = 256, int bbmax = 1 << 30,
+                          int ksplit = 1) {
     // Cin here = the contraction depth per tap (3 * Cin in split mode)
     ConvPlan best{0, 0, 0, 0, 0, 1e300};
     const double ksteps = 9.0 * Cin / 16.0;
@@ -766,13 +856,13 @@ static ConvPlan conv_plan(int B, int T, int F, int Cin, int Cout, bool pool, int
                 // tiles are dealt to the SMs (or SM pairs) in whole waves: with few tiles (small batches) a smaller patch
                 // that fills more SMs wins even though each of its MMAs is less efficient
                 const int n_mt = (Cout + kConvTileM - 1) / kConvTileM;
-                const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB) * (pair ? n_mt / 2 : n_mt);
+                const double tiles = static_cast<double>(F / BF) * n_tt * ((B + BB - 1) / BB) * (pair ? n_mt / 2 : n_mt) * ksplit;
                 const double units = pair ? sms / 2 : sms;
                 const double waves = ceil(tiles / units);
                 const double ingest = (128.0 + b_rows) * 32.0 / 52.0;                   // bytes per 16-deep step / ~52 B/clk effective
                 double step = Npad / 2.0 > ingest ? Npad / 2.0 : ingest;
                 if (step < 40.0) step = 40.0;                                           // issue + operand-fetch floor of one MMA
-                double cost = waves * (step * ksteps + 700.0);
+                double cost = waves * (step * ksteps / ksplit + 700.0);
                 // ragged batches: the tile that straddles an utterance's end computes rows that are masked afterwards
                 // (half a tile height per utterance on average, against ~3/4 of the padded length in valid rows)
                 if (ragged) cost *= 1.0 + (0.5 * BT) / (0.75 * T + 1.0);
@@ -800,7 +890,7 @@ struct ConvEntry {
     ConvKey key;
     CUtensorMap tmA, tmB;
     ConvParams p;
-    size_t smem;
+    size_t smem, ws_bytes;
     int grid, pair;
     unsigned long long stamp;
 };
@@ -873,6 +963,22 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
             if (ok && (n + 15) / 16 * 16 <= nmax) pl = ConvPlan{bf, bt, bb, n, (n + 15) / 16 * 16, 0.0};
         }
     }
+    // split-K (small batches): when the best plan leaves most SMs idle, deal the K slices of every tile to several CTAs and
+    // finish in a second, streaming kernel.  Compared through the same cost model (+ the finishing pass).
+    int splitk = 1, kpc = Kc / kConvKC;
+    if (reuse && !x3 && !fused && !k.ragged && (flags & 1) && !k.env_plan[0] && Cout % 4 == 0 && !getenv("DASV_CONV_NOSPLITK") && pl.N != 0) {
+        const int kch = Kc / kConvKC;
+        double best = pl.cost;
+        for (int sreq = 2; sreq <= 16 && sreq <= kch; sreq *= 2) {
+            const int kp = (kch + sreq - 1) / sreq, seff = (kch + kp - 1) / kp;
+            if (seff < 2) continue;
+            ConvPlan ps = conv_plan(B, T, F, Kc, Cout, pool, 2, false, sms, false, nmax, 1 << 30, seff);
+            if (ps.N == 0) continue;
+            // finishing pass: the partials are written and read once (L2-resident at these sizes), ~64 B/clk per SM, + a launch
+            const double fin = 4000.0 + 2.0 * seff * static_cast<double>(B) * T * F * Cout * 4.0 / (64.0 * sms);
+            if (ps.cost + fin < 0.8 * best) { best = ps.cost + fin; pl = ps; splitk = seff; kpc = kp; pair = 0; }
+        }
+    }
     if (pl.N == 0) { set_error("conv3x3_igemm_bf16: no patch shape for T=%d F=%d", T, F); return 1; }
     const int pair_rt = pl.BB == 1 ? pl.BT / 2 : pl.BT;           // frames per CTA half in pair mode
     const int box_t = pair ? pair_rt + 2 : pl.BT + (reuse ? 2 : 0);
@@ -913,6 +1019,8 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     p.relu = (flags & 1) ? 1 : 0;
     p.w_f16 = (flags & 16) ? 1 : 0; p.x_f16 = (flags & 32) ? 1 : 0;
     p.balanced = (k.ragged && p.n_bt <= kConvMaxGroups && !getenv("DASV_CONV_UNBALANCED")) ? 1 : 0;
+    p.splitk = splitk; p.kpc = kpc;
+    en.ws_bytes = splitk > 1 ? static_cast<size_t>(splitk) * B * T * F * Cout * sizeof(float) : 0;
     p.reuse = reuse;
     p.gap_cols = pair ? (pl.BB == 2 ? pl.Npad / 2 - pl.BT * pl.BF : 0) : (reuse ? 2 * pl.BF : 0);
     p.pair = pair; p.RT = pair_rt; p.split_t = pl.BB == 1;
@@ -948,9 +1056,9 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     while (cols < 2u * pl.Npad) cols <<= 1;
     p.tmem_cols = cols;
     if (getenv("DASV_CONV_DEBUG"))
-        fprintf(stderr, "conv plan: B=%d T=%d F=%d Cin=%d Cout=%d pool=%d reuse=%d pair=%d BF=%d BT=%d BB=%d N=%d Npad=%d stages=%d sa=%d stage_bytes=%u b_bytes=%u\n",
-                B, T, F, Cin, Cout, (int)pool, reuse, pair, pl.BF, pl.BT, pl.BB, pl.N, pl.Npad, p.stages, p.sa, p.stage_bytes, p.b_bytes);
-    const long long n_tiles = static_cast<long long>(pair ? p.n_mt / 2 : p.n_mt) * p.n_ft * p.n_tt * p.n_bt;
+        fprintf(stderr, "conv plan: B=%d T=%d F=%d Cin=%d Cout=%d pool=%d reuse=%d pair=%d BF=%d BT=%d BB=%d N=%d Npad=%d stages=%d sa=%d stage_bytes=%u b_bytes=%u splitk=%d\n",
+                B, T, F, Cin, Cout, (int)pool, reuse, pair, pl.BF, pl.BT, pl.BB, pl.N, pl.Npad, p.stages, p.sa, p.stage_bytes, p.b_bytes, splitk);
+    const long long n_tiles = static_cast<long long>(pair ? p.n_mt / 2 : p.n_mt) * p.n_ft * p.n_tt * p.n_bt * splitk;
     if (n_tiles > 0x7fffffffLL) { set_error("conv3x3_igemm_bf16: too many tiles"); return 1; }
     en.smem = static_cast<size_t>(p.stages) * p.stage_bytes + static_cast<size_t>(p.sa) * kConvABytes + kFixed;
     en.grid = pair ? 2 * static_cast<int>(n_tiles < sms / 2 ? n_tiles : sms / 2) : static_cast<int>(n_tiles < sms ? n_tiles : sms);
@@ -966,8 +1074,9 @@ struct ConvFront {            // the fused first layer's own operands (flags bit
 
 static int conv_igemm_launch(const void* x, const void* wp, const float* bias, const int32_t* lengths, const void* mask,
                              void* y, int y_dtype, int flags,
-                             int B, int T, int F, int Cin, int Cout, void* stream, const ConvFront* front = nullptr) {
-    if (!x || !wp || !y) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
+                             int B, int T, int F, int Cin, int Cout, void* stream, const ConvFront* front = nullptr,
+                             void* workspace = nullptr, size_t* ws_query = nullptr) {
+    if (!ws_query && (!x || !wp || !y)) { set_error("conv3x3_igemm_bf16: null argument"); return 1; }
     if (Cin % kConvKC != 0 || Cin <= 0) { set_error("conv3x3_igemm_bf16: Cin=%d must be a positive multiple of 64", Cin); return 1; }
     if (Cout <= 0 || Cout % 8 != 0) { set_error("conv3x3_igemm_bf16: Cout=%d must be a positive multiple of 8", Cout); return 1; }
     if (F <= 0 || F % 2 != 0 || F > 256) { set_error("conv3x3_igemm_bf16: F=%d must be even and <= 256", F); return 1; }
@@ -986,7 +1095,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     if ((flags & 64) && ((flags & 48) || !(flags & 1))) { set_error("conv3x3_igemm_bf16: the split (fp32x3) mode is bf16, forward only"); return 1; }
     if (!(flags & 1) && (flags & 48)) { set_error("conv3x3_igemm_bf16: the input-gradient pass is bf16 only"); return 1; }
     if (B <= 0 || T <= 0) return 0;
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15)) {
+    if (!ws_query && ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15))) {
         set_error("conv3x3_igemm_bf16: x and wp must be 16-byte aligned"); return 1;
     }
     ConvKey k;
@@ -999,9 +1108,17 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     if (const char* e = getenv("DASV_CONV_SB")) k.env_sb = atoi(e);
     if (const char* e = getenv("DASV_CONV_PLAN")) strncpy(k.env_plan, e, sizeof(k.env_plan) - 1);
 
+    if (ws_query) {                                              // workspace size of this shape: the plan alone (dummy addresses for the maps)
+        static __align__(128) unsigned char dummy[128];
+        k.x = dummy; k.wp = dummy;
+        ConvEntry en;
+        if (conv_build_entry(en, k)) return 1;
+        *ws_query = en.ws_bytes;
+        return 0;
+    }
     CUtensorMap tmA, tmB;
     ConvParams p;
-    size_t smem; int grid, pair;
+    size_t smem, ws_bytes; int grid, pair;
     {
         std::lock_guard<std::mutex> lock(g_conv_mu);
         ConvEntry* hit = nullptr;
@@ -1020,8 +1137,13 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
             hit = &g_conv_cache[slot];
         }
         hit->stamp = ++g_conv_clock;
-        tmA = hit->tmA; tmB = hit->tmB; p = hit->p; smem = hit->smem; grid = hit->grid; pair = hit->pair;
+        tmA = hit->tmA; tmB = hit->tmB; p = hit->p; smem = hit->smem; grid = hit->grid; pair = hit->pair; ws_bytes = hit->ws_bytes;
     }
+    if (ws_bytes && !workspace) {
+        set_error("conv3x3_igemm_bf16: this shape runs split-K and needs a workspace of %zu bytes (dasv_conv3x3_igemm_workspace_bytes)", ws_bytes);
+        return 1;
+    }
+    p.ws = static_cast<float*>(workspace);
     p.bias = bias; p.lengths = lengths; p.y = y; p.mask = mask;
     if (front) { p.x0 = front->x0; p.w11 = front->w11; p.b11 = front->b11; p.scratch = const_cast<void*>(x); }
 
@@ -1040,14 +1162,41 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_variant(variant), tmA, tmB, p);
     if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: launch failed: %s", cudaGetErrorString(e)); return 1; }
+    if (p.splitk > 1) {                                          // second half: sum the splits, bias, ReLU, pool, format
+        const size_t total = static_cast<size_t>(B) * (p.pool ? (T + 1) / 2 : T) * (p.pool ? F / 2 : F) * (Cout / 4);
+        size_t blocks = (total + 255) / 256;
+        const size_t cap = static_cast<size_t>(sm_count()) * 8;
+        if (blocks > cap) blocks = cap;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int relu = p.relu, pool = p.pool, ref = p.ref_layout;
+        if (p.y_f32) e = launch_pdl(conv_splitk_finish_kernel<0>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st,
+                                    static_cast<const float*>(p.ws), p.splitk, bias, y, B, T, F, Cout, pool, ref, relu);
+        else if (act == 2) e = launch_pdl(conv_splitk_finish_kernel<2>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st,
+                                          static_cast<const float*>(p.ws), p.splitk, bias, y, B, T, F, Cout, pool, ref, relu);
+        else e = launch_pdl(conv_splitk_finish_kernel<1>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st,
+                            static_cast<const float*>(p.ws), p.splitk, bias, y, B, T, F, Cout, pool, ref, relu);
+        if (e != cudaSuccess) { set_error("conv3x3_igemm_bf16: finishing launch failed: %s", cudaGetErrorString(e)); return 1; }
+    }
     return check_launch("conv3x3_igemm_bf16");
 }
 
 extern "C" int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, const int32_t* lengths,
                                        void* y, int y_dtype, int flags,
-                                       int B, int T, int F, int Cin, int Cout, void* stream) {
+                                       int B, int T, int F, int Cin, int Cout, void* workspace, void* stream) {
     if (!bias) { set_error("conv3x3_igemm_bf16: null bias"); return 1; }
-    return conv_igemm_launch(x, wp, bias, lengths, nullptr, y, y_dtype, flags, B, T, F, Cin, Cout, stream);
+    return conv_igemm_launch(x, wp, bias, lengths, nullptr, y, y_dtype, flags, B, T, F, Cin, Cout, stream, nullptr, workspace);
+}
+
+// Bytes of `workspace` a call with these arguments needs: 0 except for shapes with so few tiles that the launch is split
+// along K (small batches), where the partial sums of the splits pass through it.
+extern "C" size_t dasv_conv3x3_igemm_workspace_bytes(int y_dtype, int flags, int has_lengths, int B, int T, int F, int Cin, int Cout) {
+    size_t bytes = 0;
+    static const int32_t some_lengths = 0;
+    if (B <= 0 || T <= 0) return 0;
+    if (conv_igemm_launch(nullptr, nullptr, nullptr, has_lengths ? &some_lengths : nullptr, nullptr, nullptr, y_dtype, flags,
+                          B, T, F, Cin, Cout, nullptr, nullptr, nullptr, &bytes))
+        return 0;
+    return bytes;
 }
 
 extern "C" int dasv_conv3x3_dgrad_bf16(const void* g, const void* wp_rot, const void* relu_mask, const int32_t* lengths,

@@ -242,13 +242,20 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
         if ref_layout and out_dtype != torch.float32:
             out_dtype = x.dtype
         y = torch.empty(shape, device=x.device, dtype=out_dtype if ref_layout else x.dtype)
-        rc = _lib.lib().dasv_conv3x3_igemm_bf16(_p(x), _p(wp), _p(_f32(bias, 'bias')), _p(lengths), _p(y), _dtype_code(y, 'y'),
-                                                flags, B, T, Fq, Cin, Cout, _stream())
-        _lib.check(rc, 'dasv_conv3x3_igemm_bf16')
+        L = _lib.lib()
+        key = (_dtype_code(y, 'y'), flags, lengths is not None, B, T, Fq, Cin, Cout, x.device.index)
+        nws = _conv_ws_bytes.get(key)
+        if nws is None:                                      # > 0 only for small batches, which run split along K
+            nws = _conv_ws_bytes[key] = int(L.dasv_conv3x3_igemm_workspace_bytes(key[0], flags, int(key[2]), B, T, Fq, Cin, Cout))
+        ws = torch.empty((nws,), device=x.device, dtype=torch.uint8) if nws else None
+        rc = L.dasv_conv3x3_igemm_bf16(_p(x), _p(wp), _p(_f32(bias, 'bias')), _p(lengths), _p(y), key[0],
+                                       flags, B, T, Fq, Cin, Cout, _p(ws), _stream())
+        _lib.check(rc, 'dasv_conv3x3_igemm_bf16+splitk' if nws else 'dasv_conv3x3_igemm_bf16')
     return y
 
 
 _scratch_cache = {}
+_conv_ws_bytes = {}
 
 
 def conv12_fused(x, w11, b11, wp, bias, Cout, lengths=None, pool=True, act_dtype=torch.bfloat16):

@@ -142,7 +142,11 @@ int dasv_maxpool2x2(const void* x, int x_dtype, void* y, int y_dtype, int ref_la
  * (x, wp, shape, flags), and the launch is a programmatic dependent of the stream's previous kernel. */
 int dasv_conv3x3_igemm_bf16(const void* x, const void* wp, const float* bias, const int32_t* lengths,
                             void* y, int y_dtype, int flags,
-                            int B, int T, int F, int Cin, int Cout, void* stream);
+                            int B, int T, int F, int Cin, int Cout, void* workspace, void* stream);
+/* Small batches: a launch whose tiles would leave most SMs idle is split along K (every tile's K slices are dealt to
+ * several CTAs, partial sums pass through `workspace`, a second streaming kernel adds them and applies bias / ReLU /
+ * pool / format; deterministic).  Bytes of `workspace` needed for these arguments (0 = not split; NULL is then fine): */
+size_t dasv_conv3x3_igemm_workspace_bytes(int y_dtype, int flags, int has_lengths, int B, int T, int F, int Cin, int Cout);
 
 /* conv11 + conv12 of the front-end in ONE kernel (CNNs.py:72-74): x0 [B,T,F] f32, w11 [C1,1,3,3] f32, b11 [C1] f32, then
  * exactly dasv_conv3x3_igemm_bf16 on relu(conv11(x0) + b11) with wp [Cout][9][C1], bias, lengths, y, y_dtype, flags

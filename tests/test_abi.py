@@ -51,7 +51,7 @@ def test_error_reporting_without_gpu(library):
     rc = library.dasv_dmha_fwd(None, 0, None, None, None, None, None, None, None, None, None, None, 1, 1, 64, 8, None)
     assert rc != 0 and b'null' in library.dasv_last_error()
     assert library.dasv_dmha_fwd(None, 0, None, None, None, None, None, None, None, None, None, None, 0, 1, 64, 8, None) == 0   # empty batch
-    rc = library.dasv_conv3x3_igemm_bf16(1, 1, 1, None, 1, 1, 1, 1, 8, 80, 60, 64, None)
+    rc = library.dasv_conv3x3_igemm_bf16(1, 1, 1, None, 1, 1, 1, 1, 8, 80, 60, 64, None, None)
     assert rc != 0 and b'multiple of 64' in library.dasv_last_error()
     assert library.dasv_dmha_bwd_workspace_bytes(4, 10, 256, 8) == 4 * (256 + 32) * 4
     assert library.dasv_packed_conv_weight_bf16_elems(64, 128) == 128 * 9 * 128
