@@ -884,7 +884,8 @@ struct ConvKey {
     const void* x; const void* wp;
     int B, T, F, Cin, Cout, flags, y_dtype, dgrad, dev;   // flags include the operand-format bits
     int env_reuse, env_pair, env_sb, ragged;   // ragged: lengths given (the plan then prefers low tiles)
-    char env_plan[20];
+    int env_nosplit;                           // DASV_CONV_NOSPLITK=1: never split along K (bit-identical results at every batch size)
+    char env_plan[16];
 };
 struct ConvEntry {
     ConvKey key;
@@ -966,7 +967,7 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     // split-K (small batches): when the best plan leaves most SMs idle, deal the K slices of every tile to several CTAs and
     // finish in a second, streaming kernel.  Compared through the same cost model (+ the finishing pass).
     int splitk = 1, kpc = Kc / kConvKC;
-    if (reuse && !x3 && !fused && !k.ragged && (flags & 1) && !k.env_plan[0] && Cout % 4 == 0 && !getenv("DASV_CONV_NOSPLITK") && pl.N != 0) {
+    if (reuse && !x3 && !fused && !k.ragged && (flags & 1) && !k.env_plan[0] && Cout % 4 == 0 && !k.env_nosplit && pl.N != 0) {
         const int kch = Kc / kConvKC;
         double best = pl.cost;
         for (int sreq = 2; sreq <= 16 && sreq <= kch; sreq *= 2) {
@@ -1103,6 +1104,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     k.x = x; k.wp = wp; k.B = B; k.T = T; k.F = F; k.Cin = Cin; k.Cout = Cout; k.flags = flags; k.y_dtype = y_dtype;
     if (cudaGetDevice(&k.dev) != cudaSuccess) { set_error("conv3x3_igemm_bf16: no current device"); cudaGetLastError(); return 1; }
     k.env_reuse = 1; k.env_pair = -1; k.env_sb = 0; k.ragged = lengths != nullptr;
+    if (const char* e = getenv("DASV_CONV_NOSPLITK")) k.env_nosplit = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_REUSE")) k.env_reuse = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_PAIR")) k.env_pair = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_SB")) k.env_sb = atoi(e);
@@ -1193,6 +1195,7 @@ extern "C" size_t dasv_conv3x3_igemm_workspace_bytes(int y_dtype, int flags, int
     size_t bytes = 0;
     static const int32_t some_lengths = 0;
     if (B <= 0 || T <= 0) return 0;
+    cudaFree(nullptr);                                          // the plan needs the driver (tensor-map encoder): make sure the runtime is up
     if (conv_igemm_launch(nullptr, nullptr, nullptr, has_lengths ? &some_lengths : nullptr, nullptr, nullptr, y_dtype, flags,
                           B, T, F, Cin, Cout, nullptr, nullptr, nullptr, &bytes))
         return 0;

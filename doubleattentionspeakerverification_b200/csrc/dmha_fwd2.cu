@@ -395,9 +395,16 @@ int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t
     const bool bf16 = x_dtype == 1;
     const uint32_t stage_bytes = static_cast<uint32_t>(p2.fps) * p.D * (bf16 ? 2 : 4);
     size_t smem = dmha2_smem(p.D, p.H, p.dh, p2.S, p2.stages, stage_bytes).total;
-    // keep two CTAs per SM when a shallower ring allows it
-    if (!getenv("DASV_DMHA_STAGES"))
-        while (smem > 113 * 1024 && p2.stages > 3) smem = dmha2_smem(p.D, p.H, p.dh, p2.S, --p2.stages, stage_bytes).total;
+    // keep two CTAs per SM when a shallower ring allows it -- unless there are no more utterances than SMs: then a CTA has the SM
+    // to itself and the ring is as deep as shared memory allows (a lone CTA streams at bytes-in-flight / latency)
+    if (!getenv("DASV_DMHA_STAGES")) {
+        if (p.B <= sm_count()) {
+            p2.stages = 8;
+            smem = dmha2_smem(p.D, p.H, p.dh, p2.S, p2.stages, stage_bytes).total;
+            while (smem > 220 * 1024 && p2.stages > 3) smem = dmha2_smem(p.D, p.H, p.dh, p2.S, --p2.stages, stage_bytes).total;
+        }
+        else while (smem > 113 * 1024 && p2.stages > 3) smem = dmha2_smem(p.D, p.H, p.dh, p2.S, --p2.stages, stage_bytes).total;
+    }
     while (smem > 227 * 1024 && p2.stages > 2) smem = dmha2_smem(p.D, p.H, p.dh, p2.S, --p2.stages, stage_bytes).total;
     if (smem > 227 * 1024) return -1;
     p.fps = p2.fps; p.stages = p2.stages; p.S = p2.S;

@@ -16,7 +16,7 @@ namespace dasv {
 // Between the layers the relu(fc1) slices are exchanged through distributed shared memory (each CTA stores its slice
 // into every CTA of the cluster) and one cluster barrier.
 constexpr int kTailCL = 8;            // CTAs per cluster (portable maximum)
-constexpr int kTailKS = 4;            // k slices per column (threads = 64 column lanes x kTailKS)
+constexpr int kTailKS = 16;           // k slices per column (threads = 64 column lanes x kTailKS): the loads are latency-bound, so many short chains
 constexpr int kTailThreads = 64 * kTailKS;
 
 template <int UB>

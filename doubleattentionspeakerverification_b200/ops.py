@@ -2,6 +2,8 @@
 current CUDA stream, check the status code.  No arithmetic happens here and nothing falls back to
 PyTorch or the CPU: a tensor that is not on a CUDA device is an error.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -243,7 +245,7 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
             out_dtype = x.dtype
         y = torch.empty(shape, device=x.device, dtype=out_dtype if ref_layout else x.dtype)
         L = _lib.lib()
-        key = (_dtype_code(y, 'y'), flags, lengths is not None, B, T, Fq, Cin, Cout, x.device.index)
+        key = (_dtype_code(y, 'y'), flags, lengths is not None, B, T, Fq, Cin, Cout, x.device.index, os.environ.get('DASV_CONV_NOSPLITK'))
         nws = _conv_ws_bytes.get(key)
         if nws is None:                                      # > 0 only for small batches, which run split along K
             nws = _conv_ws_bytes[key] = int(L.dasv_conv3x3_igemm_workspace_bytes(key[0], flags, int(key[2]), B, T, Fq, Cin, Cout))
