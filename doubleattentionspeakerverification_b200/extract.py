@@ -390,18 +390,21 @@ def _gather_shards(local, plan, N, device, group, embedding_size):
 
 
 class HostPipeline:
-    """Double-buffered host -> device -> host streaming of fixed-shape batches: the H2D copy of batch i+1 runs on a
-    copy stream while batch i is being embedded on the compute stream, and the embeddings return to pinned host
-    memory asynchronously.  Usage:  pipe = HostPipeline(embed_fn, (B, T, F), E, device);  pipe.submit(x_pinned, out_pinned)
-    per batch, then pipe.finish().  ``embed_fn(x_dev) -> [B, E]``; an optional ``post(emb)`` hook runs on the compute
-    stream between the extraction and the D2H copy (e.g. the NCCL all-gather)."""
+    """Double-buffered host -> device -> host streaming of fixed-shape batches: the H2D copy of batch i+1 runs on a copy
+    stream while batch i is being embedded on the compute stream, and what follows the extraction -- an optional
+    ``post(emb)`` hook (e.g. the NCCL all-gather) and the D2H copy of the embeddings into pinned host memory -- runs on a
+    third stream, so the kernels of batch i+1 never wait for a collective (which is also a rendezvous with the slowest
+    rank) or a copy of batch i.  Usage:  pipe = HostPipeline(embed_fn, (B, T, F), E, device);
+    pipe.submit(x_pinned, out_pinned) per batch, then pipe.finish().  ``embed_fn(x_dev) -> [B, E]``."""
 
     def __init__(self, embed_fn, shape, embedding_size, device, post=None):
         self.embed_fn, self.post, self.device = embed_fn, post, torch.device(device)
         self.stage = [torch.empty(shape, device=self.device, dtype=torch.float32) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.out_stream = torch.cuda.Stream(device=self.device)
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.embedded = torch.cuda.Event()
         self.i = 0
 
     def submit(self, x_host, out_host):
@@ -415,14 +418,18 @@ class HostPipeline:
         compute.wait_event(self.copied[k])
         emb = self.embed_fn(self.stage[k])
         self.consumed[k].record(compute)
-        if self.post is not None:
-            emb = self.post(emb)
-        out_host.copy_(emb, non_blocking=True)
+        self.embedded.record(compute)
+        with torch.cuda.stream(self.out_stream):
+            self.out_stream.wait_event(self.embedded)
+            emb.record_stream(self.out_stream)
+            out = emb if self.post is None else self.post(emb)
+            out_host.copy_(emb, non_blocking=True)
         self.i += 1
-        return emb
+        return out
 
     def finish(self):
         torch.cuda.current_stream(self.device).synchronize()
+        self.out_stream.synchronize()
 
 
 def score_trial_list(emb, trials, device=None):
