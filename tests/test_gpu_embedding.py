@@ -100,6 +100,39 @@ def test_short_and_odd_lengths_equal_per_utterance_runs(precision):
     assert bool(torch.isfinite(got).all())
 
 
+def test_graph_replay_matches_eager_and_follows_weight_updates():
+    """Fixed-shape inference calls replay a CUDA graph per input shape (model.py): same embeddings as the eager launches,
+    across more shapes than graphs are kept, and re-captured when a parameter or a running statistic changes."""
+    cfg = synth.example_config(kernel_size=512, embedding_size=64, heads_number=16, num_spkrs=3)
+    cfg.precision = 'bf16'
+    net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, 21)).cuda().eval()
+    xs = [dev(synth.make_logmel(B, T, seed=B + T)) for B, T in ((2, 40), (3, 40), (2, 56), (5, 33))]
+    with torch.no_grad():
+        net.use_graphs = False
+        want = [net.getEmbedding(x) for x in xs]
+        net.use_graphs = True
+        for rep in range(4):                                         # capture happens on the third call of a shape
+            for x, w in zip(xs, want):
+                assert torch.equal(net.getEmbedding(x), w)
+        assert 1 <= len(net._graphs) <= net.max_graphs
+        # other data through a captured shape
+        x2 = dev(synth.make_logmel(2, 40, seed=99))
+        net.use_graphs = False
+        w2 = net.getEmbedding(x2)
+        net.use_graphs = True
+        for _ in range(3):
+            assert torch.equal(net.getEmbedding(x2), w2)
+        # a weight update and a running-statistics update must invalidate the captured graphs
+        net.front_end.conv22.weight.mul_(1.25)
+        net.b2.running_mean.add_(0.1)
+        net.use_graphs = False
+        w3 = net.getEmbedding(x2)
+        net.use_graphs = True
+        for _ in range(4):
+            assert torch.equal(net.getEmbedding(x2), w3)
+        assert not torch.equal(w3, w2)
+
+
 def test_embedding_with_fused_first_layer():
     """fuse_first=True (conv11 computed inside conv12's kernel): the same embeddings, bit for bit."""
     g = golden('embed_example_b2.npz')
