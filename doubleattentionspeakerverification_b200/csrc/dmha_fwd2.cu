@@ -136,13 +136,16 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
 
     if (warp == kDmhaConsumerWarps) {
         if (lane == 0) {                            // producer: HBM -> SMEM ring, one linear bulk copy per stage
+            // the first utterance of a CTA is its own index (no round trip to the counter, and its length -- an input of the
+            // call, never written by a kernel that lets its dependents start early -- is fetched while the previous kernel
+            // still runs); the counter hands out the utterances from gridDim.x on
+            int b = static_cast<int>(blockIdx.x);
+            int Lnext = (p.lengths && b < p.B) ? p.lengths[b] : T;
             griddep_wait();
             int st = 0;
             uint32_t ph = 0;
-            int b = p.ws_cnt ? atomicAdd(p.ws_cnt, 1) : static_cast<int>(blockIdx.x);
             while (b < p.B) {
-                int Lb = p.lengths ? p.lengths[b] : T;
-                Lb = max(0, min(Lb, T));
+                int Lb = max(0, min(Lnext, T));
                 const unsigned char* xb = p.x + static_cast<size_t>(b) * T * frame_bytes;
                 int f0 = 0;
                 do {                                // an empty utterance still gets one (empty) stage so that it is finished
@@ -159,7 +162,8 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
                     if (++st == p.stages) { st = 0; ph ^= 1u; }
                     f0 += p.fps;
                 } while (f0 < Lb);
-                b = p.ws_cnt ? atomicAdd(p.ws_cnt, 1) : b + static_cast<int>(gridDim.x);
+                b = p.ws_cnt ? static_cast<int>(gridDim.x) + atomicAdd(p.ws_cnt, 1) : b + static_cast<int>(gridDim.x);
+                if (b < p.B) Lnext = p.lengths ? p.lengths[b] : T;
             }
             mbar_wait(&empty[st], ph ^ 1u);         // terminator stage
             meta[st] = Dmha2Stage{-1, 0, 0, 0};
