@@ -100,6 +100,28 @@ def test_short_and_odd_lengths_equal_per_utterance_runs(precision):
     assert bool(torch.isfinite(got).all())
 
 
+@pytest.mark.parametrize('B,T', [(1, 1), (1, 2), (2, 5), (1, 15), (3, 16), (1, 3001)])
+def test_extreme_input_lengths(B, T):
+    """One-frame inputs up to a 30 s utterance (T' = 188), unpadded, against the CPU oracle: fp32 1e-4; bf16 cosine 0.9995
+    (a K = 512 random-init model with one or two pooled frames: 0.99987 measured at T = 16; the 0.9999 bar is held on the
+    exampleModel config)."""
+    from oracle import torch_port as tp
+    cfg = synth.example_config(kernel_size=512, embedding_size=64, heads_number=16, num_spkrs=3)
+    sd = synth.make_state_dict(cfg, 4)
+    x = synth.make_logmel(B, T, seed=T) if T > 1 else (2.0 * np.random.RandomState(1).standard_normal((B, 1, 80))).astype(np.float32)
+    want = tp.get_embedding(torch.from_numpy(x), tp.as_torch(sd), cfg).numpy()
+    for precision in ('fp32', 'bf16'):
+        cfg.precision = precision
+        net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), sd).cuda().eval()
+        with torch.no_grad():
+            got = net.getEmbedding(dev(x)).cpu().numpy()
+        assert got.shape == want.shape and np.isfinite(got).all()
+        if precision == 'fp32':
+            assert max_rel(got, want) < 1e-4, (precision, B, T)
+        else:
+            assert min_cosine(got, want) >= 0.9995, (precision, B, T)
+
+
 def test_graph_replay_matches_eager_and_follows_weight_updates():
     """Fixed-shape inference calls replay a CUDA graph per input shape (model.py): same embeddings as the eager launches,
     across more shapes than graphs are kept, and re-captured when a parameter or a running statistic changes."""
