@@ -300,6 +300,8 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
     // still has several CTAs per SM; small launches keep 8 so that they spread over the SMs
     int R = kC11Rows;
     while (R < 32 && static_cast<long long>(B) * ((T + 2 * R - 1) / (2 * R)) >= 8LL * sm_count()) R *= 2;
+    // ... and fewer when the launch would leave SMs idle (one utterance: 50 CTAs of 8 frames are FMA-bound at 11 us; 400 of 1 frame: see profiles/r2_b1_layers.txt)
+    while (R > 1 && static_cast<long long>(B) * ((T + R - 1) / R) < 2LL * sm_count()) R /= 2;
     size_t smem = static_cast<size_t>(R + 2) * (F + 2) * sizeof(float);
     while (smem > 48 * 1024 && R > 1) { R /= 2; smem = static_cast<size_t>(R + 2) * (F + 2) * sizeof(float); }
     if (smem > 48 * 1024) { set_error("conv11_direct: F=%d too wide", F); return 1; }
