@@ -52,6 +52,7 @@ SIGNATURES = {
     'dasv_amsoftmax_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_float, _c.c_float, _vp]),
     'dasv_amsoftmax_bwd_workspace_bytes': (_sz, [_i, _i]),
     'dasv_amsoftmax_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_float, _vp]),
+    'dasv_h2d_segments': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'dasv_logmel_f32': (_i, [_vp, _vp, _i, _c.c_longlong, _vp, _i, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _vp, _i, _vp]),
     'dasv_cmn_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
@@ -59,7 +60,8 @@ SIGNATURES = {
 _LIB = None
 
 # kernels launched per successful C call, and the running count bench.py reports as gpu_launches
-KERNELS_PER_CALL = {'dasv_conv3x3_igemm_bf16+splitk': 2, 'dasv_amsoftmax_fwd': 3, 'dasv_amsoftmax_bwd': 4, 'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_bias_grad_bf16': 2, 'dasv_conv11_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3}
+KERNELS_PER_CALL = {'dasv_conv3x3_igemm_bf16+splitk': 2, 'dasv_amsoftmax_fwd': 3, 'dasv_amsoftmax_bwd': 4, 'dasv_dmha_bwd': 2, 'dasv_conv3x3_wgrad_bf16': 2, 'dasv_bias_grad_bf16': 2, 'dasv_conv11_bwd': 2, 'dasv_attention_fwd': 3, 'dasv_cosine_matrix': 3,
+                    'dasv_h2d_segments': 0}     # copies, not kernels
 LAUNCHES = {}
 
 

@@ -4,6 +4,7 @@ PyTorch or the CPU: a tensor that is not on a CUDA device is an error.
 """
 import os
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -328,6 +329,23 @@ def cosine_matrix(enrol, test):
         ws = torch.empty((Ne + Nt,), device=enrol.device, dtype=torch.float32)
         _lib.check(_lib.lib().dasv_cosine_matrix(_p(enrol), _p(test), _p(scores), _p(ws), Ne, Nt, E, _stream()), 'dasv_cosine_matrix')
     return scores
+
+
+def h2d_segments(dst, src_host, src_off, dst_off, nbytes):
+    """``len(nbytes)`` host->device copies on the current stream (one cudaMemcpyAsync each, issued from C): segment i =
+    ``nbytes[i]`` bytes from byte ``src_off[i]`` of the (pinned) host tensor ``src_host`` to byte ``dst_off[i]`` of ``dst``."""
+    _dev(dst, 'dst')
+    if src_host.is_cuda or not src_host.is_contiguous() or not dst.is_contiguous():
+        raise _lib.DasvError('h2d_segments: src_host must be a contiguous host tensor, dst a contiguous device tensor')
+    so, do, nb = (np.ascontiguousarray(a, dtype=np.int64) for a in (src_off, dst_off, nbytes))
+    if not (so.shape == do.shape == nb.shape) or so.ndim != 1:
+        raise _lib.DasvError('h2d_segments: the offset / size arrays must be 1-D and equally long')
+    if len(nb) and (int((so + nb).max()) > src_host.numel() * src_host.element_size() or int((do + nb).max()) > dst.numel() * dst.element_size()
+                    or int(min(so.min(), do.min(), nb.min())) < 0):
+        raise _lib.DasvError('h2d_segments: a segment lies outside its buffer')
+    with torch.cuda.device(dst.device):
+        rc = _lib.lib().dasv_h2d_segments(_p(dst), src_host.data_ptr(), so.ctypes.data, do.ctypes.data, nb.ctypes.data, len(nb), _stream())
+        _lib.check(rc, 'dasv_h2d_segments')
 
 
 def threshold_counts(scores, thresholds):

@@ -258,6 +258,14 @@ int dasv_amsoftmax_bwd(const float* dcosth, const float* dlogits, const float* x
                        const float* inv_x, const float* inv_w, float* dx, float* dW, void* workspace,
                        int B, int E, int S, float s, void* stream);
 
+/* ---------------------------------------------------------------- host-side helper of the variable-length extractor
+ * (the reference embeds one utterance per call, scripts/train.py:117-133; the extractor batches them): n host->device
+ * copies on `stream`, one cudaMemcpyAsync each -- segment i = nbytes[i] bytes from (char*)src_host + src_off[i] to
+ * (char*)dst + dst_off[i].  src_host should be pinned (the copies then overlap the kernels of other streams); the three
+ * offset/size arrays are HOST arrays, read before the call returns. */
+int dasv_h2d_segments(void* dst, const void* src_host, const long long* src_off, const long long* dst_off,
+                      const long long* nbytes, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,13 @@ def timed(fn, iters=ITERS, graph=True):
     return e0.elapsed_time(e1) / (iters * per) * 1e3        # us
 
 total = 0.0
+# calibration: the fixed cost of a launch in these loops (a one-CTA conv11, a one-tile tensor-core conv)
+xt = torch.randn(1, 2, 2, device='cuda', generator=g)
+wt = torch.randn(128, 1, 3, 3, device='cuda', generator=g); bt = torch.zeros(128, device='cuda')
+print(f'one-CTA conv11 launch      {timed(lambda: ops.conv11_direct(xt, wt, bt, out_dtype=torch.bfloat16)):7.2f} us')
+xq = torch.randn(1, 2, 4, 64, device='cuda', generator=g).to(torch.bfloat16)
+wq = ops.pack_conv_weight_bf16(torch.randn(128, 64, 3, 3, device='cuda', generator=g))
+print(f'one-tile igemm conv launch {timed(lambda: ops.conv3x3_igemm_bf16(xq, wq, bt, 128)):7.2f} us   (K = 576: 36 MMAs)')
 x0 = torch.randn(B, 400, 80, device='cuda', generator=g)
 w0 = torch.randn(128, 1, 3, 3, device='cuda', generator=g); b0 = torch.zeros(128, device='cuda')
 us = timed(lambda: ops.conv11_direct(x0, w0, b0, out_dtype=torch.bfloat16)); total += us
@@ -42,7 +49,23 @@ for name, T, F, Cin, Cout, pool, ref in layers:
     fl = 2.0 * B * T * F * Cout * 9 * Cin
     print(f'{name}  {us:7.2f} us   floor {fl / 1.4e15 * 1e6:5.2f} us   weights {wp.numel() * 2 / 1e6:5.1f} MB')
 print(f'sum of conv kernels {total:.1f} us')
+# pooling (B x 50 x 10240 reference-layout fp32... the step feeds it what conv42 wrote) and the FC/BN tail, alone
 cfg = synth.example_config(); cfg.precision = 'bf16'
+net0 = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, 1234)).cuda().eval()
+enc = torch.randn(B, 25, 5120, device='cuda', generator=g)
+pl = net0.poolingLayer
+with torch.no_grad():
+    for dt in (torch.float32, torch.bfloat16):
+        e = enc.to(dt)
+        us = timed(lambda: pl.pooled(e))
+        print(f'pooling {str(dt)[6:]:9s} {us:7.2f} us   ({e.numel() * e.element_size() / 1e6:.2f} MB)')
+    pooled = pl.pooled(enc)
+    tp = net0._tail_params()
+    print(f'fc tail           {timed(lambda: ops.fc_tail(pooled, *tp)):7.2f} us')
+    xin = torch.randn(B, 400, 80, device='cuda'); xst = torch.empty_like(xin)
+    print(f'input copy        {timed(lambda: xst.copy_(xin)):7.2f} us')
+del net0
+
 net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, 1234)).cuda().eval()
 xs = torch.from_numpy(synth.make_logmel(B, 400, seed=1)).cuda()
 with torch.no_grad():

@@ -410,3 +410,41 @@ def test_eer_sweep_matches_reference_golden():
     th = np.arange(-1, 1, 0.01)
     cnt = ops.threshold_counts(dev(sc), th).cpu().numpy()
     assert np.array_equal(cnt, np.array([np.sum(sc.astype(np.float64) >= t) for t in th]))
+
+
+def test_h2d_segments_and_packed_batches():
+    """The extractor's scatter of pinned utterances into a batch buffer (dasv_h2d_segments) and the batches built from it."""
+    from doubleattentionspeakerverification_b200 import extract, ops
+    rs = np.random.RandomState(3)
+    src = torch.from_numpy(rs.randn(1000, 80).astype(np.float32)).pin_memory()
+    lens = np.array([7, 120, 1, 33, 250])
+    offs = np.array([10, 400, 0, 950 - 33, 600])
+    dst = torch.zeros((int(lens.sum()) + 5, 80), device='cuda')
+    starts = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    ops.h2d_segments(dst, src, offs * 320, starts * 320, lens * 320)
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    for o, s, n in zip(offs, starts, lens):
+        assert np.array_equal(got[s:s + n], src.numpy()[o:o + n])
+    assert not got[int(lens.sum()):].any()
+    with pytest.raises(Exception, match='outside'):
+        ops.h2d_segments(dst, src, np.array([999 * 320]), np.array([0]), np.array([2 * 320]))
+    with pytest.raises(Exception, match='outside'):
+        ops.h2d_segments(dst, src, np.array([0]), np.array([int(lens.sum()) * 320]), np.array([6 * 320]))
+    # the packed extractor hands embed_fn exactly the padded batches of the plan, in any batch order
+    feats = [rs.randn(int(n), 80).astype(np.float32) for n in (40, 17, 64, 33, 5, 50)]
+    packed = extract.PackedUtterances(feats)
+    seen = []
+
+    def fake_embed(x, L):
+        seen.append((x.clone(), L.clone()))
+        return torch.stack([x[i, :int(L[i])].sum(0)[:4] for i in range(x.shape[0])])
+
+    out = extract.extract_local_packed(fake_embed, packed, np.arange(6), 'cuda', max_frames=130, min_ratio=0.4)
+    want = np.stack([f.sum(0)[:4] for f in feats])
+    assert np.allclose(out.cpu().numpy(), want, atol=1e-4)
+    assert len(seen) >= 2
+    for x, L in seen:
+        for i in range(x.shape[0]):
+            n = int(L[i])
+            assert any(f.shape[0] == n and np.array_equal(x[i, :n].cpu().numpy(), f) for f in feats)
