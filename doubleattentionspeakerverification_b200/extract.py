@@ -335,7 +335,7 @@ def extract_local_audio(embed_fn, waves, indices, sfr, device, max_samples=256 *
         emb = embed_fn(feat, frames)
         if out is None:
             out = torch.empty((len(indices), emb.shape[1]), device=emb.device, dtype=emb.dtype)
-        out[torch.from_numpy(b).to(emb.device)] = emb
+        out[_to_device_async(b, emb.device)] = emb
     return out
 
 
@@ -483,8 +483,8 @@ def score_trial_list(emb, trials, device=None):
 
 def score_cross(emb, enrol_idx, test_idx):
     """Cross-product scoring: ``[len(enrol_idx), len(test_idx)]`` cosine matrix."""
-    e = emb[torch.as_tensor(np.asarray(enrol_idx), device=emb.device)].contiguous()
-    t = emb[torch.as_tensor(np.asarray(test_idx), device=emb.device)].contiguous()
+    e = emb[_to_device_async(np.asarray(enrol_idx, np.int64), emb.device)].contiguous()
+    t = emb[_to_device_async(np.asarray(test_idx, np.int64), emb.device)].contiguous()
     return utils.score_matrix(e, t)
 
 
