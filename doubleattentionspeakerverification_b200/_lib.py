@@ -53,6 +53,7 @@ SIGNATURES = {
     'dasv_amsoftmax_bwd_workspace_bytes': (_sz, [_i, _i]),
     'dasv_amsoftmax_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _c.c_float, _vp]),
     'dasv_h2d_segments': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    'dasv_debug_conv_trace': (_i, [_vp]),
     'dasv_logmel_f32': (_i, [_vp, _vp, _i, _c.c_longlong, _vp, _i, _i, _vp, _vp, _i, _c.c_float, _c.c_float, _vp, _i, _vp]),
     'dasv_cmn_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }

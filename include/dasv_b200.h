@@ -258,6 +258,12 @@ int dasv_amsoftmax_bwd(const float* dcosth, const float* dlogits, const float* x
                        const float* inv_x, const float* inv_w, float* dx, float* dW, void* workspace,
                        int B, int E, int S, float s, void* stream);
 
+/* Debugging aid: the conv3x3_igemm launches that follow write eight %globaltimer stamps (ns) per CTA into
+ * buf[blockIdx.x * 8 + i] (0 CTA start, 1 set-up done, 2 previous kernel of the stream finished, 3 first operands landed,
+ * 4 last MMA issued, 5 first accumulator complete, 6 epilogue done, 7 CTA end); buf = device memory for 8 * 148 * 2 values,
+ * NULL (the default) switches the stamps off.  Process-wide, not for concurrent use. */
+int dasv_debug_conv_trace(unsigned long long* buf);
+
 /* ---------------------------------------------------------------- host-side helper of the variable-length extractor
  * (the reference embeds one utterance per call, scripts/train.py:117-133; the extractor batches them): n host->device
  * copies on `stream`, one cudaMemcpyAsync each -- segment i = nbytes[i] bytes from (char*)src_host + src_off[i] to
