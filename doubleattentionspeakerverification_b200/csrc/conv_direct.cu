@@ -5,6 +5,7 @@
 //   * weight re-packing for both conv paths.
 // Activations are NHWC [B,T,F,C]; rows t >= lengths[b] are written as zero.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace dasv {
 
@@ -300,8 +301,10 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
     // still has several CTAs per SM; small launches keep 8 so that they spread over the SMs
     int R = kC11Rows;
     while (R < 32 && static_cast<long long>(B) * ((T + 2 * R - 1) / (2 * R)) >= 8LL * sm_count()) R *= 2;
-    // ... and fewer when the launch would leave SMs idle (one utterance: 50 CTAs of 8 frames are FMA-bound at 11 us; 400 of 1 frame: see profiles/r2_b1_layers.txt)
-    while (R > 1 && static_cast<long long>(B) * ((T + R - 1) / R) < 2LL * sm_count()) R /= 2;
+    // ... and fewer when the launch would leave SMs idle: about 200 CTAs is the optimum for 1-8 utterances of 4 s (measured,
+    // scripts/ubench/c11_rows.py: one utterance 11.3 us with 8 frames per CTA, 7.8 us with 2, 9.5 us with 1)
+    while (R > 1 && static_cast<long long>(B) * ((T + R - 1) / R) < (4LL * sm_count()) / 3) R /= 2;
+    if (const char* e = getenv("DASV_C11_ROWS")) { const int v = atoi(e); if (v >= 1 && v <= 32) R = v; }   // tuning override
     size_t smem = static_cast<size_t>(R + 2) * (F + 2) * sizeof(float);
     while (smem > 48 * 1024 && R > 1) { R /= 2; smem = static_cast<size_t>(R + 2) * (F + 2) * sizeof(float); }
     if (smem > 48 * 1024) { set_error("conv11_direct: F=%d too wide", F); return 1; }

@@ -68,6 +68,10 @@ struct DmhaFwdParams {
     float scale_log2;   // log2(e) / sqrt(H): scores are kept in log2 units for ex2.approx
     int pitch3, rowcopy3; // used by scripts/ubench/dmha_fwd3.cu only (warp-MMA variant, no longer part of the library)
     int* ws_cnt;        // dmha_fwd2.cu: utterance counter for the dynamic deal (NULL = static round-robin)
+    // dmha_fwd2.cu, head split (small batches): an utterance is cut into hs groups of H heads; B, H, D describe the
+    // pseudo-utterances (B = utterances x hs), ldx is the row pitch of x and Hq the row pitch of query, in elements.
+    // hs <= 1: off (ldx = D, Hq = H).
+    int hs, ldx, Hq;
 };
 
 // The dynamic deal's workspace: [0] next utterance, [1] CTAs that have left.  The caller provides it zeroed; the last CTA

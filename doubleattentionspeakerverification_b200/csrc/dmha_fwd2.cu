@@ -139,14 +139,16 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
             // the first utterance of a CTA is its own index (no round trip to the counter, and its length -- an input of the
             // call, never written by a kernel that lets its dependents start early -- is fetched while the previous kernel
             // still runs); the counter hands out the utterances from gridDim.x on
+            const int hs = p.hs > 1 ? p.hs : 1;     // head split: pseudo-utterance b = head group b % hs of utterance b / hs
+            const size_t row_bytes = hs > 1 ? static_cast<size_t>(p.ldx) * ES : frame_bytes;
             int b = static_cast<int>(blockIdx.x);
-            int Lnext = (p.lengths && b < p.B) ? p.lengths[b] : T;
+            int Lnext = (p.lengths && b < p.B) ? p.lengths[b / hs] : T;
             griddep_wait();
             int st = 0;
             uint32_t ph = 0;
             while (b < p.B) {
                 int Lb = max(0, min(Lnext, T));
-                const unsigned char* xb = p.x + static_cast<size_t>(b) * T * frame_bytes;
+                const unsigned char* xb = p.x + static_cast<size_t>(b / hs) * T * row_bytes + static_cast<size_t>(b % hs) * frame_bytes;
                 int f0 = 0;
                 do {                                // an empty utterance still gets one (empty) stage so that it is finished
                     const int nf = min(p.fps, Lb - f0);
@@ -155,7 +157,13 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
                     if (nf > 0) {
                         const uint32_t bytes = static_cast<uint32_t>(nf) * frame_bytes;
                         mbar_arrive_expect_tx(&full[st], bytes);
-                        bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
+                        if (hs == 1) {
+                            bulk_g2s(ring + st * stage_bytes, xb + static_cast<size_t>(f0) * frame_bytes, bytes, &full[st]);
+                        } else {                        // this head group's slice of every frame: one copy per row
+                            for (int r = 0; r < nf; ++r)
+                                bulk_g2s(ring + st * stage_bytes + static_cast<uint32_t>(r) * frame_bytes,
+                                         xb + static_cast<size_t>(f0 + r) * row_bytes, frame_bytes, &full[st]);
+                        }
                     } else {
                         mbar_arrive(&full[st]);
                     }
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
                     f0 += p.fps;
                 } while (f0 < Lb);
                 b = p.ws_cnt ? static_cast<int>(gridDim.x) + atomicAdd(p.ws_cnt, 1) : b + static_cast<int>(gridDim.x);
-                if (b < p.B) Lnext = p.lengths ? p.lengths[b] : T;
+                if (b < p.B) Lnext = p.lengths ? p.lengths[b / hs] : T;
             }
             mbar_wait(&empty[st], ph ^ 1u);         // terminator stage
             meta[st] = Dmha2Stage{-1, 0, 0, 0};
@@ -176,7 +184,8 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
     // ---------------------------------------------------------------- consumers (the producer is already streaming)
     for (int i = tid; i < D; i += kDmhaConsumerThreads) {
         const int h = i / dh, d = i - h * dh;
-        q_sm[i] = p.query[d * H + h];               // reference layout [dh, H] (poolings.py:90)
+        q_sm[i] = p.hs > 1 ? p.query[d * p.Hq + static_cast<int>(blockIdx.x % p.hs) * H + h]   // this CTA's head group (static deal)
+                           : p.query[d * H + h];    // reference layout [dh, H] (poolings.py:90)
     }
     if (p.att != nullptr)
         for (int i = tid; i < dh; i += kDmhaConsumerThreads) a_sm[i] = p.att[i];
@@ -315,6 +324,50 @@ __global__ void __launch_bounds__(kDmhaThreads, dmha_fwd2_min_ctas<BF16, NV>()) 
     }
 }
 
+// The attention over heads (poolings.py:45-51, :61-71) as its own small kernel, for launches that split the heads of an
+// utterance over several CTAs: u[h] = <ctx[b,h,:], att> (-inf where keep == 0), headw = softmax_h(u), out = sum_h headw ctx.
+// One CTA per utterance; the operation order is dmha_finish_utterance2's.
+__global__ void __launch_bounds__(256) dmha_heads_kernel(const float* __restrict__ ctx, const float* __restrict__ att,
+                                                         const uint8_t* __restrict__ keep, float* __restrict__ out,
+                                                         float* __restrict__ headw, int H, int dh) {
+    extern __shared__ float hs_sm[];              // u[H], w[H]
+    float* u_sm = hs_sm;
+    float* w_sm = hs_sm + H;
+    griddep_launch();
+    griddep_wait();
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* cb = ctx + static_cast<size_t>(b) * H * dh;
+    for (int h = warp; h < H; h += 8) {
+        float dot = 0.f;
+        for (int d = lane; d < dh; d += 32) dot = fmaf(cb[h * dh + d], att[d], dot);
+        dot = warp_sum(dot);
+        if (lane == 0) {
+            const bool kept = keep == nullptr || keep[static_cast<size_t>(b) * H + h] != 0;       // poolings.py:42
+            u_sm[h] = kept ? dot : -INFINITY;
+        }
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int h = lane; h < H; h += 32) mx = fmaxf(mx, u_sm[h]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int h = lane; h < H; h += 32) sum += expf(u_sm[h] - mx);          // all heads dropped -> NaN, as in the reference
+    sum = warp_sum(sum);
+    if (warp == 0)
+        for (int h = lane; h < H; h += 32) {
+            const float w = expf(u_sm[h] - mx) / sum;
+            w_sm[h] = w;
+            if (headw != nullptr) headw[static_cast<size_t>(b) * H + h] = w;
+        }
+    __syncthreads();
+    if (out != nullptr)
+        for (int d = tid; d < dh; d += 256) {
+            float o = 0.f;
+            for (int h = 0; h < H; ++h) o = fmaf(w_sm[h], cb[h * dh + d], o);                     // poolings.py:68-69
+            out[static_cast<size_t>(b) * dh + d] = o;
+        }
+}
+
 // ---------------------------------------------------------------------------------- host side
 struct DmhaPlan2 { int ok, G, NV, S, fps, stages, FB, ragged; };
 
@@ -393,7 +446,37 @@ size_t dmha_fwd2_workspace_bytes(int B, int D, int H) {
     return B > 0 ? 256 : 0;          // the utterance counter (padded)
 }
 
+static int dmha_fwd2_launch_plan(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream);
+
 int dmha_fwd2_launch(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream) {
+    const bool bf16 = x_dtype == 1;
+    p.hs = 1; p.ldx = p.D; p.Hq = p.H;
+    // Small batches: one CTA streams its utterance at what ONE SM can ingest (~90 GB/s: a 4 s utterance of the exampleModel,
+    // 512 KB, took 17 us at batch 1).  The heads are independent until the attention over heads, so an utterance is cut into hs
+    // head groups that stream on hs SMs; the attention over heads follows as a small second kernel over ctx.
+    if (p.ctx != nullptr && p.align == nullptr && !getenv("DASV_DMHA_NOSPLIT")) {
+        const size_t utt_bytes = static_cast<size_t>(p.T) * p.D * (bf16 ? 2 : 4);
+        int hs = 8;
+        while (hs > 1 && (p.H % hs != 0 || static_cast<long long>(p.B) * hs > sm_count() || utt_bytes / hs < 32 * 1024 ||
+                          !dmha_make_plan2(x_dtype, p.T, p.D / hs, p.H / hs).ok)) hs >>= 1;
+        if (hs > 1 && utt_bytes >= 128 * 1024) {
+            DmhaFwdParams q = p;
+            q.hs = hs; q.ldx = p.D; q.Hq = p.H;
+            q.B = p.B * hs; q.H = p.H / hs; q.D = p.D / hs;
+            q.att = nullptr; q.keep = nullptr; q.out = nullptr; q.headw = nullptr;      // the kernel stops at ctx / lse
+            const int r = dmha_fwd2_launch_plan(q, x_dtype, nullptr, stream);          // static deal: CTA i owns pseudo-utterance i
+            if (r != 0) return r;
+            if (p.att == nullptr) return 0;
+            cudaError_t e = launch_pdl(dmha_heads_kernel, dim3(p.B), dim3(256), static_cast<size_t>(2 * p.H) * sizeof(float), stream,
+                                       static_cast<const float*>(p.ctx), p.att, p.keep, p.out, p.headw, p.H, p.dh);
+            if (e != cudaSuccess) { set_error("dmha_fwd: heads kernel launch failed: %s", cudaGetErrorString(e)); return 1; }
+            return check_launch("dmha_fwd");
+        }
+    }
+    return dmha_fwd2_launch_plan(p, x_dtype, workspace, stream);
+}
+
+static int dmha_fwd2_launch_plan(DmhaFwdParams p, int x_dtype, void* workspace, cudaStream_t stream) {
     DmhaPlan2 p2 = dmha_make_plan2(x_dtype, p.T, p.D, p.H);
     if (!p2.ok) return -1;
     const bool bf16 = x_dtype == 1;
