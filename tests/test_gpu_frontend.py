@@ -225,7 +225,10 @@ def test_conv12_fused_equals_separate_kernels(B, T, F, C1, Cout, pool, act, with
                                                         (1, 50, 10, 512, 1024, False, False, torch.bfloat16),
                                                         (1, 100, 20, 256, 512, False, False, torch.float16),
                                                         (2, 101, 20, 512, 512, True, False, torch.bfloat16),
-                                                        (1, 37, 40, 256, 264, True, False, torch.bfloat16)])
+                                                        (1, 37, 40, 256, 264, True, False, torch.bfloat16),
+                                                        (4, 7, 10, 1024, 1024, True, True, torch.bfloat16),      # several utterances per patch
+                                                        (3, 5, 20, 512, 512, False, False, torch.bfloat16),
+                                                        (5, 9, 4, 1024, 256, True, False, torch.float16)])
 def test_igemm_split_k_small_batches(B, T, F, Cin, Cout, pool, ref, dt):
     """Launches with too few tiles for the SMs run split along K (partials through a workspace + a finishing kernel):
     same results as the oracle, and the shapes here really take that path."""

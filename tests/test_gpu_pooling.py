@@ -216,3 +216,29 @@ def test_attention_and_head_attention_train_under_autograd():
     with torch.no_grad():
         out2, w2 = ha(h.detach(), keep=keep)
     assert max_rel(out.detach().cpu().numpy(), out2.cpu().numpy()) < 1e-5 and h.grad is not None
+
+
+@pytest.mark.parametrize('B,T,D,H', [(4, 25, 5120, 32), (2, 30, 10240, 32), (3, 50, 2048, 16), (1, 64, 1024, 8), (18, 25, 5120, 32)])
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+def test_head_split_small_batches(B, T, D, H, dtype, monkeypatch):
+    """Small batches without an alignment output cut every utterance into head groups that stream on separate SMs, and run the
+    attention over heads as a second kernel over ctx: same results as the one-CTA-per-utterance launch and as the oracle."""
+    c = synth.make_pooling_case(B, T, D, H, seed=B * 100 + T, with_lengths=True)
+    x = dev(c['x'], torch.bfloat16 if dtype == 'bf16' else None)
+    xo = x.float().cpu().numpy()
+    q, a = dev(c['query']), dev(c['att'])
+    for lengths, keep in ((None, None), (c['lengths'], None), (c['lengths'], c['keep'])):
+        kw = dict(lengths=None if lengths is None else dev(lengths), keep=None if keep is None else dev(keep), need_align=False)
+        monkeypatch.delenv('DASV_DMHA_NOSPLIT', raising=False)
+        r = ops.dmha_fwd(x, q, a, **kw)
+        monkeypatch.setenv('DASV_DMHA_NOSPLIT', '1')
+        r1 = ops.dmha_fwd(x, q, a, **kw)
+        f = po.dmha_forward(xo, c['query'], c['att'], lengths=lengths, keep=keep)
+        for k, ko in (('out', 'out'), ('ctx', 'ctx'), ('headw', 'w'), ('lse', 'lse')):
+            assert max_rel(r[k].cpu().numpy(), f[ko]) < TOL, k
+            assert max_rel(r[k].cpu().numpy(), r1[k].cpu().numpy()) < TOL, k
+        assert r['align'] is None
+    monkeypatch.delenv('DASV_DMHA_NOSPLIT', raising=False)
+    ctx_o, _, _ = po.mha_forward(xo, c['query'], c['lengths'])
+    r = ops.dmha_fwd(x, q, None, lengths=dev(c['lengths']), need_align=False)         # MultiHeadAttention-only mode: no heads kernel
+    assert r['out'] is None and max_rel(r['ctx'].cpu().numpy(), ctx_o) < TOL
