@@ -202,6 +202,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-dmha', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary measurements (training step, feature extraction, other precisions)')
+    ap.add_argument('--pairs', action='store_true', help='A/B: pooled layers with >= 256 input channels on CTA pairs (cta_group::2), the default until late in round 2')
     ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs[3] (2-20 s ragged) and configs[4] (1 M trials)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -227,6 +228,7 @@ def main():
     cfg = synth.example_config()
     cfg.precision = args.precision
     net = synth.load_state_dict(model.SpeakerClassifier(cfg, dev), synth.make_state_dict(cfg, 1234)).to(dev).eval()
+    net.front_end.use_pairs = bool(args.pairs)
     Bn = args.batch
     xs = [torch.from_numpy(synth.make_logmel(Bn, FRAMES, seed=100 + rank * 7 + i)).to(dev) for i in range(2)]
     x_host = torch.from_numpy(synth.make_logmel(Bn, FRAMES, seed=300 + rank)).pin_memory()

@@ -67,6 +67,7 @@ class _VGG(nn.Module):
         # warps (tensor pipe 71 % -> 54 % active): 2.38 ms against 0.77 + 1.78 ms for the two kernels, and no gain per step
         # under the power cap (profiles/r2_fused_conv12_summary.txt).
         self.fuse_first = False
+        self.use_pairs = False           # pooled layers on CTA pairs (cta_group::2); see _forward_kernels
         self._packed = {}
 
     # ---------------------------------------------------------------- weight packing cache
@@ -185,9 +186,12 @@ class _VGG(nn.Module):
                     h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk], wk), c.bias, c.out_channels, L, x3=x3)
                 c = getattr(self, self._names[2 * blk + 1])
                 last = blk == nblocks - 1
-                # CTA pairs (cta_group::2) measured faster on the pooled layers with >= 256 input channels (conv22 +3 %,
-                # conv32 +9 %, conv42 +1 %) and slower elsewhere; results are bit-identical either way
-                pair = c.in_channels >= 256 and c.out_channels % 256 == 0
+                # CTA pairs (cta_group::2: 256 channels x N pixels per pair, the patch shared) were faster on the pooled layers with
+                # >= 256 input channels in round 1; with tap-row reuse, the wave-aware plans and the balanced schedule the
+                # single-CTA tiles now win at every batch size (B = 256: conv32 1844 -> 1770 us, conv42 2048 -> 1986 us, step
+                # 10.78 -> 10.62 ms; B = 64: conv42 536 -> 476 us; profiles/r2_pair_vs_single.txt).  Results are bit-identical
+                # either way; `use_pairs` keeps the pair kernels reachable.
+                pair = self.use_pairs and c.in_channels >= 256 and c.out_channels % 256 == 0
                 h = ops.conv3x3_igemm_bf16(h, self._pack(self._names[2 * blk + 1], wk), c.bias, c.out_channels, L,
                                            pool=True, ref_layout=last, out_dtype=torch.float32, pair=pair, x3=x3)
                 if L is not None:

@@ -45,7 +45,11 @@ for name, T, F, Cin, Cout, pool, ref in layers:
     w = torch.randn(Cout, Cin, 3, 3, device='cuda', generator=g) * (2.0 / (9 * Cin)) ** 0.5
     wp = ops.pack_conv_weight_bf16(w); bias = torch.zeros(Cout, device='cuda')
     od = torch.float32 if ref else torch.bfloat16
-    us = timed(lambda: ops.conv3x3_igemm_bf16(x, wp, bias, Cout, pool=pool, ref_layout=ref, out_dtype=od)); total += us
+    pair = pool and Cin >= 256 and Cout % 256 == 0            # what CNNs.py asks for (split-K launches ignore it)
+    us = timed(lambda: ops.conv3x3_igemm_bf16(x, wp, bias, Cout, pool=pool, ref_layout=ref, out_dtype=od, pair=pair)); total += us
+    if pair:
+        us0 = timed(lambda: ops.conv3x3_igemm_bf16(x, wp, bias, Cout, pool=pool, ref_layout=ref, out_dtype=od, pair=False))
+        print(f'        (without CTA pairs {us0:7.2f} us)')
     fl = 2.0 * B * T * F * Cout * 9 * Cin
     print(f'{name}  {us:7.2f} us   floor {fl / 1.4e15 * 1e6:5.2f} us   weights {wp.numel() * 2 / 1e6:5.1f} MB')
 print(f'sum of conv kernels {total:.1f} us')
