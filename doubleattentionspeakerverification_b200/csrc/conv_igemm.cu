@@ -952,6 +952,7 @@ struct ConvKey {
     int B, T, F, Cin, Cout, flags, y_dtype, dgrad, dev;   // flags include the operand-format bits
     int env_reuse, env_pair, env_sb, ragged;   // ragged: lengths given (the plan then prefers low tiles)
     int env_nosplit;                           // DASV_CONV_NOSPLITK=1: never split along K (bit-identical results at every batch size)
+    int env_split;                             // DASV_CONV_SPLITK=n: force this split factor where the launch may split (tuning)
     char env_plan[16];
 };
 struct ConvEntry {
@@ -1037,16 +1038,19 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     int splitk = 1, kpc = Kc / kConvKC;
     if (reuse && !x3 && !fused && !k.ragged && (flags & 1) && !k.env_plan[0] && Cout % 4 == 0 && !k.env_nosplit && pl.N != 0) {
         const int kch = Kc / kConvKC;
-        double best = pl.cost;
+        // the cheapest split by the model (+ its finishing pass), taken when it beats the unsplit launch (single-CTA tiles) by 10 %;
+        // threshold and the per-split term fitted to scripts/ubench/splitk_sweep.py (B = 1..8, profiles/r2_splitk_sweep.txt)
+        const ConvPlan base = pair ? conv_plan(B, T, F, Kc, Cout, pool, 2, false, sms, false, nmax) : pl;
+        double best = 0.9 * (base.N ? (base.cost < pl.cost ? base.cost : pl.cost) : pl.cost);
         for (int sreq = 2; sreq <= 16 && sreq <= kch; sreq *= 2) {
             const int kp = (kch + sreq - 1) / sreq, seff = (kch + kp - 1) / kp;
-            if (seff < 2) continue;
+            if (seff < 2 || (k.env_split > 1 && seff != k.env_split)) continue;
             ConvPlan ps = conv_plan(B, T, F, Kc, Cout, pool, 2, false, sms, false, nmax, 1 << 30, seff);
             if (ps.N == 0) continue;
             // finishing pass: the partials are written and read once (L2-resident at these sizes), ~64 B/clk per SM, + a launch
-            const double fin = 4000.0 + 2.0 * seff * static_cast<double>(B) * T * F * Cout * 4.0 / (64.0 * sms);
+            const double fin = 4000.0 + 500.0 * seff + 2.0 * seff * static_cast<double>(B) * T * F * Cout * 4.0 / (64.0 * sms);
             if (static_cast<double>(seff) * B * T * F * Cout >= 2147483648.0) continue;   // the raw epilogue indexes the workspace with 32 bits
-            if (ps.cost + fin < 0.8 * best) { best = ps.cost + fin; pl = ps; splitk = seff; kpc = kp; pair = 0; }
+            if (ps.cost + fin < best || (k.env_split > 1 && splitk == 1)) { best = ps.cost + fin; pl = ps; splitk = seff; kpc = kp; pair = 0; }
         }
     }
     if (pl.N == 0) { set_error("conv3x3_igemm_bf16: no patch shape for T=%d F=%d", T, F); return 1; }
@@ -1174,6 +1178,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     if (cudaGetDevice(&k.dev) != cudaSuccess) { set_error("conv3x3_igemm_bf16: no current device"); cudaGetLastError(); return 1; }
     k.env_reuse = 1; k.env_pair = -1; k.env_sb = 0; k.ragged = lengths != nullptr;
     if (const char* e = getenv("DASV_CONV_NOSPLITK")) k.env_nosplit = atoi(e) != 0;
+    if (const char* e = getenv("DASV_CONV_SPLITK")) k.env_split = atoi(e);
     if (const char* e = getenv("DASV_CONV_REUSE")) k.env_reuse = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_PAIR")) k.env_pair = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_SB")) k.env_sb = atoi(e);

@@ -246,7 +246,7 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
             out_dtype = x.dtype
         y = torch.empty(shape, device=x.device, dtype=out_dtype if ref_layout else x.dtype)
         L = _lib.lib()
-        key = (_dtype_code(y, 'y'), flags, lengths is not None, B, T, Fq, Cin, Cout, x.device.index, os.environ.get('DASV_CONV_NOSPLITK'))
+        key = (_dtype_code(y, 'y'), flags, lengths is not None, B, T, Fq, Cin, Cout, x.device.index, os.environ.get('DASV_CONV_NOSPLITK'), os.environ.get('DASV_CONV_SPLITK'))
         nws = _conv_ws_bytes.get(key)
         if nws is None:                                      # > 0 only for small batches, which run split along K
             nws = _conv_ws_bytes[key] = int(L.dasv_conv3x3_igemm_workspace_bytes(key[0], flags, int(key[2]), B, T, Fq, Cin, Cout))
