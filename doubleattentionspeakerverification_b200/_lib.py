@@ -22,6 +22,7 @@ SIGNATURES = {
     'dasv_dmha_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'dasv_attention_fwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'dasv_conv11_direct': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'dasv_conv11_direct_lazy': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'dasv_pack_conv_weight_f32': (_i, [_vp, _vp, _i, _i, _vp]),
     'dasv_packed_conv_weight_bf16_elems': (_sz, [_i, _i]),
     'dasv_pack_conv_weight_bf16': (_i, [_vp, _vp, _i, _i, _vp]),

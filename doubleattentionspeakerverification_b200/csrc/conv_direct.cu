@@ -19,13 +19,14 @@ constexpr int kC11Rows = 8;            // frames per CTA when the launch is smal
 template <int OUT>      // 0 = f32, 1 = bf16, 2 = f16 output (the C ABI's dtype codes); 3 = split bf16 [hi(Cout) | lo(Cout)] per pixel
 __global__ void __launch_bounds__(256) conv11_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const int32_t* __restrict__ lengths,
-                                                           void* __restrict__ y, int B, int T, int F, int Cout, int R) {
+                                                           void* __restrict__ y, int B, int T, int F, int Cout, int R, int lazy) {
     extern __shared__ float x_sm[];       // [R + 2][F + 2], zero halo (R = frames per CTA)
     griddep_launch();                     // the next kernel of the stream may start its prologue
     griddep_wait();                       // x and the buffer behind y belong to earlier work of the stream
     const int chunks = (T + R - 1) / R;
     const int b = blockIdx.x / chunks, t0 = (blockIdx.x - b * chunks) * R;
     const int L = lengths ? min(max(lengths[b], 0), T) : T;
+    if (lazy && t0 > L) return;           // lazy masking: of the rows >= L the next layer reads row L only (its bottom halo)
     const int rows = min(R, T - t0);
     const int CG = Cout / 8;
     const int PL = 256 / CG;                                  // pixel lanes (CG <= 256 checked by the host)
@@ -289,8 +290,8 @@ __global__ void maxpool2x2_bf16x8_kernel(const uint4* __restrict__ x, uint4* __r
 
 using namespace dasv;
 
-extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* bias, const int32_t* lengths,
-                                  void* y, int y_dtype, int B, int T, int F, int Cout, void* stream) {
+static int conv11_launch(const float* x, const float* w, const float* bias, const int32_t* lengths,
+                         void* y, int y_dtype, int B, int T, int F, int Cout, void* stream, int lazy) {
     if (!x || !w || !bias || !y) { set_error("conv11_direct: null argument"); return 1; }
     if (Cout % 8 != 0 || Cout <= 0) { set_error("conv11_direct: Cout=%d must be a positive multiple of 8", Cout); return 1; }
     if (y_dtype < 0 || y_dtype > 3) { set_error("conv11_direct: bad dtype %d", y_dtype); return 1; }
@@ -312,12 +313,24 @@ extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* b
     const unsigned grid = static_cast<unsigned>(B) * chunks;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (y_dtype == 1) e = launch_pdl(conv11_direct_kernel<1>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R);
-    else if (y_dtype == 2) e = launch_pdl(conv11_direct_kernel<2>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R);
-    else if (y_dtype == 3) e = launch_pdl(conv11_direct_kernel<3>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R);
-    else e = launch_pdl(conv11_direct_kernel<0>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R);
+    if (y_dtype == 1) e = launch_pdl(conv11_direct_kernel<1>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R, lazy);
+    else if (y_dtype == 2) e = launch_pdl(conv11_direct_kernel<2>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R, lazy);
+    else if (y_dtype == 3) e = launch_pdl(conv11_direct_kernel<3>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R, lazy);
+    else e = launch_pdl(conv11_direct_kernel<0>, dim3(grid), dim3(256), smem, s, x, w, bias, lengths, y, B, T, F, Cout, R, lazy);
     if (e != cudaSuccess) { set_error("conv11_direct: launch failed: %s", cudaGetErrorString(e)); return 1; }
     return check_launch("conv11_direct");
+}
+
+extern "C" int dasv_conv11_direct(const float* x, const float* w, const float* bias, const int32_t* lengths,
+                                  void* y, int y_dtype, int B, int T, int F, int Cout, void* stream) {
+    return conv11_launch(x, w, bias, lengths, y, y_dtype, B, T, F, Cout, stream, 0);
+}
+
+// The same layer for pipelines whose consumers read, of the rows at or beyond an utterance's length L, only row L (the 3x3
+// kernels that follow: DASV_CONV_LAZY_MASK): rows > L of y may be left unwritten.  Rows < L and row L are as above.
+extern "C" int dasv_conv11_direct_lazy(const float* x, const float* w, const float* bias, const int32_t* lengths,
+                                       void* y, int y_dtype, int B, int T, int F, int Cout, void* stream) {
+    return conv11_launch(x, w, bias, lengths, y, y_dtype, B, T, F, Cout, stream, lengths != nullptr);
 }
 
 extern "C" int dasv_pack_conv_weight_f32(const float* w, float* packed, int Cout, int Cin, void* stream) {

@@ -69,6 +69,7 @@ struct ConvParams {
     // applies ReLU / pool / format.  kpc = K slices per split.
     int splitk, kpc;
     float* ws;
+    int lazy_mask;           // DASV_CONV_LAZY_MASK: all-masked tiles are only zero-filled where the next layer reads them (see conv_tile_needs_zeros)
     int balanced;            // ragged batches: tiles with valid frames are compacted through a per-CTA prefix table so that every
                              // CTA gets the same number of them (and of the all-masked tiles, which only store zeros)
     unsigned long long* trace;   // debugging aid (dasv_debug_conv_trace): per CTA 8 x globaltimer stamps, or nullptr
@@ -104,6 +105,20 @@ DASV_DEVICE bool conv_tile_masked(const ConvParams& p, const ConvTile& c) {
     for (int bb = 0; bb < p.BB; ++bb)
         if (conv_len(p, c.b0 + bb) > c.t0) return false;
     return true;
+}
+
+// Lazy masking (inference pipelines): the next layer reads, of the rows at or beyond an utterance's length L, only row L
+// (the bottom halo of its last valid row; after a 2x2 ceil pool: row 2*ceil(L/2) of this layer, i.e. pooled row ceil(L/2)).
+// Whatever lies further down only feeds output rows that are masked themselves.  A tile that straddles L zeroes its rows
+// >= L anyway; an ALL-masked tile therefore needs zeros only if that one row is its first row -- otherwise it is skipped
+// and the memory behind it stays unwritten.
+DASV_DEVICE bool conv_tile_needs_zeros(const ConvParams& p, const ConvTile& c) {
+    if (!p.lazy_mask) return true;
+    for (int bb = 0; bb < p.BB; ++bb) {
+        const int L = conv_len(p, c.b0 + bb);
+        if (c.b0 + bb < p.B && (p.pool ? ((L + 1) & ~1) : L) == c.t0) return true;
+    }
+    return false;
 }
 
 // ---- balanced schedule for ragged batches.  A group = the BB utterances of one patch column; its first vt t-tiles
@@ -538,6 +553,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int tile = tile0; tile < (pass == 0 ? sched.n_pass0 : sched.n_pass1); tile += tile_step) {
             bool masked;
             const ConvTile c = conv_tile_at(p, sched, tile, pass, n_mt_eff, static_cast<int>(rank), masked);
+            if (masked && !conv_tile_needs_zeros(p, c)) continue;           // lazy masking: nobody reads this tile
             const int n = c.m * kConvTileM + ch;
             const bool n_ok = n < Cout;
             const int ot0 = p.pool ? (c.t0 >> 1) : c.t0, of0 = p.pool ? (c.f0 >> 1) : c.f0;
@@ -1091,6 +1107,7 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     p.kcx_wrap = x3 ? 2 * Cin / kConvKC : 0x7fffffff;
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (k.y_dtype == 0);
     p.relu = (flags & 1) ? 1 : 0;
+    p.lazy_mask = (flags & 256) ? 1 : 0;
     p.w_f16 = (flags & 16) ? 1 : 0; p.x_f16 = (flags & 32) ? 1 : 0;
     p.balanced = (k.ragged && p.n_bt <= kConvMaxGroups && !getenv("DASV_CONV_UNBALANCED")) ? 1 : 0;
     p.splitk = splitk; p.kpc = kpc;

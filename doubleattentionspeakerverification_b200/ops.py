@@ -12,6 +12,7 @@ from . import _lib
 F32, BF16, F16 = 0, 1, 2
 CONV_RELU, CONV_POOL, CONV_REF_LAYOUT, CONV_PAIR, CONV_W_F16, CONV_X_F16, CONV_X3 = 1, 2, 4, 8, 16, 32, 64
 SPLIT_BF16 = 3
+CONV_LAZY_MASK = 256
 
 
 def _dev(t, name):
@@ -164,9 +165,10 @@ def pack_conv_weight_bf16(w, dtype=torch.bfloat16):
     return p
 
 
-def conv11_direct(x, w, bias, lengths=None, out_dtype=torch.float32, split=False):
+def conv11_direct(x, w, bias, lengths=None, out_dtype=torch.float32, split=False, lazy_mask=False):
     """x [B,T,F] f32 -> relu(conv3x3(x) + bias) as NHWC [B,T,F,Cout]; ``split=True``: [B,T,F,2*Cout] bf16 holding every fp32
-    value as hi = bf16(v) (channel c) and lo = bf16(v - hi) (channel Cout + c), the activation format of the fp32x3 mode."""
+    value as hi = bf16(v) (channel c) and lo = bf16(v - hi) (channel Cout + c), the activation format of the fp32x3 mode.
+    ``lazy_mask`` (with lengths): rows beyond row ``lengths[b]`` may stay unwritten (see ``conv3x3_igemm_bf16``)."""
     x = _f32(x, 'x')
     B, T, Fq = x.shape
     w, bias = _f32(w, 'w'), _f32(bias, 'bias')
@@ -174,7 +176,8 @@ def conv11_direct(x, w, bias, lengths=None, out_dtype=torch.float32, split=False
     with torch.cuda.device(x.device):
         lengths = _lengths(lengths, B, x.device)
         y = torch.empty((B, T, Fq, 2 * Cout if split else Cout), device=x.device, dtype=torch.bfloat16 if split else out_dtype)
-        rc = _lib.lib().dasv_conv11_direct(_p(x), _p(w), _p(bias), _p(lengths), _p(y), SPLIT_BF16 if split else _dtype_code(y, 'y'), B, T, Fq, Cout, _stream())
+        fn = _lib.lib().dasv_conv11_direct_lazy if (lazy_mask and lengths is not None) else _lib.lib().dasv_conv11_direct
+        rc = fn(_p(x), _p(w), _p(bias), _p(lengths), _p(y), SPLIT_BF16 if split else _dtype_code(y, 'y'), B, T, Fq, Cout, _stream())
         _lib.check(rc, 'dasv_conv11_direct')
     return y
 
@@ -218,9 +221,14 @@ def maxpool2x2(x, ref_layout=False, out_dtype=None):
     return y
 
 
-def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False, relu=True, x3=False):
+def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=False, out_dtype=torch.bfloat16, pair=False, relu=True, x3=False,
+                       lazy_mask=False):
     """tcgen05 implicit-GEMM conv3x3 + bias + ReLU (+ fused 2x2 ceil max-pool) on NHWC 16-bit activations (bf16 or fp16; the
-    output has the input's format) with bf16 or fp16 packed weights, fp32 accumulation."""
+    output has the input's format) with bf16 or fp16 packed weights, fp32 accumulation.
+
+    ``lazy_mask`` (with lengths, for pipelines that carry the lengths through every layer): of the output rows at or beyond
+    an utterance's length only the one the next 3x3 layer reads is guaranteed zero; tiles that lie wholly further down are
+    skipped and their memory stays unwritten (valid rows are unaffected: a 3x3 kernel never looks further than one row)."""
     _dev(x, 'x')
     if x.dtype not in (torch.bfloat16, torch.float16) or wp.dtype not in (torch.bfloat16, torch.float16):
         raise _lib.DasvError('conv3x3_igemm_bf16: x and wp must be bfloat16 or float16')
@@ -228,6 +236,7 @@ def conv3x3_igemm_bf16(x, wp, bias, Cout, lengths=None, pool=False, ref_layout=F
     B, T, Fq, Cin = x.shape
     flags = (CONV_RELU if relu else 0) | (CONV_POOL if pool else 0) | (CONV_REF_LAYOUT if ref_layout else 0) | (CONV_PAIR if pair else 0)
     flags |= (CONV_W_F16 if wp.dtype == torch.float16 else 0) | (CONV_X_F16 if x.dtype == torch.float16 else 0)
+    flags |= CONV_LAZY_MASK if (lazy_mask and lengths is not None) else 0
     if x3:                                                   # fp32x3 mode: x is [hi | lo] split bf16 (2 * Cin channels), so is an NHWC y
         if x.dtype != torch.bfloat16 or Cin % 2:
             raise _lib.DasvError('conv3x3_igemm_bf16: the fp32x3 mode takes split bf16 activations')

@@ -38,6 +38,9 @@ extern "C" {
 #define DASV_CONV_W_F16 16      /* wp was packed as fp16 (dasv_pack_conv_weight_16 with DASV_F16) */
 #define DASV_CONV_X_F16 32      /* x (and an NHWC y) are fp16 instead of bf16; fp16 stores saturate at +-65504 */
 #define DASV_CONV_X3 64         /* fp32x3 mode: x is [B,T,F,2*Cin] split bf16, wp from dasv_pack_conv_weight_x3, an NHWC y is [..,2*Cout] split bf16 */
+#define DASV_CONV_LAZY_MASK 256 /* with lengths: of the rows at or beyond an utterance's length L, only the one the NEXT 3x3 layer reads is
+                                   guaranteed zero (row L; with POOL: pooled row ceil(L/2)); all-masked tiles further down are skipped and
+                                   the memory behind them is left unwritten.  For pipelines that carry `lengths` through every layer. */
 
 int dasv_abi_version(void);
 const char* dasv_last_error(void);
@@ -98,6 +101,10 @@ int dasv_attention_fwd(const void* x, int x_dtype, const int32_t* lengths, const
  * x [B,T,F] f32, w [Cout,1,3,3] f32 (reference layout), bias [Cout] f32, y [B,T,F,Cout] (y_dtype). */
 int dasv_conv11_direct(const float* x, const float* w, const float* bias, const int32_t* lengths,
                        void* y, int y_dtype, int B, int T, int F, int Cout, void* stream);
+/* The same layer with LAZY masking (inference pipelines, see DASV_CONV_LAZY_MASK): rows t > lengths[b] of y may be left
+ * unwritten; rows < lengths[b] and the zero row t = lengths[b] are as above. */
+int dasv_conv11_direct_lazy(const float* x, const float* w, const float* bias, const int32_t* lengths,
+                            void* y, int y_dtype, int B, int T, int F, int Cout, void* stream);
 
 /* Weight re-packing (done once per module, cached by the caller):
  *   f32 path : w [Cout,Cin,3,3] f32 -> [9][Cin][Cout] f32

@@ -285,3 +285,45 @@ def test_conv11_and_pool_kernels():
     assert max_rel(p.cpu().numpy(), pp) == 0.0
     pr = ops.maxpool2x2(y, ref_layout=True)
     assert max_rel(pr.cpu().numpy(), pp.transpose(0, 1, 3, 2).reshape(2, 5, -1)) == 0.0
+
+
+@pytest.mark.parametrize('T,F,Cin,Cout,pool', [(64, 20, 128, 128, True), (64, 20, 128, 256, False), (50, 10, 512, 512, True), (37, 8, 64, 128, False)])
+def test_lazy_masking_leaves_valid_rows_and_the_halo_row_intact(T, F, Cin, Cout, pool):
+    """DASV_CONV_LAZY_MASK: tiles wholly beyond an utterance's length are skipped.  Rows below the length are bit-identical to the
+    eager-masking result and the one row the next 3x3 layer reads beyond them is zero -- also when the rows further down
+    of the INPUT hold garbage (NaN here), which is what a lazily masked previous layer leaves behind."""
+    lens = np.array([T, T - 1, (3 * T) // 4, T // 2, T // 2 - 1, 13, 12, 2, 1, 0], np.int32)
+    B = len(lens)
+    rs = np.random.RandomState(T + Cin)
+    x = np.maximum(rs.standard_normal((B, T, F, Cin)), 0).astype(np.float32)
+    w = (rs.standard_normal((Cout, Cin, 3, 3)) * np.sqrt(2.0 / (9 * Cin))).astype(np.float32)
+    bias = (rs.standard_normal((Cout,)) * 0.1).astype(np.float32)
+    x_clean, x_dirty = x.copy(), x.copy()
+    for b, L in enumerate(lens):
+        x_clean[b, L:] = 0
+        x_dirty[b, L:] = 0
+        x_dirty[b, L + 1:] = np.nan                               # row L is the zero halo; anything below is garbage
+    wp, bd, Ld = ops.pack_conv_weight_bf16(dev(w)), dev(bias), dev(lens)
+    want = ops.conv3x3_igemm_bf16(dev(x_clean, torch.bfloat16), wp, bd, Cout, Ld, pool=pool)
+    got = ops.conv3x3_igemm_bf16(dev(x_dirty, torch.bfloat16), wp, bd, Cout, Ld, pool=pool, lazy_mask=True)
+    for b, L in enumerate(lens):
+        Lo = (L + 1) // 2 if pool else L
+        assert torch.equal(got[b, :Lo], want[b, :Lo]), b
+        if Lo < got.shape[1]:
+            assert not got[b, Lo].float().abs().max().item() > 0, b   # the row the next layer's last valid row looks at
+        assert torch.isfinite(got[b, :min(Lo + 1, got.shape[1])].float()).all()
+
+
+def test_lazy_masking_first_layer():
+    rs = np.random.RandomState(5)
+    T, F = 70, 80
+    lens = np.array([70, 69, 33, 32, 31, 8, 1, 0], np.int32)
+    x = rs.standard_normal((len(lens), T, F)).astype(np.float32)
+    w = rs.standard_normal((128, 1, 3, 3)).astype(np.float32) * 0.3
+    bias = rs.standard_normal((128,)).astype(np.float32) * 0.1
+    want = ops.conv11_direct(dev(x), dev(w), dev(bias), dev(lens), out_dtype=torch.bfloat16)
+    got = ops.conv11_direct(dev(x), dev(w), dev(bias), dev(lens), out_dtype=torch.bfloat16, lazy_mask=True)
+    for b, L in enumerate(lens):
+        assert torch.equal(got[b, :L], want[b, :L])
+        if L < T:
+            assert not got[b, L].float().abs().max().item() > 0
