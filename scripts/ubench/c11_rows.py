@@ -1,5 +1,6 @@
+"""conv11 frames per CTA (DASV_C11_ROWS) at batch 1-8: one layer, 20 launches per graph."""
 import os, sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from doubleattentionspeakerverification_b200 import ops
 g = torch.Generator(device='cuda').manual_seed(0)
 for B in (1, 2, 4, 8):

@@ -1,5 +1,6 @@
+"""getEmbedding at batch 1-8 with and without conv11 fused into conv12 (front_end.fuse_first)."""
 import os, sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from doubleattentionspeakerverification_b200 import model, synth
 cfg = synth.example_config(); cfg.precision = 'bf16'
 net = synth.load_state_dict(model.SpeakerClassifier(cfg, 'cuda'), synth.make_state_dict(cfg, 1234)).cuda().eval()
