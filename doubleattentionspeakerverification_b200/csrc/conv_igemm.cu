@@ -69,6 +69,7 @@ struct ConvParams {
     // applies ReLU / pool / format.  kpc = K slices per split.
     int splitk, kpc;
     float* ws;
+    int wide_epi;            // pooled epilogue: 16- / 8-column TMEM loads where a pooled row of the patch allows it
     int lazy_mask;           // DASV_CONV_LAZY_MASK: all-masked tiles are only zero-filled where the next layer reads them (see conv_tile_needs_zeros)
     int balanced;            // ragged batches: tiles with valid frames are compacted through a per-CTA prefix table so that every
                              // CTA gets the same number of them (and of the all-masked tiles, which only store zeros)
@@ -182,6 +183,12 @@ DASV_DEVICE void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
+}
+DASV_DEVICE void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 DASV_DEVICE void tmem_ld_x1(uint32_t taddr, uint32_t& r0) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
@@ -693,6 +700,9 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     // phase 1: this thread's channel of `cnt` output pixels -> staging[pixel][ch]
                     uint16_t* dst = reinterpret_cast<uint16_t*>(buf) + ch;
                     if (!p.pool) {
+                        // (Tried: both 16-column loads of a chunk issued before one wait -- conv21, the layer whose epilogue is
+                        //  as long as its K = 1152 main loop, went from 1228 to 1128 TFLOP/s: the two warps of a scheduler then
+                        //  wait and convert in lockstep instead of covering each other.)
                         // output o of utterance bb sits in accumulator column o + bb * gap_cols
 #pragma unroll
                         for (int g16 = 0; g16 < kConvEpiChunk / 16; ++g16) {
@@ -739,6 +749,46 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         int rem = o0 - bb * OPP;
                         int tp = __float2int_rz((static_cast<float>(rem) + 0.5f) * inv_obf), fp = rem - tp * OBF;
                         int Lcur = conv_len(p, c.b0 + bb);
+                        // Wide path: when a pooled row of the patch holds a multiple of 8 (4) outputs, the two accumulator rows of
+                        // 8 (4) consecutive windows are 16 (8) consecutive columns each -- two TMEM loads instead of sixteen
+                        // (eight), and one index decomposition per group.  (Short-K layers are epilogue-bound: conv12.)
+                        constexpr bool kWide = ACT != 3 && !FUSE11;      // (those variants have no registers to spare)
+                        const int wide = (!kWide || !p.wide_epi) ? 0 : ((OBF & 7) == 0 ? 8 : ((OBF & 3) == 0 ? 4 : 0));
+                        if (kWide && wide == 8) {
+                            for (int j0 = 0; j0 < cnt; j0 += 8) {       // o0 and cnt are multiples of 8 here (OPP is)
+                                const uint32_t col = tcol + static_cast<uint32_t>(bb * UC + 2 * tp * BF + 2 * fp);
+                                const bool r1 = (c.t0 + 2 * tp + 1) < Lcur;
+                                uint32_t ra[16], rb[16];
+                                tmem_ld_x16(col, ra);
+                                tmem_ld_x16(col + BF, rb);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    float m = fmaxf(__uint_as_float(ra[2 * u]), __uint_as_float(ra[2 * u + 1]));
+                                    if (r1) m = fmaxf(m, fmaxf(__uint_as_float(rb[2 * u]), __uint_as_float(rb[2 * u + 1])));
+                                    dst[(j0 + u) * kConvTileM] = cvt_out(fmaxf(m + bias, 0.f), part);
+                                }
+                                fp += 8;
+                                if (fp == OBF) { fp = 0; if (++tp == OBT) { tp = 0; ++bb; Lcur = conv_len(p, c.b0 + bb); } }
+                            }
+                        } else if (kWide && wide == 4) {
+                            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                                const uint32_t col = tcol + static_cast<uint32_t>(bb * UC + 2 * tp * BF + 2 * fp);
+                                const bool r1 = (c.t0 + 2 * tp + 1) < Lcur;
+                                uint32_t ra[8], rb[8];
+                                tmem_ld_x8(col, ra);
+                                tmem_ld_x8(col + BF, rb);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    float m = fmaxf(__uint_as_float(ra[2 * u]), __uint_as_float(ra[2 * u + 1]));
+                                    if (r1) m = fmaxf(m, fmaxf(__uint_as_float(rb[2 * u]), __uint_as_float(rb[2 * u + 1])));
+                                    dst[(j0 + u) * kConvTileM] = cvt_out(fmaxf(m + bias, 0.f), part);
+                                }
+                                fp += 4;
+                                if (fp == OBF) { fp = 0; if (++tp == OBT) { tp = 0; ++bb; Lcur = conv_len(p, c.b0 + bb); } }
+                            }
+                        } else
                         for (int j0 = 0; j0 < cnt; j0 += 4) {
                             uint32_t v[4][4], v2[ACT == 3 ? 4 : 1][4];
                             bool r1[4];
@@ -968,6 +1018,7 @@ struct ConvKey {
     int B, T, F, Cin, Cout, flags, y_dtype, dgrad, dev;   // flags include the operand-format bits
     int env_reuse, env_pair, env_sb, ragged;   // ragged: lengths given (the plan then prefers low tiles)
     int env_nosplit;                           // DASV_CONV_NOSPLITK=1: never split along K (bit-identical results at every batch size)
+    int env_nowide;                            // DASV_CONV_NOWIDE=1: pooled epilogue with the narrow TMEM loads (A/B runs)
     int env_split;                             // DASV_CONV_SPLITK=n: force this split factor where the launch may split (tuning)
     char env_plan[16];
 };
@@ -1108,6 +1159,7 @@ static int conv_build_entry(ConvEntry& en, const ConvKey& k) {
     p.pool = pool; p.ref_layout = ref; p.y_f32 = (k.y_dtype == 0);
     p.relu = (flags & 1) ? 1 : 0;
     p.lazy_mask = (flags & 256) ? 1 : 0;
+    p.wide_epi = k.env_nowide ? 0 : 1;
     p.w_f16 = (flags & 16) ? 1 : 0; p.x_f16 = (flags & 32) ? 1 : 0;
     p.balanced = (k.ragged && p.n_bt <= kConvMaxGroups && !getenv("DASV_CONV_UNBALANCED")) ? 1 : 0;
     p.splitk = splitk; p.kpc = kpc;
@@ -1196,6 +1248,7 @@ static int conv_igemm_launch(const void* x, const void* wp, const float* bias, c
     k.env_reuse = 1; k.env_pair = -1; k.env_sb = 0; k.ragged = lengths != nullptr;
     if (const char* e = getenv("DASV_CONV_NOSPLITK")) k.env_nosplit = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_SPLITK")) k.env_split = atoi(e);
+    if (const char* e = getenv("DASV_CONV_NOWIDE")) k.env_nowide = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_REUSE")) k.env_reuse = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_PAIR")) k.env_pair = atoi(e) != 0;
     if (const char* e = getenv("DASV_CONV_SB")) k.env_sb = atoi(e);
