@@ -244,7 +244,9 @@ def extract_local_packed(embed_fn, packed, indices, device, max_frames=256 * 400
         b, st = batches[k], starts[k]
         with (torch.cuda.stream(copy_stream) if cuda else _NullCtx()):
             frames = torch.empty((int(st[-1]), Fdim), device=dev, dtype=torch.float32)
-            if cuda and packed.data.is_pinned():
+            if int(st[-1]) == 0:
+                pass                                             # nothing to copy (empty utterances only)
+            elif cuda and packed.data.is_pinned():
                 ops.h2d_segments(frames, packed.data, packed.offsets[indices[b]] * row_bytes, st[:-1] * row_bytes, L[b] * row_bytes)
             else:
                 for j, i in enumerate(indices[b]):
